@@ -1,0 +1,111 @@
+"""GPU bring-up probe: runs the tcgen05 self-test kernel over a table of operand-layout /
+descriptor hypotheses and prints which ones reproduce A @ B.T exactly.  Each case runs in its own
+subprocess so a trapped kernel cannot poison the next one.
+
+usage: python tools/umma_probe.py            (on a B200)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {
+    # name: (mode, n, k, variant)
+    "kmajor_n256_k128": ("k", 256, 128, "std"),
+    "kmajor_n16_k64": ("k", 16, 64, "std"),
+    "kmajor_n64_k64_lbo0": ("k", 64, 64, "lbo0"),
+    "mnmajor_n256_k128": ("mn", 256, 128, "std"),
+    "mnmajor_n64_k64": ("mn", 64, 64, "std"),
+    "mnmajor_n256_k128_swapped": ("mn", 256, 128, "swap"),
+    "amn_bk_n128_k64": ("amn_bk", 128, 64, "std"),
+}
+
+
+def run_case(name):
+    import ctypes
+    import numpy as np
+    import torch
+    import spnerf_b200
+    from spnerf_b200 import _cabi, slab
+
+    mode, n, k, variant = CASES[name]
+    rng = np.random.default_rng(7)
+    a = rng.integers(-4, 5, size=(128, k)).astype(np.float16)
+    b = rng.integers(-4, 5, size=(n, k)).astype(np.float16)
+    want = a.astype(np.float32) @ b.astype(np.float32).T
+    args = _cabi.UmmaSelftest()
+    ksteps = k // 16
+
+    def kmajor(x, rows):
+        img = slab.pack_matrix(x)
+        offs = [(s // 4) * rows * 128 + (s % 4) * 32 for s in range(ksteps)]
+        lbo = 0 if variant == "lbo0" else 16
+        return img, offs, slab.smem_desc_template(lbo, 1024)
+
+    def mnmajor(x):
+        # x: (rows=M or N, K) -> store transposed: slabs of (K rows, 64 cols of M/N)
+        xt = np.ascontiguousarray(x.T)                    # (K, rows)
+        img = slab.pack_matrix(xt)
+        offs = [s * 2048 for s in range(ksteps)]
+        slab_bytes = k * 128
+        if variant == "swap":
+            return img, offs, slab.smem_desc_template(1024, slab_bytes)
+        return img, offs, slab.smem_desc_template(slab_bytes, 1024)
+
+    if mode == "k":
+        a_img, a_off, a_t = kmajor(a, 128)
+        b_img, b_off, b_t = kmajor(b, n)
+        idesc = slab.idesc_f16(128, n, 0, 0)
+    elif mode == "mn":
+        a_img, a_off, a_t = mnmajor(a)
+        b_img, b_off, b_t = mnmajor(b)
+        idesc = slab.idesc_f16(128, n, 1, 1)
+    else:
+        a_img, a_off, a_t = mnmajor(a)
+        b_img, b_off, b_t = kmajor(b, n)
+        idesc = slab.idesc_f16(128, n, 1, 0)
+
+    dev = torch.device("cuda:0")
+    ta = torch.from_numpy(a_img.copy()).to(dev)
+    tb = torch.from_numpy(b_img.copy()).to(dev)
+    td = torch.full((128, n), float("nan"), device=dev)
+    args.a_img, args.b_img, args.d_out = ta.data_ptr(), tb.data_ptr(), td.data_ptr()
+    args.a_bytes, args.b_bytes = ta.numel(), tb.numel()
+    args.n, args.ksteps, args.idesc = n, ksteps, idesc
+    args.a_desc_template, args.b_desc_template = a_t, b_t
+    for i in range(ksteps):
+        args.a_off[i] = a_off[i]
+        args.b_off[i] = b_off[i]
+    rc = _cabi.lib().spnerf_selftest_umma(ctypes.byref(args), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = td.cpu().numpy()
+    err = float(np.nanmax(np.abs(got - want))) if not np.isnan(got).all() else float("nan")
+    ok = bool(rc == 0 and np.array_equal(got, want))
+    print(json.dumps({"case": name, "rc": rc, "ok": ok, "max_abs_err": err,
+                      "nan": int(np.isnan(got).sum()), "watchdog": int(_cabi.lib().spnerf_watchdog_code())}))
+    return 0 if ok else 1
+
+
+def main():
+    if len(sys.argv) > 1:
+        sys.exit(run_case(sys.argv[1]))
+    results = {}
+    for name in CASES:
+        try:
+            p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=120)
+            line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            results[name] = json.loads(line[-1]) if line else {"ok": False, "rc": p.returncode,
+                                                               "stderr": p.stderr[-400:]}
+        except subprocess.TimeoutExpired:
+            results[name] = {"ok": False, "timeout": True}
+        print(name, results[name], flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "umma_probe.json"), "w") as f:
+        json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
