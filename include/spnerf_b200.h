@@ -61,6 +61,82 @@ typedef struct SpnerfUmmaSelftest {
 } SpnerfUmmaSelftest;
 int spnerf_selftest_umma(const SpnerfUmmaSelftest* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Point network (replaces models/spnerf.py:162-369 SPNeRF.__init__/forward as executed through
+ * models/spnerf.py:83-113, i.e. the chunked per-point MLP call of inference()).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct SpnerfNetConfig {
+  int32_t feat;            /* fc_units; only 512 is built (modules/opt.py:43)                 */
+  int32_t layers;          /* fc_layers; only 8 (modules/opt.py:45)                           */
+  int32_t skip_layer;      /* 4 (models/spnerf.py:164 skips=[4])                              */
+  int32_t mapping;         /* 1: 10-frequency positional encoding (models/spnerf.py:5-37)     */
+  int32_t sem;             /* 1: label embedding input + semantic head                        */
+  int32_t num_sem_classes; /* C <= 8                                                          */
+  int32_t emb_dim;         /* C * s_embedding_factor; encoded input width must stay <= 64     */
+  int32_t beta;            /* 1: uncertainty head                                             */
+  int32_t t_dim;           /* t_embbeding_tau <= 8                                            */
+} SpnerfNetConfig;
+
+/* Parameter slots, in the reference's state_dict order. */
+enum {
+  SPNERF_P_SEM_EMB = 0,          /* semantic_embedding.weight (C+1, emb_dim)            */
+  SPNERF_P_FC_W0 = 1,            /* fc_net.{2i}.weight at 1+2i, .bias at 2+2i, i=0..7   */
+  SPNERF_P_SIGMA_W = 17, SPNERF_P_SIGMA_B = 18,
+  SPNERF_P_FEATS_W = 19, SPNERF_P_FEATS_B = 20,
+  SPNERF_P_SEM0_W = 21, SPNERF_P_SEM0_B = 22, SPNERF_P_SEM2_W = 23, SPNERF_P_SEM2_B = 24,
+  SPNERF_P_RGB0_W = 25, SPNERF_P_RGB0_B = 26, SPNERF_P_RGB2_W = 27, SPNERF_P_RGB2_B = 28,
+  SPNERF_P_SUN0_W = 29,          /* sun_v_net.{0,2,4,6}: weight at 29+2j, bias at 30+2j */
+  SPNERF_P_SKY0_W = 37, SPNERF_P_SKY0_B = 38, SPNERF_P_SKY2_W = 39, SPNERF_P_SKY2_B = 40,
+  SPNERF_P_BETA0_W = 41, SPNERF_P_BETA0_B = 42, SPNERF_P_BETA2_W = 43, SPNERF_P_BETA2_B = 44,
+  SPNERF_NUM_PARAMS = 45
+};
+
+typedef struct SpnerfNetSizes {
+  int64_t fwd_blob_bytes;      /* packed fp16 weight stream for the forward kernel          */
+  int64_t bwd_blob_bytes;      /* packed (transposed) stream for the backward-data kernel   */
+  int64_t small_floats;        /* fp32 block: biases, tiny last layers, embedding, sky net  */
+  int64_t steps_bytes;         /* per step table (forward and backward each)                */
+  int32_t fwd_steps, bwd_steps;
+  int32_t save_slabs_per_tile; /* x 16384 bytes x ceil(points/128) = activation save area   */
+  int32_t n_out;               /* columns of the network output row                         */
+  int32_t in_dim;
+  int32_t tile_points;         /* 128 */
+} SpnerfNetSizes;
+
+/* host only; no device work */
+int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* sizes_host);
+
+/* fp32 parameters -> packed operands.  params_host[k] is a device pointer (or NULL for absent
+ * heads).  Must be re-run after every parameter update. */
+int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* params_host, void* fwd_blob,
+                    void* bwd_blob, float* small, void* fwd_steps, void* bwd_steps, void* stream);
+
+/* sky_color(sun_dir) per ray (models/spnerf.py:355, 244-249; constant along a ray).
+ * sky (n_rays,3); hidden (n_rays,256) post-ReLU or NULL. */
+int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, const float* rays, int64_t n_rays,
+                   float* sky, float* hidden, void* stream);
+
+typedef struct SpnerfMlpFwd {
+  SpnerfNetConfig cfg;
+  const float* rays;      /* (n_rays, 11) */
+  const float* z;         /* (n_rays, n_samples) sample depths; points = origin + dir * z      */
+  const float* xyz;       /* optional (n_rays*n_samples, 3): used instead of rays/z if non-NULL */
+  const float* dir_override; /* optional (n_rays,3): march along this instead of rays[:,3:6]
+                                (solar-correction pass, modules/rendering.py:172)             */
+  const int64_t* labels;  /* (n_rays) or NULL; -100 = ignore (models/spnerf.py:310-315)        */
+  const float* t_emb;     /* (n_rays, t_dim) or NULL                                           */
+  const float* sky;       /* (n_rays, 3) from spnerf_sky_fwd                                   */
+  int64_t n_rays;
+  int32_t n_samples;
+  int32_t n_steps;
+  const void* blob;       /* fwd_blob */
+  const void* steps;      /* fwd_steps */
+  const float* small;
+  float* out;             /* (n_rays*n_samples, n_out) fp32, reference column order            */
+  void* saves;            /* activation save area or NULL (inference)                          */
+} SpnerfMlpFwd;
+int spnerf_mlp_fwd(const SpnerfMlpFwd* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

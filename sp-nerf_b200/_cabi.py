@@ -62,3 +62,73 @@ def check(rc, what):
         names = {1: "bad argument", 2: "unsupported configuration", 3: "workspace too small"}
         raise SpnerfError(f"{what}: {names.get(rc, rc)}")
     raise SpnerfError(f"{what}: CUDA error {-rc}")
+
+
+# ------------------------------------------------------------------------------------------------
+# point network
+# ------------------------------------------------------------------------------------------------
+NUM_PARAMS = 45
+
+# reference state_dict key -> parameter slot (include/spnerf_b200.h SPNERF_P_*)
+PARAM_SLOTS = {"semantic_embedding.weight": 0}
+for _i in range(8):
+    PARAM_SLOTS[f"fc_net.{2 * _i}.weight"] = 1 + 2 * _i
+    PARAM_SLOTS[f"fc_net.{2 * _i}.bias"] = 2 + 2 * _i
+PARAM_SLOTS.update({
+    "sigma_from_xyz.0.weight": 17, "sigma_from_xyz.0.bias": 18,
+    "feats_from_xyz.weight": 19, "feats_from_xyz.bias": 20,
+    "logit_from_label.0.weight": 21, "logit_from_label.0.bias": 22,
+    "logit_from_label.2.weight": 23, "logit_from_label.2.bias": 24,
+    "rgb_from_xyzdir.0.weight": 25, "rgb_from_xyzdir.0.bias": 26,
+    "rgb_from_xyzdir.2.weight": 27, "rgb_from_xyzdir.2.bias": 28,
+    "sky_color.0.weight": 37, "sky_color.0.bias": 38, "sky_color.2.weight": 39, "sky_color.2.bias": 40,
+    "beta_from_xyz.0.weight": 41, "beta_from_xyz.0.bias": 42,
+    "beta_from_xyz.2.weight": 43, "beta_from_xyz.2.bias": 44,
+})
+for _j in range(4):
+    PARAM_SLOTS[f"sun_v_net.{2 * _j}.weight"] = 29 + 2 * _j
+    PARAM_SLOTS[f"sun_v_net.{2 * _j}.bias"] = 30 + 2 * _j
+
+
+class NetConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("feat", "layers", "skip_layer", "mapping", "sem", "num_sem_classes", "emb_dim", "beta", "t_dim")]
+
+
+class NetSizes(ctypes.Structure):
+    _fields_ = [("fwd_blob_bytes", ctypes.c_int64), ("bwd_blob_bytes", ctypes.c_int64),
+                ("small_floats", ctypes.c_int64), ("steps_bytes", ctypes.c_int64),
+                ("fwd_steps", ctypes.c_int32), ("bwd_steps", ctypes.c_int32),
+                ("save_slabs_per_tile", ctypes.c_int32), ("n_out", ctypes.c_int32),
+                ("in_dim", ctypes.c_int32), ("tile_points", ctypes.c_int32)]
+
+
+class MlpFwd(ctypes.Structure):
+    _fields_ = [("cfg", NetConfig),
+                ("rays", ctypes.c_void_p), ("z", ctypes.c_void_p), ("xyz", ctypes.c_void_p),
+                ("dir_override", ctypes.c_void_p), ("labels", ctypes.c_void_p), ("t_emb", ctypes.c_void_p),
+                ("sky", ctypes.c_void_p),
+                ("n_rays", ctypes.c_int64), ("n_samples", ctypes.c_int32), ("n_steps", ctypes.c_int32),
+                ("blob", ctypes.c_void_p), ("steps", ctypes.c_void_p), ("small", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("saves", ctypes.c_void_p)]
+
+
+def _declare_net(L):
+    L.spnerf_net_sizes.restype = ctypes.c_int
+    L.spnerf_net_sizes.argtypes = [ctypes.POINTER(NetConfig), ctypes.POINTER(NetSizes)]
+    L.spnerf_net_pack.restype = ctypes.c_int
+    L.spnerf_net_pack.argtypes = [ctypes.POINTER(NetConfig), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.spnerf_sky_fwd.restype = ctypes.c_int
+    L.spnerf_sky_fwd.argtypes = [ctypes.c_void_p, ctypes.POINTER(NetConfig), ctypes.c_void_p, ctypes.c_int64,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.spnerf_mlp_fwd.restype = ctypes.c_int
+    L.spnerf_mlp_fwd.argtypes = [ctypes.POINTER(MlpFwd), ctypes.c_void_p]
+
+
+_declare_base = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_base(L)
+    _declare_net(L)

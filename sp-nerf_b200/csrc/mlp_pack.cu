@@ -1,0 +1,353 @@
+// Host-side plan builder and the device pack kernel for the fused point-network kernels.
+//
+// The forward / backward-data kernels consume the weights as a linear stream of pre-swizzled fp16
+// B tiles ("items"), in exactly the order the MMA issuer walks them, so the weight producer is a
+// sequence of 1-D bulk copies.  This file derives that order from the layer graph of
+// models/spnerf.py:202-264 and converts the fp32 parameters into it.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <vector>
+#include <cstring>
+#include "net_plan.h"
+#include "sm100.cuh"
+
+using namespace net;
+
+namespace {
+
+struct PackItem {
+  const float* src;   // W, row-major (rows x ld)
+  int ld;
+  int rows, cols;     // valid extent of W
+  int row0, col0;     // tile row i / tile col k  <->  W[row0+i][col0+k]  (or W[row0+k][col0+i] if transposed)
+  int transpose;
+  int mode;           // 0: fp16(w)   1: fp16(w - fp16(w))
+  int n;              // tile rows to fill (starting at dst_row0)
+  int dst_row0;
+  uint32_t dst_off16;
+};
+
+__global__ void pack_kernel(const PackItem* __restrict__ items, uint8_t* __restrict__ blob) {
+  const PackItem it = items[blockIdx.x];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < it.n * 8; t += gridDim.y * blockDim.x) {
+    const int r = t >> 3, c = t & 7;   // tile row, 16-byte chunk
+    __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c * 8 + e;
+      const int wr = it.transpose ? it.row0 + k : it.row0 + r;
+      const int wc = it.transpose ? it.col0 + r : it.col0 + k;
+      float w = 0.f;
+      if (wr < it.rows && wc < it.cols) w = it.src[(size_t)wr * it.ld + wc];
+      __half hi = __float2half_rn(w);
+      h[e] = it.mode == 0 ? hi : __float2half_rn(w - __half2float(hi));
+    }
+    uint8_t* dst = blob + (size_t)it.dst_off16 * 16 + sm100::slab_chunk_offset(it.dst_row0 + r, c);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+struct CopyItem {
+  const float* src;
+  int dst, rows, cols, ld, transpose;   // dst[r*cols+c] = src[r*ld+c]  (transpose: dst[c*rows+r])
+};
+
+__global__ void small_copy_kernel(const CopyItem* __restrict__ items, float* __restrict__ small) {
+  const CopyItem it = items[blockIdx.x];
+  if (!it.src) return;
+  const int n = it.rows * it.cols;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int r = t / it.cols, c = t % it.cols;
+    const float v = it.src[(size_t)r * it.ld + c];
+    small[it.dst + (it.transpose ? c * it.rows + r : t)] = v;
+  }
+}
+
+struct Builder {
+  std::vector<MmaStep> steps;
+  std::vector<PackItem> items;
+  uint32_t off16 = 0;
+
+  // one accumulation chunk: D[:, tmem_col : tmem_col+n] = sum over listed (a_slab, W column block)
+  // each entry: a_slab, col0 of W, ksteps, mode.  Rows row0..row0+n of W (non-transposed) form B.
+  struct Src { int a_slab, col0, ksteps, mode; };
+  void chunk(const float* W, int rows, int cols, int row0, int n, int tmem_col, const std::vector<Src>& srcs,
+             bool transpose = false) {
+    bool first = true;
+    for (const Src& s : srcs) {
+      MmaStep st{};
+      st.w_off16 = off16;
+      st.n = (uint16_t)n;
+      st.tmem_col = (uint16_t)tmem_col;
+      st.a_slab = (uint8_t)s.a_slab;
+      st.ksteps = (uint8_t)s.ksteps;
+      st.first = first ? 1 : 0;
+      st.last = 0;
+      steps.push_back(st);
+      PackItem it{};
+      it.src = W; it.ld = cols; it.rows = rows; it.cols = cols;
+      it.row0 = transpose ? s.col0 : row0;
+      it.col0 = transpose ? row0 : s.col0;
+      it.transpose = transpose ? 1 : 0;
+      it.mode = s.mode; it.n = n; it.dst_row0 = 0; it.dst_off16 = off16;
+      items.push_back(it);
+      off16 += (uint32_t)(n * 128 / 16);
+      first = false;
+    }
+  }
+  void end_phase() { steps.back().last = 1; }
+};
+
+// Forward order; must match the phase sequence of mlp_fwd.cu.
+void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) {
+  const NetDims d = make_dims(c);
+  const int ink = d.in_ksteps;
+  auto act8 = [](int ncols) {
+    std::vector<Builder::Src> v;
+    for (int k = 0; k < ncols / 64; ++k) v.push_back({k, 64 * k, 4, 0});
+    return v;
+  };
+  // layer 0: split-precision product  in_hi*W_hi + in_lo*W_hi + in_hi*W_lo   (models/spnerf.py:202)
+  for (int g = 0; g < 2; ++g)
+    b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, g * kHalf, kHalf, g * kHalf,
+            {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}});
+  b.end_phase();
+  for (int i = 1; i < 8; ++i) {   // models/spnerf.py:203-208, skip concat [h, input] at :327
+    const bool skip = (i == c.skip_layer);
+    const int cols = kFeat + (skip ? d.in_dim : 0);
+    for (int g = 0; g < 2; ++g) {
+      auto srcs = act8(kFeat);
+      if (skip) srcs.push_back({kSlabInpHi, kFeat, ink, 0});
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs);
+    }
+    b.end_phase();
+  }
+  // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212)
+  if (c.sem) b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat));
+  {
+    // sigma: B row 0 = fp16(w), row 1 = residual; the epilogue adds the two accumulator columns
+    auto srcs = act8(kFeat);
+    const size_t i0 = b.items.size();
+    b.chunk(P[SPNERF_P_SIGMA_W], 1, kFeat, 0, 16, kHalf, srcs);
+    const size_t i1 = b.items.size();
+    for (size_t i = i0; i < i1; ++i) {
+      b.items[i].n = 1;
+      PackItem lo = b.items[i];
+      lo.mode = 1; lo.dst_row0 = 1;
+      b.items.push_back(lo);
+    }
+  }
+  b.end_phase();
+  for (int g = 0; g < 2; ++g)   // feats_from_xyz (:215)
+    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, act8(kFeat));
+  b.end_phase();
+  b.chunk(P[SPNERF_P_RGB0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat));                 // :226-231
+  if (c.beta) {
+    b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, 0, kHalf, kHalf, act8(kFeat));   // :258-264
+    b.end_phase();
+    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, 0, act8(kFeat));              // :234-241
+    b.end_phase();
+  } else {
+    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, kHalf, act8(kFeat));
+    b.end_phase();
+  }
+  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, act8(kHalf));
+  b.end_phase();
+  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, act8(kHalf));
+  b.end_phase();
+}
+
+int validate(const SpnerfNetConfig* c) {
+  if (!c) return SPNERF_ERR_BAD_ARG;
+  if (c->feat != 512 || c->layers != 8 || c->skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (c->sem && (c->num_sem_classes < 1 || c->num_sem_classes > 8 || c->emb_dim < 1 || c->emb_dim > 8))
+    return SPNERF_ERR_UNSUPPORTED;
+  if (c->beta && (c->t_dim < 1 || c->t_dim > 8)) return SPNERF_ERR_UNSUPPORTED;
+  if (make_dims(*c).in_dim > 64) return SPNERF_ERR_UNSUPPORTED;
+  return 0;
+}
+
+}  // namespace
+
+void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
+                    std::vector<PackItem>* items, uint32_t* off16);   // mlp_pack_bwd section below
+
+extern "C" int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* s) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!s) return SPNERF_ERR_BAD_ARG;
+  const float* P[SPNERF_NUM_PARAMS] = {};
+  Builder f;
+  build_forward(*cfg, P, f);
+  std::memset(s, 0, sizeof(*s));
+  s->fwd_blob_bytes = (int64_t)f.off16 * 16;
+  s->fwd_steps = (int32_t)f.steps.size();
+  std::vector<MmaStep> bsteps;
+  uint32_t boff = 0;
+  build_backward(*cfg, P, bsteps, nullptr, &boff);
+  s->bwd_blob_bytes = (int64_t)boff * 16;
+  s->bwd_steps = (int32_t)bsteps.size();
+  s->small_floats = make_small_offsets(*cfg).total;
+  s->steps_bytes = (int64_t)kMaxSteps * sizeof(MmaStep);
+  s->save_slabs_per_tile = make_save_map(*cfg).total;
+  const NetDims d = make_dims(*cfg);
+  s->n_out = d.n_out;
+  s->in_dim = d.in_dim;
+  s->tile_points = kTileM;
+  if (s->fwd_steps > kMaxSteps || s->bwd_steps > kMaxSteps) return SPNERF_ERR_UNSUPPORTED;
+  return 0;
+}
+
+// Temporary device tables live at the tail of the step buffers' allocation?  No: the caller's
+// buffers hold only results.  The pack tables are staged through a small static device scratch
+// owned by this translation unit (allocated once, 64 KB), which keeps the call allocation-free
+// after the first use.
+namespace {
+void* g_scratch = nullptr;
+constexpr size_t kScratchBytes = 256 * 1024;
+}
+
+extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* P, void* fwd_blob, void* bwd_blob,
+                               float* small, void* fwd_steps, void* bwd_steps, void* stream_) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!P || !fwd_blob || !small || !fwd_steps) return SPNERF_ERR_BAD_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!g_scratch) {
+    cudaError_t e = cudaMalloc(&g_scratch, kScratchBytes);
+    if (e != cudaSuccess) return -(int)e;
+  }
+  Builder f;
+  build_forward(*cfg, P, f);
+  std::vector<MmaStep> bsteps;
+  std::vector<PackItem> bitems;
+  uint32_t boff = 0;
+  if (bwd_blob && bwd_steps) build_backward(*cfg, P, bsteps, &bitems, &boff);
+
+  // small fp32 block
+  const SmallOffsets o = make_small_offsets(*cfg);
+  std::vector<CopyItem> cp;
+  auto add = [&](int slot, int dst, int rows, int cols, int ld, int col0 = 0, int transpose = 0) {
+    if (!P[slot]) return;
+    cp.push_back({P[slot] + col0, dst, rows, cols, ld, transpose});
+  };
+  for (int i = 0; i < 8; ++i) add(SPNERF_P_FC_W0 + 2 * i + 1, o.fc_b[i], 1, kFeat, kFeat);
+  add(SPNERF_P_SIGMA_B, o.sigma_b, 1, 1, 1);
+  add(SPNERF_P_FEATS_B, o.feats_b, 1, kFeat, kFeat);
+  if (cfg->sem) {
+    add(SPNERF_P_SEM0_B, o.sem0_b, 1, kHalf, kHalf);
+    add(SPNERF_P_SEM2_W, o.sem2_w, cfg->num_sem_classes, kHalf, kHalf);
+    add(SPNERF_P_SEM2_B, o.sem2_b, 1, cfg->num_sem_classes, cfg->num_sem_classes);
+    add(SPNERF_P_SEM_EMB, o.emb, cfg->num_sem_classes + 1, cfg->emb_dim, cfg->emb_dim);
+  }
+  add(SPNERF_P_RGB0_B, o.rgb0_b, 1, kHalf, kHalf);
+  add(SPNERF_P_RGB2_W, o.rgb2_w, 3, kHalf, kHalf);
+  add(SPNERF_P_RGB2_B, o.rgb2_b, 1, 3, 3);
+  add(SPNERF_P_SUN0_W + 1, o.sun0_b, 1, kHalf, kHalf);
+  add(SPNERF_P_SUN0_W, o.sun0_wsun, kHalf, 3, kFeat + 3, kFeat, 1);          // -> [3][256]
+  add(SPNERF_P_SUN0_W + 3, o.sun2_b, 1, kHalf, kHalf);
+  add(SPNERF_P_SUN0_W + 5, o.sun4_b, 1, kHalf, kHalf);
+  add(SPNERF_P_SUN0_W + 6, o.sun6_w, 1, kHalf, kHalf);
+  add(SPNERF_P_SUN0_W + 7, o.sun6_b, 1, 1, 1);
+  if (cfg->beta) {
+    add(SPNERF_P_BETA0_B, o.beta0_b, 1, kHalf, kHalf);
+    add(SPNERF_P_BETA0_W, o.beta0_wt, kHalf, cfg->t_dim, kFeat + cfg->t_dim, kFeat, 1);   // -> [t][256]
+    add(SPNERF_P_BETA2_W, o.beta2_w, 1, kHalf, kHalf);
+    add(SPNERF_P_BETA2_B, o.beta2_b, 1, 1, 1);
+  }
+  add(SPNERF_P_SKY0_W, o.sky0_w, kHalf, 3, 3, 0, 1);                           // -> [3][256]
+  add(SPNERF_P_SKY0_B, o.sky0_b, 1, kHalf, kHalf);
+  add(SPNERF_P_SKY2_W, o.sky2_w, 3, kHalf, kHalf);
+  add(SPNERF_P_SKY2_B, o.sky2_b, 1, 3, 3);
+
+  const size_t bytes_f = f.items.size() * sizeof(PackItem), bytes_b = bitems.size() * sizeof(PackItem),
+               bytes_c = cp.size() * sizeof(CopyItem);
+  if (bytes_f + bytes_b + bytes_c + 64 > kScratchBytes) return SPNERF_ERR_WORKSPACE;
+  uint8_t* sc = static_cast<uint8_t*>(g_scratch);
+  cudaError_t e;
+  // The tables come from pageable host vectors: these copies complete before returning, and the
+  // previous pack's kernels on this stream must be done with the scratch first.
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return -(int)e;
+  e = cudaMemcpyAsync(sc, f.items.data(), bytes_f, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return -(int)e;
+  if (bytes_b) cudaMemcpyAsync(sc + bytes_f, bitems.data(), bytes_b, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(sc + bytes_f + bytes_b, cp.data(), bytes_c, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(fwd_steps, f.steps.data(), f.steps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
+  if (bytes_b)
+    cudaMemcpyAsync(bwd_steps, bsteps.data(), bsteps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
+  cudaMemsetAsync(fwd_blob, 0, (size_t)f.off16 * 16, stream);
+  if (bytes_b) cudaMemsetAsync(bwd_blob, 0, (size_t)boff * 16, stream);
+  cudaMemsetAsync(small, 0, (size_t)o.total * sizeof(float), stream);
+  pack_kernel<<<dim3((unsigned)f.items.size(), 2), 256, 0, stream>>>(reinterpret_cast<const PackItem*>(sc),
+                                                                     static_cast<uint8_t*>(fwd_blob));
+  if (bytes_b)
+    pack_kernel<<<dim3((unsigned)bitems.size(), 2), 256, 0, stream>>>(
+        reinterpret_cast<const PackItem*>(sc + bytes_f), static_cast<uint8_t*>(bwd_blob));
+  small_copy_kernel<<<(unsigned)cp.size(), 256, 0, stream>>>(
+      reinterpret_cast<const CopyItem*>(sc + bytes_f + bytes_b), small);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sky colour per ray: sigmoid(W2 relu(W0 s + b0) + b2)   (models/spnerf.py:244-249, :355)
+// one warp per ray, 8 hidden units per lane
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void sky_fwd_kernel(const float* __restrict__ small, SmallOffsets o, const float* __restrict__ rays,
+                               int64_t n_rays, float* __restrict__ sky, float* __restrict__ hidden) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rays; r += nwarps) {
+    const float sx = rays[r * 11 + 8], sy = rays[r * 11 + 9], sz = rays[r * 11 + 10];
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = u * 32 + lane;
+      float h = small[o.sky0_b + j];
+      h = fmaf(small[o.sky0_w + j], sx, h);
+      h = fmaf(small[o.sky0_w + kHalf + j], sy, h);
+      h = fmaf(small[o.sky0_w + 2 * kHalf + j], sz, h);
+      h = fmaxf(h, 0.f);
+      if (hidden) hidden[r * kHalf + j] = h;
+      acc0 = fmaf(small[o.sky2_w + j], h, acc0);
+      acc1 = fmaf(small[o.sky2_w + kHalf + j], h, acc1);
+      acc2 = fmaf(small[o.sky2_w + 2 * kHalf + j], h, acc2);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, s);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, s);
+      acc2 += __shfl_xor_sync(0xffffffffu, acc2, s);
+    }
+    if (lane < 3) {
+      const float a = (lane == 0 ? acc0 : lane == 1 ? acc1 : acc2) + small[o.sky2_b + lane];
+      sky[r * 3 + lane] = 1.f / (1.f + expf(-a));
+    }
+  }
+}
+}  // namespace
+
+extern "C" int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, const float* rays, int64_t n_rays,
+                              float* sky, float* hidden, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!small || !rays || !sky || n_rays < 0) return SPNERF_ERR_BAD_ARG;
+  if (n_rays == 0) return 0;
+  const int threads = 256;
+  const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
+  sky_fwd_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      small, make_small_offsets(*cfg), rays, n_rays, sky, hidden);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward-data order (filled in with mlp_bwd.cu)
+// ------------------------------------------------------------------------------------------------
+void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
+                    std::vector<PackItem>* items, uint32_t* off16) {
+  (void)c; (void)P; (void)steps; (void)items; (void)off16;
+}

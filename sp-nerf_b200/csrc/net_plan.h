@@ -1,0 +1,117 @@
+// Host+device shared definitions for the fused point-network kernels: the shared-memory map, the
+// step list that drives the weight producer and the MMA issuer, the layout of the small fp32
+// parameter block, and the per-tile activation save map.
+//
+// Network being executed: models/spnerf.py:273-369 (SPNeRF.forward) with feat=512, 8 layers,
+// skip at 4 (modules/opt.py:43-46 defaults).
+#pragma once
+#include <stdint.h>
+#include "../../include/spnerf_b200.h"
+
+namespace net {
+
+constexpr int kTileM = 128;          // points per tile (= accumulator rows = TMEM lanes)
+constexpr int kSlabBytes = 16384;    // 128 rows x 64 halves, 128B-swizzled (sm100.cuh)
+constexpr int kActSlabs = 8;         // 512-wide activation tile
+constexpr int kSlabInpHi = 8;        // encoded input (fp16 high part)
+constexpr int kSlabInpLo = 9;        // encoded input (fp16 residual); scratch after layer 0
+constexpr int kNumSlabs = 10;
+constexpr int kWStageBytes = 32768;  // one weight item: up to 256 rows x 64 k
+constexpr int kNumWStages = 2;
+constexpr int kSmemBars = kNumSlabs * kSlabBytes + kNumWStages * kWStageBytes;
+constexpr int kSmemTotal = kSmemBars + 256;
+
+constexpr int kFeat = 512;
+constexpr int kHalf = 256;
+constexpr int kMaxSteps = 320;
+
+// One weight item = one 64-wide K slab of one accumulation chunk.
+struct __align__(16) MmaStep {
+  uint32_t w_off16;   // offset of the packed B tile in the weight blob, in 16-byte units
+  uint16_t n;         // B rows (accumulator columns) of this item
+  uint16_t tmem_col;  // first accumulator column
+  uint8_t a_slab;     // shared-memory slab holding the A operand
+  uint8_t ksteps;     // K=16 instructions to issue from this slab (1..4)
+  uint8_t first;      // 1: overwrite the accumulator (first item of a chunk)
+  uint8_t last;       // 1: last item of a phase -> signal the epilogue
+  uint32_t _pad;
+};
+
+// Offsets (in floats) into the small fp32 parameter block copied by the pack kernel.
+struct SmallOffsets {
+  int fc_b[8];
+  int sigma_b, feats_b;
+  int sem0_b, sem2_w, sem2_b;
+  int rgb0_b, rgb2_w, rgb2_b;
+  int sun0_b, sun0_wsun, sun2_b, sun4_b, sun6_w, sun6_b;
+  int beta0_b, beta0_wt, beta2_w, beta2_b;
+  int emb;       // (C+1, emb_dim)
+  int sky0_w, sky0_b, sky2_w, sky2_b;
+  int total;
+};
+
+// Per-tile activation save area, in slabs (training forward -> backward).
+struct SaveMap {
+  int inp;         // encoded input (hi)                          1 slab
+  int aux;         // [1, sun_dir(3), t_emb(t_dim), 0...]          1 slab
+  int y[8];        // post-activation of trunk layer i            8 slabs each
+  int x[8];        // sine argument of trunk layer i (x[0]: cos of it, see mlp_fwd.cu)
+  int f;           // feats_from_xyz output                       8 slabs
+  int sem_x, sem_y, rgb_x, rgb_y, beta_x, beta_y;   // 4 slabs each (-1 if absent)
+  int sun_x[3], sun_y[3];                           // 4 slabs each
+  int total;
+};
+
+struct NetDims {
+  int in_dim;      // encoded xyz (3 or 60) + emb_dim
+  int in_ksteps;   // K=16 steps covering in_dim
+  int n_out;       // 8 (+1 beta) (+C sem)
+  int col_beta, col_sem;
+};
+
+inline NetDims make_dims(const SpnerfNetConfig& c) {
+  NetDims d;
+  d.in_dim = (c.mapping ? 60 : 3) + (c.sem ? c.emb_dim : 0);
+  d.in_ksteps = (d.in_dim + 15) / 16;
+  d.col_beta = c.beta ? 8 : -1;
+  d.col_sem = c.sem ? 8 + (c.beta ? 1 : 0) : -1;
+  d.n_out = 8 + (c.beta ? 1 : 0) + (c.sem ? c.num_sem_classes : 0);
+  return d;
+}
+
+inline SaveMap make_save_map(const SpnerfNetConfig& c) {
+  SaveMap m;
+  int s = 0;
+  m.inp = s++;
+  m.aux = s++;
+  for (int i = 0; i < 8; ++i) { m.y[i] = s; s += 8; m.x[i] = s; s += 8; }
+  m.f = s; s += 8;
+  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += 4; return r; };
+  m.sem_x = four(c.sem); m.sem_y = four(c.sem);
+  m.rgb_x = four(true); m.rgb_y = four(true);
+  m.beta_x = four(c.beta); m.beta_y = four(c.beta);
+  for (int i = 0; i < 3; ++i) { m.sun_x[i] = four(true); m.sun_y[i] = four(true); }
+  m.total = s;
+  return m;
+}
+
+inline SmallOffsets make_small_offsets(const SpnerfNetConfig& c) {
+  SmallOffsets o;
+  int s = 0;
+  auto take = [&](int n) { int r = s; s += (n + 3) & ~3; return r; };   // keep float4 alignment
+  for (int i = 0; i < 8; ++i) o.fc_b[i] = take(kFeat);
+  o.sigma_b = take(1);
+  o.feats_b = take(kFeat);
+  o.sem0_b = take(kHalf); o.sem2_w = take(8 * kHalf); o.sem2_b = take(8);
+  o.rgb0_b = take(kHalf); o.rgb2_w = take(3 * kHalf); o.rgb2_b = take(3);
+  o.sun0_b = take(kHalf); o.sun0_wsun = take(3 * kHalf);
+  o.sun2_b = take(kHalf); o.sun4_b = take(kHalf); o.sun6_w = take(kHalf); o.sun6_b = take(1);
+  o.beta0_b = take(kHalf); o.beta0_wt = take(8 * kHalf); o.beta2_w = take(kHalf); o.beta2_b = take(1);
+  o.emb = take(9 * 8);
+  o.sky0_w = take(3 * kHalf); o.sky0_b = take(kHalf); o.sky2_w = take(3 * kHalf); o.sky2_b = take(3);
+  o.total = s;
+  (void)c;
+  return o;
+}
+
+}  // namespace net
