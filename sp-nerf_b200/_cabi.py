@@ -110,7 +110,8 @@ class MlpFwd(ctypes.Structure):
                 ("sky", ctypes.c_void_p),
                 ("n_rays", ctypes.c_int64), ("n_samples", ctypes.c_int32), ("n_steps", ctypes.c_int32),
                 ("blob", ctypes.c_void_p), ("steps", ctypes.c_void_p), ("small", ctypes.c_void_p),
-                ("out", ctypes.c_void_p), ("saves", ctypes.c_void_p)]
+                ("out", ctypes.c_void_p), ("saves", ctypes.c_void_p),
+                ("debug_flags", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
 def _declare_net(L):

@@ -85,7 +85,7 @@ class NetEngine:
         return sky, hidden
 
     def forward(self, rays, n_samples, z=None, xyz=None, dir_override=None, labels=None, t_emb=None, sky=None,
-                save=False):
+                save=False, debug_flags=0):
         """Network output rows (n_rays*n_samples, n_out) fp32 in the reference's column order."""
         self.ensure_packed()
         n_rays = rays.shape[0]
@@ -106,5 +106,6 @@ class NetEngine:
         a.blob, a.steps, a.small = self.fwd_blob.data_ptr(), self.fwd_steps.data_ptr(), self.small.data_ptr()
         a.out = out.data_ptr()
         a.saves = saves.data_ptr() if saves is not None else None
+        a.debug_flags = debug_flags
         _cabi.check(_cabi.lib().spnerf_mlp_fwd(ctypes.byref(a), _stream()), "spnerf_mlp_fwd")
         return out, saves
