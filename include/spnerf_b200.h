@@ -39,6 +39,8 @@ enum {
 int spnerf_abi_version(void);
 /* nonzero if a bounded device-side wait expired since load (debug aid; 0 in normal operation) */
 unsigned int spnerf_watchdog_code(void);
+/* sizeof() of every argument struct below, in declaration order (binding self-check) */
+void spnerf_struct_sizes(int32_t* out10_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core bring-up check (tests only): D[128,n] = A * B^T from caller-built shared-memory
@@ -98,6 +100,7 @@ typedef struct SpnerfNetSizes {
   int64_t steps_bytes;         /* per step table (forward and backward each)                */
   int32_t fwd_steps, bwd_steps;
   int32_t save_slabs_per_tile; /* x 16384 bytes x ceil(points/128) = activation save area   */
+  int32_t grad_slabs_per_tile; /* same unit: gradient save area (backward-data -> weight GEMMs) */
   int32_t n_out;               /* columns of the network output row                         */
   int32_t in_dim;
   int32_t tile_points;         /* 128 */
@@ -115,6 +118,12 @@ int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* params_host,
  * sky (n_rays,3); hidden (n_rays,256) post-ReLU or NULL. */
 int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, const float* rays, int64_t n_rays,
                    float* sky, float* hidden, void* stream);
+
+/* Backward of the sky network over rays: += into the four sky_color gradients (pre-zeroed).
+ * sky, hidden: outputs of spnerf_sky_fwd; g_sky: (n_rays,3) dL/d sky summed over samples. */
+int spnerf_sky_bwd(const float* small, const SpnerfNetConfig* cfg, const float* rays, const float* sky,
+                   const float* hidden, const float* g_sky, int64_t n_rays, float* g_w0, float* g_b0,
+                   float* g_w2, float* g_b2, void* stream);
 
 typedef struct SpnerfMlpFwd {
   SpnerfNetConfig cfg;
@@ -139,6 +148,156 @@ typedef struct SpnerfMlpFwd {
   int32_t _pad;
 } SpnerfMlpFwd;
 int spnerf_mlp_fwd(const SpnerfMlpFwd* args, void* stream);
+
+/* Backward of the point network, in two kernels (replaces autograd through SPNeRF.forward):
+ *  1. spnerf_mlp_bwd_data: dL/d(out) -> pre-activation gradients of every layer (fp16 tiles in
+ *     `grad_saves`, scaled by the power of two written to `scale_out`), plus the gradients that
+ *     are cheap row reductions: label embedding, last-layer biases, transient embedding input;
+ *  2. spnerf_mlp_bwd_weights: every weight / bias gradient as tensor-core GEMMs over the point
+ *     dimension between `grad_saves` and the forward's `saves`.                                 */
+typedef struct SpnerfMlpBwd {
+  SpnerfNetConfig cfg;
+  const float* g_out;       /* (points, n_out) from spnerf_composite_bwd                         */
+  const float* out;         /* (points, n_out) forward output                                    */
+  const float* rays;
+  const int64_t* labels;    /* (n_rays) or NULL                                                  */
+  const float* t_emb;       /* (n_rays, t_dim) or NULL                                           */
+  int64_t n_rays;
+  int32_t n_samples;
+  int32_t n_steps;          /* sizes.bwd_steps */
+  const void* blob;         /* bwd_blob  */
+  const void* steps;        /* bwd_steps */
+  const float* small;
+  const void* saves;        /* written by spnerf_mlp_fwd */
+  void* grad_saves;         /* grad_slabs_per_tile * 16384 * ceil(points/128) bytes              */
+  const float* g_absmax;    /* max|g_out| (device scalar, from spnerf_composite_bwd)             */
+  float* scale_out;         /* device scalar: the gradient scale used                            */
+  float* g_emb;             /* (C+1, emb_dim) += ; pre-zeroed; padding row stays zero            */
+  float* g_small_bias;      /* 14 floats += : d rgb.2.bias(3), sun.6.bias, sigma.bias, beta.2.bias,
+                               logit.2.bias(8); pre-zeroed                                       */
+  float* g_t_emb;           /* (n_rays, t_dim) += or NULL; pre-zeroed                            */
+  int32_t debug_flags;
+  int32_t _pad;
+} SpnerfMlpBwd;
+int spnerf_mlp_bwd_data(const SpnerfMlpBwd* args, void* stream);
+
+typedef struct SpnerfMlpWgrad {
+  SpnerfNetConfig cfg;
+  int64_t n_points;
+  const void* saves;
+  const void* grad_saves;
+  const float* scale;        /* scale_out of spnerf_mlp_bwd_data                                 */
+  float* const* grads_host;  /* SPNERF_NUM_PARAMS device pointers (same slots / shapes as the
+                                parameters); weight and hidden-layer bias gradients are OVERWRITTEN;
+                                slots fed by g_small_bias / g_emb are not touched                 */
+  void* workspace;           /* >= spnerf_mlp_wgrad_workspace_bytes(cfg) bytes                   */
+  int64_t workspace_bytes;
+} SpnerfMlpWgrad;
+int64_t spnerf_mlp_wgrad_workspace_bytes(const SpnerfNetConfig* cfg);
+/* uploads the GEMM tables into the workspace tail: once per (cfg, grads_host, workspace); syncs the stream */
+int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* args, void* stream);
+int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Volume integration (replaces models/spnerf.py:109-157 and its autograd graph).
+ * `out` is the network output (n_rays*n_samples, n_out) with the reference's columns
+ * [albedo(3), sigma, sun, sky(3), (beta), (logits)] (models/spnerf.py:110-113,148-156).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct SpnerfCompositeFwd {
+  const float* out;
+  const float* z;            /* (n_rays, n_samples) sorted depths                                */
+  const float* noise;        /* (n_rays, n_samples) standard normals or NULL (spnerf.py:121-122)  */
+  int64_t n_rays;
+  int32_t n_samples;         /* <= 256 */
+  int32_t n_out;
+  int32_t col_sem, n_sem;    /* first logit column / number of classes (0: no semantic head)      */
+  float noise_std;
+  int32_t _pad;
+  float* weights;            /* (n_rays, n_samples)  alpha_i * T_i                                */
+  float* transparency;       /* (n_rays, n_samples)  T_i                                          */
+  float* rgb;                /* (n_rays, 3) clamped to [0,1]                                      */
+  float* rgb_raw;            /* (n_rays, 3) before the clamp, or NULL (needed by the backward)    */
+  float* depth;              /* (n_rays)                                                          */
+  float* sem_logits;         /* (n_rays, n_sem): plain mean over samples (spnerf.py:156)          */
+} SpnerfCompositeFwd;
+int spnerf_composite_fwd(const SpnerfCompositeFwd* args, void* stream);
+
+typedef struct SpnerfCompositeBwd {
+  const float* out; const float* z; const float* noise;
+  const float* weights; const float* transparency; const float* rgb_raw;   /* saved by the forward */
+  const float* g_rgb;          /* (n_rays,3) or NULL          upstream gradients ...              */
+  const float* g_depth;        /* (n_rays) or NULL                                                */
+  const float* g_sem_logits;   /* (n_rays,n_sem) or NULL                                          */
+  const float* g_weights;      /* (n_rays,n_samples) or NULL                                      */
+  const float* g_transparency; /* (n_rays,n_samples) or NULL                                      */
+  const float* g_out_ext;      /* (points,n_out) or NULL: gradients arriving directly on `out`    */
+  int64_t n_rays;
+  int32_t n_samples, n_out, col_sem, n_sem;
+  float noise_std;
+  int32_t _pad;
+  float* g_out;                /* (points, n_out) gradient w.r.t. the network output              */
+  float* g_sky_ray;            /* (n_rays,3) or NULL: sum over samples of the sky-colour gradient */
+  float* g_absmax;             /* one float, atomically max-updated with max|g_out| (pre-zeroed)  */
+} SpnerfCompositeBwd;
+int spnerf_composite_bwd(const SpnerfCompositeBwd* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss reductions with their gradients in one pass (replaces modules/metrics.py:27-45 colour MSE,
+ * :68-159 DepthLoss subset / all-depth MSE variants, :162-183 SemanticLoss).
+ * Scalars land in `losses` (device): [0] colour, [1] depth, [2] semantic, [3] rays the depth term
+ * applied to, [4] labelled rays.  Gradients are d(loss_k)/d(input), NOT summed over k.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct SpnerfLosses {
+  int64_t n_rays;
+  int32_t n_samples, n_sem;
+  /* colour (NULL rgb: skip) */
+  const float* rgb; const float* rgb_target; float* g_rgb;
+  /* depth supervision (NULL depth: skip) */
+  const float* depth; const float* z; const float* weights;
+  const float* target_depth; const float* target_weight; const float* target_std;
+  const int64_t* valid_depth;  /* NULL: every ray is valid (metrics.py:83-87) */
+  float lambda_ds;             /* the constructor's lambda_ds; the kernel applies the /3 of metrics.py:71 */
+  int32_t use_all_depth;       /* metrics.py:140,154-156 */
+  float* g_depth;
+  /* semantic (NULL sem_logits: skip) */
+  const float* sem_logits; const int64_t* labels; float lambda_ss; int32_t _pad;
+  float* g_sem_logits;
+  float* losses;               /* 8 floats */
+  void* workspace;             /* >= spnerf_losses_workspace_bytes() bytes */
+} SpnerfLosses;
+int64_t spnerf_losses_workspace_bytes(void);
+int spnerf_losses(const SpnerfLosses* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ray samplers (replace modules/rendering.py:128-144 and :14-116,165-167).  Uniform draws are
+ * inputs; `t_table` = torch.linspace(0,1,n_samples) and `gauss_table` =
+ * 1/sqrt(2 pi) * exp(-0.5 * linspace(-3,3,n_samples-1)^2) as computed by torch on the host
+ * (rendering.py:60,68-70), so the device arithmetic reproduces the reference bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+int spnerf_sample_coarse(const float* rays, const float* t_table, const float* uniforms, int64_t n_rays,
+                         int32_t n_samples, float* z, void* stream);
+
+typedef struct SpnerfGuided {
+  const float* rays;          /* (n_rays,11); rays[0,6:8] clamp every ray (rendering.py:95) */
+  const float* z;             /* (n_rays,n) coarse depths (sorted)                                  */
+  const float* weights;       /* (n_rays,n) and ...                                                 */
+  const float* depth;         /* (n_rays)   ... of the first pass (rendering.py:77-81)               */
+  const int64_t* valid_depth; /* (n_rays) or NULL (test mode): >0 -> sample around the depth prior   */
+  const float* target_depth;  /* element r at target_depth[r*target_depth_stride] (depths[:,0])      */
+  int64_t target_depth_stride;
+  const float* target_std;    /* (n_rays) */
+  const float* u_pred;        /* (n_rays,n) uniforms for rays sampled around the predicted depth     */
+  const float* u_gt;          /* (n_rays,n) uniforms for rays sampled around the prior (row = ray)   */
+  const float* t_table;       /* (n) */
+  const float* gauss_table;   /* (n-1) */
+  int64_t n_rays;
+  int32_t n_samples;
+  int32_t _pad;
+  float* z_unsort;            /* (n_rays,2n) = [z, sort(z2)]   (rendering.py:165-166)                */
+  float* z_sorted;            /* (n_rays,2n) = sort([z, z2])   (rendering.py:167)                    */
+  int32_t* searchsorted_out;  /* (n_rays,n) indices of rendering.py:38, or NULL (parity tests)       */
+} SpnerfGuided;
+int spnerf_sample_guided(const SpnerfGuided* args, void* stream);
 
 #ifdef __cplusplus
 }

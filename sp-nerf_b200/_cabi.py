@@ -99,7 +99,8 @@ class NetSizes(ctypes.Structure):
     _fields_ = [("fwd_blob_bytes", ctypes.c_int64), ("bwd_blob_bytes", ctypes.c_int64),
                 ("small_floats", ctypes.c_int64), ("steps_bytes", ctypes.c_int64),
                 ("fwd_steps", ctypes.c_int32), ("bwd_steps", ctypes.c_int32),
-                ("save_slabs_per_tile", ctypes.c_int32), ("n_out", ctypes.c_int32),
+                ("save_slabs_per_tile", ctypes.c_int32), ("grad_slabs_per_tile", ctypes.c_int32),
+                ("n_out", ctypes.c_int32),
                 ("in_dim", ctypes.c_int32), ("tile_points", ctypes.c_int32)]
 
 
@@ -127,9 +128,84 @@ def _declare_net(L):
     L.spnerf_mlp_fwd.argtypes = [ctypes.POINTER(MlpFwd), ctypes.c_void_p]
 
 
+VP, I32, I64, F32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+
+class CompositeFwd(ctypes.Structure):
+    _fields_ = [("out", VP), ("z", VP), ("noise", VP), ("n_rays", I64), ("n_samples", I32), ("n_out", I32),
+                ("col_sem", I32), ("n_sem", I32), ("noise_std", F32), ("_pad", I32),
+                ("weights", VP), ("transparency", VP), ("rgb", VP), ("rgb_raw", VP), ("depth", VP),
+                ("sem_logits", VP)]
+
+
+class CompositeBwd(ctypes.Structure):
+    _fields_ = [("out", VP), ("z", VP), ("noise", VP), ("weights", VP), ("transparency", VP), ("rgb_raw", VP),
+                ("g_rgb", VP), ("g_depth", VP), ("g_sem_logits", VP), ("g_weights", VP), ("g_transparency", VP),
+                ("g_out_ext", VP), ("n_rays", I64), ("n_samples", I32), ("n_out", I32), ("col_sem", I32),
+                ("n_sem", I32), ("noise_std", F32), ("_pad", I32), ("g_out", VP), ("g_sky_ray", VP),
+                ("g_absmax", VP)]
+
+
+class Losses(ctypes.Structure):
+    _fields_ = [("n_rays", I64), ("n_samples", I32), ("n_sem", I32),
+                ("rgb", VP), ("rgb_target", VP), ("g_rgb", VP),
+                ("depth", VP), ("z", VP), ("weights", VP), ("target_depth", VP), ("target_weight", VP),
+                ("target_std", VP), ("valid_depth", VP), ("lambda_ds", F32), ("use_all_depth", I32),
+                ("g_depth", VP),
+                ("sem_logits", VP), ("labels", VP), ("lambda_ss", F32), ("_pad", I32), ("g_sem_logits", VP),
+                ("losses", VP), ("workspace", VP)]
+
+
+class Guided(ctypes.Structure):
+    _fields_ = [("rays", VP), ("z", VP), ("weights", VP), ("depth", VP), ("valid_depth", VP),
+                ("target_depth", VP), ("target_depth_stride", I64), ("target_std", VP), ("u_pred", VP),
+                ("u_gt", VP), ("t_table", VP), ("gauss_table", VP), ("n_rays", I64), ("n_samples", I32),
+                ("_pad", I32), ("z_unsort", VP), ("z_sorted", VP), ("searchsorted_out", VP)]
+
+
+class MlpBwd(ctypes.Structure):
+    _fields_ = [("cfg", NetConfig), ("g_out", VP), ("out", VP), ("rays", VP), ("labels", VP), ("t_emb", VP),
+                ("n_rays", I64), ("n_samples", I32), ("n_steps", I32), ("blob", VP), ("steps", VP), ("small", VP),
+                ("saves", VP), ("grad_saves", VP), ("g_absmax", VP), ("scale_out", VP), ("g_emb", VP),
+                ("g_small_bias", VP), ("g_t_emb", VP), ("debug_flags", I32), ("_pad", I32)]
+
+
+class MlpWgrad(ctypes.Structure):
+    _fields_ = [("cfg", NetConfig), ("n_points", I64), ("saves", VP), ("grad_saves", VP), ("scale", VP),
+                ("grads_host", ctypes.POINTER(VP)), ("workspace", VP), ("workspace_bytes", I64)]
+
+
+def _declare_rest(L):
+    for name, st in (("spnerf_composite_fwd", CompositeFwd), ("spnerf_composite_bwd", CompositeBwd),
+                     ("spnerf_losses", Losses), ("spnerf_sample_guided", Guided),
+                     ("spnerf_mlp_bwd_data", MlpBwd), ("spnerf_mlp_wgrad_prepare", MlpWgrad),
+                     ("spnerf_mlp_bwd_weights", MlpWgrad)):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.POINTER(st), VP]
+    L.spnerf_losses_workspace_bytes.restype = I64
+    L.spnerf_losses_workspace_bytes.argtypes = []
+    L.spnerf_mlp_wgrad_workspace_bytes.restype = I64
+    L.spnerf_mlp_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(NetConfig)]
+    L.spnerf_sample_coarse.restype = ctypes.c_int
+    L.spnerf_sample_coarse.argtypes = [VP, VP, VP, I64, I32, VP, VP]
+    L.spnerf_sky_bwd.restype = ctypes.c_int
+    L.spnerf_sky_bwd.argtypes = [VP, ctypes.POINTER(NetConfig), VP, VP, VP, VP, I64, VP, VP, VP, VP, VP]
+    L.spnerf_struct_sizes.restype = None
+    L.spnerf_struct_sizes.argtypes = [ctypes.POINTER(I32)]
+
+
+STRUCTS = (UmmaSelftest, NetConfig, NetSizes, MlpFwd, CompositeFwd, CompositeBwd, Losses, Guided, MlpBwd, MlpWgrad)
+
 _declare_base = _declare
 
 
 def _declare(L):  # noqa: F811
     _declare_base(L)
     _declare_net(L)
+    _declare_rest(L)
+    sizes = (I32 * len(STRUCTS))()
+    L.spnerf_struct_sizes(sizes)
+    for st, n in zip(STRUCTS, sizes):
+        if ctypes.sizeof(st) != n:
+            raise SpnerfError(f"ABI mismatch: {st.__name__} is {ctypes.sizeof(st)} bytes here, {n} in the library")

@@ -1,0 +1,329 @@
+// Fused point-network backward, data path: walks the layers of models/spnerf.py:305-369 in reverse
+// for a tile of 128 sample points per CTA, gradient tile resident in shared memory (fp16, scaled
+// by a power of two chosen from max|dL/d out|), accumulators in tensor memory.
+//
+// Replaces the autograd backward of SPNeRF.forward (cuBLAS dgrad GEMMs + elementwise cos kernels
+// in the reference).  For every layer the pre-activation gradient G = dL/d(sine argument) is
+//   * left in shared memory as the A operand of the next (earlier) layer's GEMM, and
+//   * streamed to the gradient save area, where the weight-gradient GEMMs (mlp_wgrad.cu) read it.
+// Same roles / handshake as mlp_fwd.cu; step order from build_backward() in mlp_pack.cu.
+#include "mlp_roles.cuh"
+
+using namespace roles;
+
+namespace {
+
+struct BwdParams {
+  const float* g_out; const float* out; const float* rays; const int64_t* labels; const float* t_emb;
+  int64_t n_rays; int64_t n_points; int n_samples;
+  const uint8_t* blob; const MmaStep* steps; int n_steps;
+  const float* small; SmallOffsets so; SaveMap sm; GradMap gm;
+  const uint8_t* saves; uint8_t* gsaves;
+  const float* absmax; float* scale_out;
+  float* g_emb; float* g_small_bias; float* g_t_emb;
+  int sem, n_classes, emb_dim, beta, t_dim, n_out, col_beta, col_sem, debug;
+};
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint32_t slab_off(int col, int row) {
+  return (uint32_t)(col >> 6) * kSlabBytes + slab_chunk_offset(row, (col & 63) >> 3);
+}
+
+// G[j] = acc[j] * dact(j) for columns [j0, j0+ncols) of a chunk at TMEM column tcol0;
+// MODE 0: dact = cos(x)  (x = saved fp16 sine argument)     MODE 1: dact = 30 * saved cos     MODE 2: dact = 1
+// result -> fp16 -> shared slab at column dst_col0 + j (+ gradient save area)
+template <int MODE>
+__device__ __forceinline__ void bwd_columns(uint32_t taddr, int tcol0, int j0, int ncols, const uint8_t* xsave,
+                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave, int skip) {
+  if (skip) ncols = 32;
+  for (int jb = j0; jb < j0 + ncols; jb += 32) {
+    uint4 xr[4];
+    if (MODE != 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xr[c] = ldg16(xsave + slab_off(jb + c * 8, row));
+    }
+    uint32_t v[32];
+    tmem_ld32(taddr + tcol0 + jb, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float g[8];
+      if (MODE != 2) {
+        float x[8];
+        unpack8(xr[c], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? __cosf(x[e]) : 30.f * x[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
+      }
+      const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+      const uint32_t off = slab_off(dst_col0 + jb + c * 8, row);
+      *reinterpret_cast<uint4*>(act + off) = gp;
+      if (gsave) *reinterpret_cast<uint4*>(gsave + slab_off(jb + c * 8, row)) = gp;
+    }
+  }
+}
+
+// Gradient entering a 256-wide hidden layer from its tiny output layer (CUDA cores):
+//   G[j] = (sum_c coef[c] * W2[c][j]) * cos(x[j])   for j in [j0, j0+ncols)
+// `each(j, G)` lets the caller fold further per-row reductions (t_emb gradient).
+template <int NC, class Each>
+__device__ __forceinline__ void gen_columns(const float* coef, const float* __restrict__ w2, int j0, int ncols,
+                                            const uint8_t* xsave, uint8_t* act, int dst_col0, int row,
+                                            uint8_t* gsave, Each each) {
+  for (int jb = j0; jb < j0 + ncols; jb += 8) {
+    float x[8], g[8];
+    unpack8(ldg16(xsave + slab_off(jb, row)), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a = fmaf(coef[c], __ldg(w2 + c * kHalf + jb + e), a);
+      g[e] = a * __cosf(x[e]);
+      each(jb + e, g[e]);
+    }
+    const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+    *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb, row)) = gp;
+    if (gsave) *reinterpret_cast<uint4*>(gsave + slab_off(jb, row)) = gp;
+  }
+}
+struct NoEachG { __device__ __forceinline__ void operator()(int, float) const {} };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem sh = carve(smem);
+  uint8_t* act = sh.act;
+  float* scratch = reinterpret_cast<float*>(smem + kSlabInpLo * kSlabBytes);   // unused input slab: scratch
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_base = setup(sh, smem);
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+
+  // power-of-two gradient scale keeping fp16 operands in range
+  float scale = 1.f;
+  {
+    const float am = *p.absmax;
+    if (am > 0.f && isfinite(am)) {
+      int e = (int)floorf(log2f(64.f / am));
+      e = e < -60 ? -60 : (e > 60 ? 60 : e);
+      scale = exp2f((float)e);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.scale_out = scale;
+  }
+  const float inv_scale = 1.f / scale;
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(sh, p.blob, p.steps, p.n_steps, n_tiles, p.debug);
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(sh, tmem_base, p.steps, p.n_steps, n_tiles, p.debug);
+  } else if (warp >= kEpiWarp0) {
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float* S = p.small;
+    const int skip = p.debug & 2;
+    EpiSync sync(sh);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t pt = tile * kTileM + row;
+      const bool valid = pt < p.n_points;
+      const int64_t ray = valid ? pt / p.n_samples : 0;
+      const uint8_t* tsave = p.saves + (size_t)tile * p.sm.total * kSlabBytes;
+      uint8_t* tg = p.gsaves + (size_t)tile * p.gm.total * kSlabBytes;
+      auto xs = [&](int slab) { return tsave + (size_t)slab * kSlabBytes; };
+      auto gs = [&](int slab) { return tg + (size_t)slab * kSlabBytes; };
+
+      // ---- head-level gradients of this row (fp32, unscaled) ----
+      float g_u[3] = {0.f, 0.f, 0.f}, g_v = 0.f, g_sp = 0.f, g_bp = 0.f, g_lg[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g_lg[c] = 0.f;
+      if (valid) {
+        const float* go = p.g_out + pt * p.n_out;
+        const float* o = p.out + pt * p.n_out;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {                  // rgb = sigmoid(u)*1.002 - 0.001  (spnerf.py:346-347)
+          const float s = (o[c] + 0.001f) / 1.002f;
+          g_u[c] = go[c] * 1.002f * s * (1.f - s);
+        }
+        g_sp = go[3] * (1.f - expf(-o[3]));            // softplus' = 1 - exp(-softplus)
+        g_v = go[4] * o[4] * (1.f - o[4]);             // sigmoid'
+        if (p.beta) g_bp = go[p.col_beta] * (1.f - expf(-o[p.col_beta]));
+        if (p.sem)
+          for (int c = 0; c < p.n_classes; ++c) g_lg[c] = go[p.col_sem + c];
+      }
+      sync.drain_stores();
+      // small-gradient slab [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)] (scaled), the B operand
+      // of the tiny last-layer weight gradients; bias gradients of those layers are reduced right here
+      if (grp == 0) {
+        uint8_t* d = gs(p.gm.gsmall);
+        const float sc = scale;
+        *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, 0)) =
+            make_uint4(pack2(g_u[0] * sc, g_u[1] * sc), pack2(g_u[2] * sc, g_v * sc), pack2(g_sp * sc, g_bp * sc), 0u);
+        *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, 1)) =
+            make_uint4(pack2(g_lg[0] * sc, g_lg[1] * sc), pack2(g_lg[2] * sc, g_lg[3] * sc),
+                       pack2(g_lg[4] * sc, g_lg[5] * sc), pack2(g_lg[6] * sc, g_lg[7] * sc));
+        for (int c = 2; c < 8; ++c) *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, c)) = make_uint4(0, 0, 0, 0);
+        float sums[14] = {g_u[0], g_u[1], g_u[2], g_v, g_sp, g_bp, g_lg[0], g_lg[1], g_lg[2], g_lg[3],
+                          g_lg[4], g_lg[5], g_lg[6], g_lg[7]};
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+          const float t = warp_sum(sums[k]);
+          if (lane == 0 && t != 0.f) atomicAdd(p.g_small_bias + k, t);
+        }
+      }
+      // ---- E_in: G_s3 = g_v * W_sun6 * cos(x_s3) -> slabs 0..3 ----
+      {
+        const float coef[1] = {g_v * scale};
+        gen_columns<1>(coef, S + p.so.sun6_w, grp * 128, 128, xs(p.sm.sun_x[2]), act, 0, row, gs(p.gm.G_sun[2]),
+                       NoEachG());
+      }
+      sync.end(true, nullptr, 0, 0);
+      // ---- after sun_v_net.4^T: G_s2 ----
+      sync.begin();
+      bwd_columns<0>(taddr, 0, grp * 128, 128, xs(p.sm.sun_x[1]), act, 0, row, gs(p.gm.G_sun[1]), 0);
+      sync.end(true, nullptr, 0, 0);
+      // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
+      sync.begin();
+      bwd_columns<0>(taddr, 0, grp * 128, 128, xs(p.sm.sun_x[0]), act, 0, row, gs(p.gm.G_sun[0]), 0);
+      {
+        const float coef[3] = {g_u[0] * scale, g_u[1] * scale, g_u[2] * scale};
+        gen_columns<3>(coef, S + p.so.rgb2_w, grp * 128, 128, xs(p.sm.rgb_x), act, kHalf, row, gs(p.gm.G_rgb),
+                       NoEachG());
+      }
+      sync.end(true, nullptr, 0, 0);
+      if (p.beta) {
+        // ---- beta hidden G_b1 -> slabs 0..3 (the sun/albedo GEMMs have retired); d t_emb on the way ----
+        sync.begin();
+        float tacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tacc[e] = 0.f;
+        const float coef[1] = {g_bp * scale};
+        const float* wt = S + p.so.beta0_wt;
+        gen_columns<1>(coef, S + p.so.beta2_w, grp * 128, 128, xs(p.sm.beta_x), act, 0, row, gs(p.gm.G_beta),
+                       [&](int j, float g) {
+#pragma unroll
+                         for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * kHalf + j), tacc[e]);
+                       });
+        if (p.g_t_emb && valid)
+          for (int e = 0; e < p.t_dim; ++e) atomicAdd(p.g_t_emb + ray * p.t_dim + e, tacc[e] * inv_scale);
+        sync.end(true, nullptr, 0, 0);
+      }
+      // ---- g_f (linear) -> slabs 0..7 ----
+      sync.begin();
+      bwd_columns<2>(taddr, 0, grp * kHalf, kHalf, nullptr, act, 0, row, gs(p.gm.g_f), skip);
+      sync.end(true, nullptr, 0, 0);
+      // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
+      sync.begin();
+      if (p.sem) {
+        float coef[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) coef[c] = g_lg[c] * scale;
+        gen_columns<8>(coef, S + p.so.sem2_w, grp * 128, 128, xs(p.sm.sem_x), act, 0, row, gs(p.gm.G_sem), NoEachG());
+      }
+      if (grp == 0) {
+        *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 0)) =
+            make_uint4(pack2(g_sp * scale, 0.f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      sync.end(true, nullptr, 0, 0);
+      // ---- G_7 = g_h * cos(x_7), then the trunk ----
+      float gemb[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gemb[e] = 0.f;
+      auto emb_phase = [&](bool signal) {      // 16-wide product with the embedding columns of a weight
+        sync.begin();
+        if (grp == 0) {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gemb[e] += __uint_as_float(v[e]);
+        }
+        if (signal) sync.end(true, nullptr, 0, 0);
+      };
+      for (int L = 7; L >= 0; --L) {
+        sync.begin();
+        if (L > 0) bwd_columns<0>(taddr, 0, grp * kHalf, kHalf, xs(p.sm.x[L]), act, 0, row, gs(p.gm.G[L]), skip);
+        else       bwd_columns<1>(taddr, 0, grp * kHalf, kHalf, xs(p.sm.x[0]), act, 0, row, gs(p.gm.G[0]), skip);
+        const bool more = (L > 0) || p.sem;
+        if (more) sync.end(true, nullptr, 0, 0);
+        if (p.sem && L == 4) emb_phase(true);
+        if (p.sem && L == 0) emb_phase(false);
+      }
+      // ---- label-embedding gradient: rows of one warp share a ray (hence a label) when n_samples % 32 == 0 ----
+      if (p.sem && grp == 0 && p.g_emb) {
+        int lab = -1;
+        if (valid && p.labels) { const int64_t l = p.labels[ray]; lab = (l == -100) ? -1 : (int)l; }   // padding row: no grad
+        const int lab0 = __shfl_sync(0xffffffffu, lab, 0);
+        const bool uniform = __all_sync(0xffffffffu, lab == lab0);
+        for (int e = 0; e < p.emb_dim; ++e) {
+          const float val = gemb[e] * inv_scale;
+          if (uniform) {
+            const float t = warp_sum(val);
+            if (lane == 0 && lab0 >= 0) atomicAdd(p.g_emb + lab0 * p.emb_dim + e, t);
+          } else if (lab >= 0) {
+            atomicAdd(p.g_emb + lab * p.emb_dim + e, val);
+          }
+        }
+      }
+      // the last epilogue of the tile sends no signal; the next tile's E_in does
+      tc_fence_before();
+      epi_bar_sync();
+    }
+    sync.finish();
+  }
+  (void)scratch;
+  teardown(tmem_base);
+}
+
+}  // namespace
+
+extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
+  if (!a || !a->g_out || !a->out || !a->rays || !a->blob || !a->steps || !a->small || !a->saves || !a->grad_saves ||
+      !a->g_absmax || !a->scale_out || !a->g_small_bias)
+    return SPNERF_ERR_BAD_ARG;
+  if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (a->cfg.sem && (!a->labels || !a->g_emb)) return SPNERF_ERR_BAD_ARG;
+  if (a->cfg.beta && !a->t_emb) return SPNERF_ERR_BAD_ARG;
+  if (a->n_rays <= 0 || a->n_samples < 1) return a->n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
+  BwdParams p;
+  p.g_out = a->g_out; p.out = a->out; p.rays = a->rays; p.labels = a->labels; p.t_emb = a->t_emb;
+  p.n_rays = a->n_rays; p.n_samples = a->n_samples; p.n_points = a->n_rays * a->n_samples;
+  p.blob = static_cast<const uint8_t*>(a->blob); p.steps = static_cast<const MmaStep*>(a->steps);
+  p.n_steps = a->n_steps; p.small = a->small;
+  p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg); p.gm = make_grad_map(a->cfg);
+  p.saves = static_cast<const uint8_t*>(a->saves); p.gsaves = static_cast<uint8_t*>(a->grad_saves);
+  p.absmax = a->g_absmax; p.scale_out = a->scale_out;
+  p.g_emb = a->g_emb; p.g_small_bias = a->g_small_bias; p.g_t_emb = a->g_t_emb;
+  const NetDims d = make_dims(a->cfg);
+  p.sem = a->cfg.sem; p.n_classes = a->cfg.num_sem_classes; p.emb_dim = a->cfg.emb_dim; p.beta = a->cfg.beta;
+  p.t_dim = a->cfg.t_dim; p.n_out = d.n_out; p.col_beta = d.col_beta; p.col_sem = d.col_sem;
+  p.debug = a->debug_flags;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return -(int)e;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  mlp_bwd_kernel<<<(unsigned)(n_tiles < sms ? n_tiles : sms), kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+SPNERF_DEFINE_WATCHDOG_GETTER(spnerf_watchdog_code_bwd)

@@ -13,11 +13,9 @@
 //               layer's A operand) and, when training, -> the activation save area
 // Phases alternate MMA and epilogue (handshake on two mbarriers); the step list built by
 // mlp_pack.cu fixes the order on both sides.
-#include "sm100.cuh"
-#include "net_plan.h"
+#include "mlp_roles.cuh"
 
-using namespace sm100;
-using namespace net;
+using namespace roles;
 
 namespace {
 
@@ -32,17 +30,6 @@ struct FwdParams {
   int debug;
 };
 
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
-constexpr int kEpiWarp0 = 4;
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // Process columns [j0, j0+ncols) of one accumulation chunk (whose column 0 sits at TMEM column tcol0)
 // for this thread's row:
@@ -99,111 +86,26 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* act = smem;
-  uint8_t* wst = smem + kNumSlabs * kSlabBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
-  uint64_t* bar_full = bars;          // [2]
-  uint64_t* bar_empty = bars + 2;     // [2]
-  uint64_t* bar_mma = bars + 4;       // MMA phase retired -> epilogue
-  uint64_t* bar_epi = bars + 5;       // epilogue phase done -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const Smem sh = carve(smem);
+  uint8_t* act = sh.act;
   float* scratch = reinterpret_cast<float*>(smem + kSlabInpLo * kSlabBytes);   // free after layer 0
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) { atomicCAS(&g_watchdog_code, 0u, 900u); __trap(); }
-    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-    mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
-    mbar_init(bar_mma, 1); mbar_init(bar_epi, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = setup(sh, smem);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
 
   if (warp == 0) {
-    // ---------------- weight producer ----------------
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < p.n_steps; ++s) {
-          const MmaStep st = p.steps[s];
-          mbar_wait(&bar_empty[stage], phase ^ 1, 10);
-          const uint32_t bytes = (uint32_t)st.n * 128u;
-          if (p.debug & 1) { mbar_arrive(&bar_full[stage]); }
-          else {
-            mbar_expect_tx(&bar_full[stage], bytes);
-            bulk_g2s(wst + stage * kWStageBytes, p.blob + (size_t)st.w_off16 * 16, bytes, &bar_full[stage]);
-          }
-          stage ^= 1; if (stage == 0) phase ^= 1;
-        }
-      }
-    }
+    if (lane == 0) producer_loop(sh, p.blob, p.steps, p.n_steps, n_tiles, p.debug);
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint64_t tmpl = make_smem_desc_template(16, 1024, kSwizzle128B);
-      const uint32_t act_addr = smem_u32(act), wst_addr = smem_u32(wst);
-      uint32_t stage = 0, phase = 0, epi_par = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int s = 0;
-        while (s < p.n_steps) {
-          mbar_wait(bar_epi, epi_par, 20); epi_par ^= 1;
-          tc_fence_after();
-          bool last;
-          do {
-            const MmaStep st = p.steps[s++];
-            last = st.last;
-            mbar_wait(&bar_full[stage], phase, 21);
-            tc_fence_after();
-            const uint32_t a0 = act_addr + (uint32_t)st.a_slab * kSlabBytes, b0 = wst_addr + stage * kWStageBytes;
-            const uint32_t idesc = make_idesc_f16(128, st.n, 0, 0);
-            for (uint32_t k = 0; k < ((p.debug & 4) ? 0u : st.ksteps); ++k)
-              umma_f16(tmem_base + st.tmem_col, smem_desc(tmpl, a0 + k * 32), smem_desc(tmpl, b0 + k * 32), idesc,
-                       (st.first && k == 0) ? 0u : 1u);
-            umma_commit(&bar_empty[stage]);
-            stage ^= 1; if (stage == 0) phase ^= 1;
-          } while (!last);
-          umma_commit(bar_mma);
-        }
-      }
-    }
+    if (lane == 0) mma_loop(sh, tmem_base, p.steps, p.n_steps, n_tiles, p.debug);
   } else if (warp >= kEpiWarp0) {
-    // ---------------- epilogue ----------------
-    const int ew = warp - kEpiWarp0;
-    const int grp = ew >> 2;                 // column half handled by this thread
-    const int row = (warp & 3) * 32 + lane;  // TMEM lane quarter = warp % 4
+    const int grp = (warp - kEpiWarp0) >> 2;   // column half handled by this thread
+    const int row = (warp & 3) * 32 + lane;    // TMEM lane quarter = warp % 4
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const bool issuer = (threadIdx.x == kEpiWarp0 * 32);
     const float* S = p.small;
-    uint32_t mma_par = 0;
-    bool stores_pending = false;
-
-    auto phase_begin = [&]() {
-      mbar_wait(bar_mma, mma_par, 30); mma_par ^= 1;
-      tc_fence_after();
-      if (stores_pending) {          // previous phase's bulk stores must have read their slabs
-        if (issuer) bulk_wait_read<0>();
-        epi_bar_sync();
-        stores_pending = false;
-      }
-    };
-    // writers: make st.shared visible to the async proxy, order TMEM reads, then release the MMA warp
+    EpiSync sync(sh);
+    auto phase_begin = [&]() { sync.begin(); };
     auto phase_end = [&](bool signal, uint8_t* save_dst, int slab0, int nslabs) {
-      fence_proxy_async_smem();
-      tc_fence_before();
-      epi_bar_sync();
-      if (issuer) {
-        if (signal) mbar_arrive(bar_epi);
-        if (save_dst) {
-          bulk_s2g(save_dst, act + slab0 * kSlabBytes, (uint32_t)nslabs * kSlabBytes);
-          bulk_commit();
-        }
-      }
-      if (save_dst) stores_pending = true;
+      sync.end(signal, save_dst, slab0, nslabs);
     };
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -215,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
       float* orow = p.out + pt * p.n_out;
 
       // ---- encoded input: [PE(xyz) | label embedding] as fp16 hi + residual ----
-      if (stores_pending) { if (issuer) bulk_wait_read<0>(); epi_bar_sync(); stores_pending = false; }
+      sync.drain_stores();
       float sun[3] = {0.f, 0.f, 0.f};
       {
         float q[3] = {0.f, 0.f, 0.f};
@@ -407,12 +309,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
       // no signal: the next tile's input phase releases the MMA warp (it also protects `scratch`)
       epi_bar_sync();
     }
-    if (issuer) bulk_wait_all<0>();
+    sync.finish();
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  teardown(tmem_base);
 }
 
 }  // namespace

@@ -68,12 +68,15 @@ struct Builder {
   std::vector<PackItem> items;
   uint32_t off16 = 0;
 
-  // one accumulation chunk: D[:, tmem_col : tmem_col+n] = sum over listed (a_slab, W column block)
-  // each entry: a_slab, col0 of W, ksteps, mode.  Rows row0..row0+n of W (non-transposed) form B.
-  struct Src { int a_slab, col0, ksteps, mode; };
+  // one accumulation chunk: D[:, tmem_col : tmem_col+n] (+)= sum over the listed sources.
+  // Each source names the A slab, the K offset inside its weight matrix, the K=16 steps to issue and
+  // the pack mode; a source may bring its own weight matrix (several layers feeding one accumulator).
+  // Forward (transpose=false): B tile row i <-> W row row0+i, tile col k <-> W col col0+k.
+  // Backward (transpose=true): B tile row i <-> W col row0+i (an input unit), col k <-> W row col0+k.
+  struct Src { int a_slab, col0, ksteps, mode; const float* W = nullptr; int rows = 0, cols = 0; };
   void chunk(const float* W, int rows, int cols, int row0, int n, int tmem_col, const std::vector<Src>& srcs,
-             bool transpose = false) {
-    bool first = true;
+             bool transpose = false, bool accumulate_all = false) {
+    bool first = !accumulate_all;
     for (const Src& s : srcs) {
       MmaStep st{};
       st.w_off16 = off16;
@@ -85,7 +88,8 @@ struct Builder {
       st.last = 0;
       steps.push_back(st);
       PackItem it{};
-      it.src = W; it.ld = cols; it.rows = rows; it.cols = cols;
+      const bool own = s.rows > 0;
+      it.src = own ? s.W : W; it.ld = own ? s.cols : cols; it.rows = own ? s.rows : rows; it.cols = own ? s.cols : cols;
       it.row0 = transpose ? s.col0 : row0;
       it.col0 = transpose ? row0 : s.col0;
       it.transpose = transpose ? 1 : 0;
@@ -190,6 +194,7 @@ extern "C" int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* s) {
   s->small_floats = make_small_offsets(*cfg).total;
   s->steps_bytes = (int64_t)kMaxSteps * sizeof(MmaStep);
   s->save_slabs_per_tile = make_save_map(*cfg).total;
+  s->grad_slabs_per_tile = make_grad_map(*cfg).total;
   const NetDims d = make_dims(*cfg);
   s->n_out = d.n_out;
   s->in_dim = d.in_dim;
@@ -345,9 +350,152 @@ extern "C" int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward-data order (filled in with mlp_bwd.cu)
+// backward-data order; must match the phase sequence of mlp_bwd.cu.  Gradient tiles are the A
+// operands, transposed weights the B operands: g_in[n] = sum_k G[k] * W[k][n].
 // ------------------------------------------------------------------------------------------------
 void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
                     std::vector<PackItem>* items, uint32_t* off16) {
-  (void)c; (void)P; (void)steps; (void)items; (void)off16;
+  Builder b;
+  const NetDims d = make_dims(c);
+  const int base = c.mapping ? 60 : 3;
+  using Src = Builder::Src;
+  auto ks = [](int first_slab, int nslabs) {
+    std::vector<Src> v;
+    for (int k = 0; k < nslabs; ++k) v.push_back(Src{first_slab + k, 64 * k, 4, 0});
+    return v;
+  };
+  // sun_v_net.4 and .2 (256x256): G_s3 -> g_s2 -> g_s1
+  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, ks(0, 4), true);
+  b.end_phase();
+  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, ks(0, 4), true);
+  b.end_phase();
+  // g_f = G_s1 * W_sun0[:, :512] + G_r1 * W_rgb0 (+ G_b1 * W_beta0[:, :512] in a second phase)
+  for (int g = 0; g < 2; ++g) {
+    std::vector<Src> v;
+    for (int k = 0; k < 4; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SUN0_W], kHalf, kFeat + 3});
+    for (int k = 0; k < 4; ++k) v.push_back(Src{4 + k, 64 * k, 4, 0, P[SPNERF_P_RGB0_W], kHalf, kFeat});
+    b.chunk(nullptr, 0, 0, g * kHalf, kHalf, g * kHalf, v, true);
+  }
+  b.end_phase();
+  if (c.beta) {
+    for (int g = 0; g < 2; ++g)
+      b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, g * kHalf, kHalf, g * kHalf, ks(0, 4), true, true);
+    b.end_phase();
+  }
+  // g_h = g_f * W_feats (+ G_sem1 * W_sem0 + g_sigma_pre * W_sigma accumulated in the next phase)
+  for (int g = 0; g < 2; ++g)
+    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, ks(0, 8), true);
+  b.end_phase();
+  for (int g = 0; g < 2; ++g) {
+    std::vector<Src> v;
+    if (c.sem)
+      for (int k = 0; k < 4; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SEM0_W], kHalf, kFeat});
+    v.push_back(Src{4, 0, 1, 0, P[SPNERF_P_SIGMA_W], 1, kFeat});
+    b.chunk(nullptr, 0, 0, g * kHalf, kHalf, g * kHalf, v, true, true);
+  }
+  b.end_phase();
+  // trunk, layers 7..1; the label-embedding columns of the skip layer and of layer 0 get their own
+  // 16-wide mini phases (only when the embedding exists)
+  for (int L = 7; L >= 1; --L) {
+    const bool skip = (L == c.skip_layer);
+    const int cols = kFeat + (skip ? d.in_dim : 0);
+    if (skip && c.sem) {
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, kFeat + base, 16, 0, ks(0, 8), true);
+      b.end_phase();
+    }
+    for (int g = 0; g < 2; ++g)
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, g * kHalf, kHalf, g * kHalf, ks(0, 8), true);
+    b.end_phase();
+  }
+  if (c.sem) {
+    b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, base, 16, 0, ks(0, 8), true);
+    b.end_phase();
+  }
+  steps = b.steps;
+  if (items) *items = b.items;
+  *off16 = b.off16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sky colour backward (adjoint of sky_fwd_kernel): one warp per ray, 8 hidden units per lane,
+// register accumulation over the warp's rays, then shared-memory and global atomics.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) sky_bwd_kernel(const float* __restrict__ small, SmallOffsets o,
+                                                      const float* __restrict__ rays, const float* __restrict__ sky,
+                                                      const float* __restrict__ hidden, const float* __restrict__ g_sky,
+                                                      int64_t n_rays, float* g_w0, float* g_b0, float* g_w2,
+                                                      float* g_b2) {
+  __shared__ float acc[3 * kHalf + kHalf + 3 * kHalf + 4];   // w0 [256][3] | b0 [256] | w2 [3][256] | b2
+  for (int i = threadIdx.x; i < 7 * kHalf + 4; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float aw0[8][3], ab0[8], aw2[3][8], ab2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    ab0[u] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { aw0[u][c] = 0.f; aw2[c][u] = 0.f; }
+  }
+  for (int64_t r = warp; r < n_rays; r += nwarps) {
+    float gp[3], s[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float y = sky[r * 3 + c];
+      gp[c] = g_sky[r * 3 + c] * y * (1.f - y);
+      s[c] = rays[r * 11 + 8 + c];
+      ab2[c] += gp[c];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = u * 32 + lane;
+      const float h = hidden[r * kHalf + j];
+      float gh = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        aw2[c][u] = fmaf(gp[c], h, aw2[c][u]);
+        gh = fmaf(gp[c], small[o.sky2_w + c * kHalf + j], gh);
+      }
+      gh = h > 0.f ? gh : 0.f;
+      ab0[u] += gh;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) aw0[u][c] = fmaf(gh, s[c], aw0[u][c]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = u * 32 + lane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(&acc[j * 3 + c], aw0[u][c]);
+      atomicAdd(&acc[4 * kHalf + c * kHalf + j], aw2[c][u]);
+    }
+    atomicAdd(&acc[3 * kHalf + j], ab0[u]);
+  }
+  if (lane == 0)
+    for (int c = 0; c < 3; ++c) atomicAdd(&acc[7 * kHalf + c], ab2[c]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * kHalf; i += blockDim.x) {
+    atomicAdd(g_w0 + i, acc[i]);
+    atomicAdd(g_w2 + i, acc[4 * kHalf + i]);
+  }
+  for (int i = threadIdx.x; i < kHalf; i += blockDim.x) atomicAdd(g_b0 + i, acc[3 * kHalf + i]);
+  if (threadIdx.x < 3) atomicAdd(g_b2 + threadIdx.x, acc[7 * kHalf + threadIdx.x]);
+}
+}  // namespace
+
+extern "C" int spnerf_sky_bwd(const float* small, const SpnerfNetConfig* cfg, const float* rays, const float* sky,
+                              const float* hidden, const float* g_sky, int64_t n_rays, float* g_w0, float* g_b0,
+                              float* g_w2, float* g_b2, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!small || !rays || !sky || !hidden || !g_sky || !g_w0 || !g_b0 || !g_w2 || !g_b2) return SPNERF_ERR_BAD_ARG;
+  if (n_rays <= 0) return n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
+  const int64_t blocks = (n_rays + 63) / 64;     // >= 8 rays per warp
+  sky_bwd_kernel<<<(unsigned)(blocks > 148 ? 148 : blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      small, make_small_offsets(*cfg), rays, sky, hidden, g_sky, n_rays, g_w0, g_b0, g_w2, g_b2);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
 }

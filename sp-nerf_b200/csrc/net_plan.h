@@ -62,6 +62,17 @@ struct SaveMap {
   int total;
 };
 
+// Per-tile gradient save area written by the backward-data kernel, in slabs: every entry is a
+// pre-activation gradient tile (fp16, scaled), the A operand of one weight-gradient GEMM.
+struct GradMap {
+  int G[8];        // trunk layers                         8 slabs each
+  int g_f;         // feats_from_xyz output gradient       8 slabs
+  int G_sem, G_rgb, G_beta;   // 256-wide hidden layers    4 slabs each (-1 if absent)
+  int G_sun[3];
+  int gsmall;      // [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8), 0...]   1 slab
+  int total;
+};
+
 struct NetDims {
   int in_dim;      // encoded xyz (3 or 60) + emb_dim
   int in_ksteps;   // K=16 steps covering in_dim
@@ -91,6 +102,19 @@ inline SaveMap make_save_map(const SpnerfNetConfig& c) {
   m.rgb_x = four(true); m.rgb_y = four(true);
   m.beta_x = four(c.beta); m.beta_y = four(c.beta);
   for (int i = 0; i < 3; ++i) { m.sun_x[i] = four(true); m.sun_y[i] = four(true); }
+  m.total = s;
+  return m;
+}
+
+inline GradMap make_grad_map(const SpnerfNetConfig& c) {
+  GradMap m;
+  int s = 0;
+  for (int i = 0; i < 8; ++i) { m.G[i] = s; s += 8; }
+  m.g_f = s; s += 8;
+  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += 4; return r; };
+  m.G_sem = four(c.sem); m.G_rgb = four(true); m.G_beta = four(c.beta);
+  for (int i = 0; i < 3; ++i) m.G_sun[i] = four(true);
+  m.gsmall = s++;
   m.total = s;
   return m;
 }

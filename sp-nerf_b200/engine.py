@@ -1,6 +1,8 @@
 """Device-side state of one SPNeRF module: packed tensor-core operands, step tables and the
-workspace buffers the C ABI needs.  PyTorch is used here only for device memory and streams."""
+workspace buffers the C ABI needs, plus thin wrappers over every kernel entry point.
+PyTorch is used here only for device memory and streams."""
 import ctypes
+import math
 
 import torch
 
@@ -10,16 +12,148 @@ SLAB_BYTES = 16384
 TILE = 128
 
 
-def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+def _p(t):
+    return t.data_ptr() if t is not None else None
 
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _require_cuda(t, what):
+    if t.device.type != "cuda":
+        raise _cabi.SpnerfError(f"{what} must live on a CUDA device: spnerf_b200 has no CPU path")
+
+
+_tables = {}
+
+
+def sampler_tables(n, device):
+    """torch.linspace(0,1,n) and the Gaussian bin weights of modules/rendering.py:60,68-70, computed by
+    torch on the host exactly as the reference does, so the device kernels reproduce its bits."""
+    key = (n, str(device))
+    if key not in _tables:
+        t = torch.linspace(0, 1, n)
+        x = torch.linspace(-3., 3., steps=(n - 1))
+        g = (1. / math.sqrt(2 * math.pi) * torch.exp(-0.5 * x.pow(2)))
+        _tables[key] = (t.to(device).contiguous(), g.to(device).contiguous())
+    return _tables[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# model-independent kernels
+# ------------------------------------------------------------------------------------------------
+def sample_coarse(rays, uniforms, n):
+    """modules/rendering.py:128-144."""
+    _require_cuda(rays, "rays")
+    t_tab, _ = sampler_tables(n, rays.device)
+    z = torch.empty(rays.shape[0], n, dtype=torch.float32, device=rays.device)
+    _cabi.check(_cabi.lib().spnerf_sample_coarse(_p(rays), _p(t_tab), _p(uniforms), rays.shape[0], n, _p(z), _stream()),
+                "spnerf_sample_coarse")
+    return z
+
+
+def sample_guided(rays, z, weights, depth, u_pred, valid_depth=None, target_depths=None, target_std=None, u_gt=None,
+                  want_indices=False):
+    """modules/rendering.py:92-116 + :165-167.  Returns (z_unsort (B,2N), z_sorted (B,2N)[, indices])."""
+    b, n = z.shape
+    t_tab, g_tab = sampler_tables(n, rays.device)
+    z_unsort = torch.empty(b, 2 * n, dtype=torch.float32, device=rays.device)
+    z_sorted = torch.empty(b, 2 * n, dtype=torch.float32, device=rays.device)
+    inds = torch.empty(b, n, dtype=torch.int32, device=rays.device) if want_indices else None
+    a = _cabi.Guided()
+    a.rays, a.z, a.weights, a.depth = _p(rays), _p(z), _p(weights), _p(depth)
+    a.valid_depth = _p(valid_depth)
+    if valid_depth is not None:
+        if target_depths.dim() == 2:
+            if target_depths.stride(1) != 1:
+                target_depths = target_depths.contiguous()
+            a.target_depth, a.target_depth_stride = _p(target_depths), target_depths.stride(0)
+        else:
+            a.target_depth, a.target_depth_stride = _p(target_depths), target_depths.stride(0)
+        a.target_std, a.u_gt = _p(target_std), _p(u_gt)
+    a.u_pred, a.t_table, a.gauss_table = _p(u_pred), _p(t_tab), _p(g_tab)
+    a.n_rays, a.n_samples = b, n
+    a.z_unsort, a.z_sorted, a.searchsorted_out = _p(z_unsort), _p(z_sorted), _p(inds)
+    _cabi.check(_cabi.lib().spnerf_sample_guided(ctypes.byref(a), _stream()), "spnerf_sample_guided")
+    return (z_unsort, z_sorted, inds) if want_indices else (z_unsort, z_sorted)
+
+
+def composite_fwd(out, z, n_out, col_sem, n_sem, noise=None, noise_std=0.0, want_raw=True):
+    """models/spnerf.py:109-157."""
+    b, n = z.shape
+    dev = z.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    weights, trans = torch.empty(b, n, **f32), torch.empty(b, n, **f32)
+    rgb, depth = torch.empty(b, 3, **f32), torch.empty(b, **f32)
+    rgb_raw = torch.empty(b, 3, **f32) if want_raw else None
+    sem = torch.empty(b, n_sem, **f32) if n_sem > 0 else None
+    a = _cabi.CompositeFwd()
+    a.out, a.z, a.noise = _p(out), _p(z), _p(noise)
+    a.n_rays, a.n_samples, a.n_out, a.col_sem, a.n_sem, a.noise_std = b, n, n_out, max(col_sem, 0), n_sem, noise_std
+    a.weights, a.transparency, a.rgb, a.rgb_raw, a.depth, a.sem_logits = \
+        _p(weights), _p(trans), _p(rgb), _p(rgb_raw), _p(depth), _p(sem)
+    _cabi.check(_cabi.lib().spnerf_composite_fwd(ctypes.byref(a), _stream()), "spnerf_composite_fwd")
+    return weights, trans, rgb, rgb_raw, depth, sem
+
+
+def composite_bwd(out, z, weights, trans, rgb_raw, n_out, col_sem, n_sem, g_rgb=None, g_depth=None, g_sem=None,
+                  g_w=None, g_t=None, g_out_ext=None, noise=None, noise_std=0.0):
+    """Adjoint of composite_fwd.  Returns (g_out, g_sky_ray, absmax scalar)."""
+    b, n = z.shape
+    dev = z.device
+    g_out = torch.empty(b * n, n_out, dtype=torch.float32, device=dev)
+    g_sky = torch.empty(b, 3, dtype=torch.float32, device=dev)
+    absmax = torch.zeros(1, dtype=torch.float32, device=dev)
+    a = _cabi.CompositeBwd()
+    a.out, a.z, a.noise, a.weights, a.transparency, a.rgb_raw = _p(out), _p(z), _p(noise), _p(weights), _p(trans), \
+        _p(rgb_raw)
+    a.g_rgb, a.g_depth, a.g_sem_logits, a.g_weights, a.g_transparency, a.g_out_ext = \
+        _p(g_rgb), _p(g_depth), _p(g_sem), _p(g_w), _p(g_t), _p(g_out_ext)
+    a.n_rays, a.n_samples, a.n_out, a.col_sem, a.n_sem, a.noise_std = b, n, n_out, max(col_sem, 0), n_sem, noise_std
+    a.g_out, a.g_sky_ray, a.g_absmax = _p(g_out), _p(g_sky), _p(absmax)
+    _cabi.check(_cabi.lib().spnerf_composite_bwd(ctypes.byref(a), _stream()), "spnerf_composite_bwd")
+    return g_out, g_sky, absmax
+
+
+_loss_ws = {}
+
+
+def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, target_depth=None,
+           target_weight=None, target_std=None, valid_depth=None, lambda_ds=0.0, use_all_depth=False,
+           sem_logits=None, labels=None, lambda_ss=0.0):
+    """Fused loss reductions + gradients (modules/metrics.py:27-45, 68-159, 162-183).
+    Returns (scalars (8,), g_rgb, g_depth, g_sem_logits)."""
+    ref = rgb if rgb is not None else (depth if depth is not None else sem_logits)
+    dev = ref.device
+    _require_cuda(ref, "loss inputs")
+    if dev not in _loss_ws:
+        _loss_ws[dev] = torch.empty(int(_cabi.lib().spnerf_losses_workspace_bytes()), dtype=torch.uint8, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = torch.empty(8, **f32)
+    g_rgb = torch.empty_like(rgb) if rgb is not None else None
+    g_depth = torch.empty_like(depth) if depth is not None else None
+    g_sem = torch.empty_like(sem_logits) if sem_logits is not None else None
+    a = _cabi.Losses()
+    a.n_rays = n_rays
+    a.n_samples = z.shape[1] if z is not None else 0
+    a.n_sem = sem_logits.shape[1] if sem_logits is not None else 0
+    a.rgb, a.rgb_target, a.g_rgb = _p(rgb), _p(rgb_target), _p(g_rgb)
+    a.depth, a.z, a.weights = _p(depth), _p(z), _p(weights)
+    a.target_depth, a.target_weight, a.target_std, a.valid_depth = \
+        _p(target_depth), _p(target_weight), _p(target_std), _p(valid_depth)
+    a.lambda_ds, a.use_all_depth, a.g_depth = lambda_ds, 1 if use_all_depth else 0, _p(g_depth)
+    a.sem_logits, a.labels, a.lambda_ss, a.g_sem_logits = _p(sem_logits), _p(labels), lambda_ss, _p(g_sem)
+    a.losses, a.workspace = _p(out), _p(_loss_ws[dev])
+    _cabi.check(_cabi.lib().spnerf_losses(ctypes.byref(a), _stream()), "spnerf_losses")
+    return out, g_rgb, g_depth, g_sem
+
+
+# ------------------------------------------------------------------------------------------------
+# per-model state
+# ------------------------------------------------------------------------------------------------
 class NetEngine:
-    """Packed operands for the fused point-network kernels (include/spnerf_b200.h)."""
+    """Packed operands and workspaces for the fused point-network kernels (include/spnerf_b200.h)."""
 
     def __init__(self, module):
         self.module = module
@@ -32,22 +166,27 @@ class NetEngine:
         _cabi.check(_cabi.lib().spnerf_net_sizes(ctypes.byref(self.cfg), ctypes.byref(self.sizes)),
                     "spnerf_net_sizes (only fc_units=512, fc_layers=8, skip 4, encoded input <= 64 are built)")
         self.n_out = self.sizes.n_out
+        self.col_sem = 8 + (1 if module.beta else 0) if module.sem else -1
+        self.n_sem = module.num_sem_classes if module.sem else 0
+        self.col_beta = 8 if module.beta else -1
         self.device = None
         self._packed_key = None
+        self._grad_key = None
+        self.names = [n for n, _ in module.named_parameters()]
 
     # -- buffers ------------------------------------------------------------------------------
     def _alloc(self, device):
         s = self.sizes
         self.device = device
-        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16), dtype=torch.uint8, device=device)
-        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16), dtype=torch.uint8, device=device)
+        u8 = dict(dtype=torch.uint8, device=device)
+        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16), **u8)
+        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16), **u8)
         self.small = torch.empty(int(s.small_floats), dtype=torch.float32, device=device)
-        self.fwd_steps = torch.empty(int(s.steps_bytes), dtype=torch.uint8, device=device)
-        self.bwd_steps = torch.empty(int(s.steps_bytes), dtype=torch.uint8, device=device)
+        self.fwd_steps = torch.empty(int(s.steps_bytes), **u8)
+        self.bwd_steps = torch.empty(int(s.steps_bytes), **u8)
+        self.wgrad_ws = torch.empty(int(_cabi.lib().spnerf_mlp_wgrad_workspace_bytes(ctypes.byref(self.cfg))), **u8)
         self._packed_key = None
-
-    def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+        self._grad_key = None
 
     def ensure_packed(self):
         """(Re)pack the fp32 parameters if any of them changed since the last pack."""
@@ -57,7 +196,7 @@ class NetEngine:
             raise _cabi.SpnerfError("spnerf_b200 runs on CUDA devices only (no CPU path); move the model to cuda")
         if self.device != dev:
             self._alloc(dev)
-        key = self._param_key()
+        key = tuple((p.data_ptr(), p._version) for p in params.values())
         if key == self._packed_key:
             return
         table = (ctypes.c_void_p * _cabi.NUM_PARAMS)()
@@ -65,23 +204,24 @@ class NetEngine:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise _cabi.SpnerfError(f"parameter {name} must be contiguous fp32")
             table[_cabi.PARAM_SLOTS[name]] = p.data_ptr()
-        has_bwd = self.sizes.bwd_blob_bytes > 0
         _cabi.check(_cabi.lib().spnerf_net_pack(
-            ctypes.byref(self.cfg), table, _ptr(self.fwd_blob), _ptr(self.bwd_blob) if has_bwd else None,
-            _ptr(self.small), _ptr(self.fwd_steps), _ptr(self.bwd_steps) if has_bwd else None, _stream()),
-            "spnerf_net_pack")
+            ctypes.byref(self.cfg), table, _p(self.fwd_blob), _p(self.bwd_blob), _p(self.small), _p(self.fwd_steps),
+            _p(self.bwd_steps), _stream()), "spnerf_net_pack")
         self._packed_key = key
 
-    # -- kernels ------------------------------------------------------------------------------
     def save_bytes(self, n_points):
         return ((n_points + TILE - 1) // TILE) * self.sizes.save_slabs_per_tile * SLAB_BYTES
 
+    def grad_save_bytes(self, n_points):
+        return ((n_points + TILE - 1) // TILE) * self.sizes.grad_slabs_per_tile * SLAB_BYTES
+
+    # -- forward ------------------------------------------------------------------------------
     def sky(self, rays):
         n = rays.shape[0]
         sky = torch.empty(n, 3, dtype=torch.float32, device=rays.device)
         hidden = torch.empty(n, 256, dtype=torch.float32, device=rays.device)
-        _cabi.check(_cabi.lib().spnerf_sky_fwd(_ptr(self.small), ctypes.byref(self.cfg), _ptr(rays), n, _ptr(sky),
-                                               _ptr(hidden), _stream()), "spnerf_sky_fwd")
+        _cabi.check(_cabi.lib().spnerf_sky_fwd(_p(self.small), ctypes.byref(self.cfg), _p(rays), n, _p(sky),
+                                               _p(hidden), _stream()), "spnerf_sky_fwd")
         return sky, hidden
 
     def forward(self, rays, n_samples, z=None, xyz=None, dir_override=None, labels=None, t_emb=None, sky=None,
@@ -96,16 +236,81 @@ class NetEngine:
         saves = torch.empty(self.save_bytes(n_points), dtype=torch.uint8, device=rays.device) if save else None
         a = _cabi.MlpFwd()
         a.cfg = self.cfg
-        a.rays, a.z, a.xyz = rays.data_ptr(), (z.data_ptr() if z is not None else None), \
-            (xyz.data_ptr() if xyz is not None else None)
-        a.dir_override = dir_override.data_ptr() if dir_override is not None else None
-        a.labels = labels.data_ptr() if labels is not None else None
-        a.t_emb = t_emb.data_ptr() if t_emb is not None else None
-        a.sky = sky.data_ptr()
+        a.rays, a.z, a.xyz, a.dir_override = _p(rays), _p(z), _p(xyz), _p(dir_override)
+        a.labels, a.t_emb, a.sky = _p(labels), _p(t_emb), _p(sky)
         a.n_rays, a.n_samples, a.n_steps = n_rays, n_samples, self.sizes.fwd_steps
-        a.blob, a.steps, a.small = self.fwd_blob.data_ptr(), self.fwd_steps.data_ptr(), self.small.data_ptr()
-        a.out = out.data_ptr()
-        a.saves = saves.data_ptr() if saves is not None else None
-        a.debug_flags = debug_flags
+        a.blob, a.steps, a.small = _p(self.fwd_blob), _p(self.fwd_steps), _p(self.small)
+        a.out, a.saves, a.debug_flags = _p(out), _p(saves), debug_flags
         _cabi.check(_cabi.lib().spnerf_mlp_fwd(ctypes.byref(a), _stream()), "spnerf_mlp_fwd")
         return out, saves
+
+    # -- backward -----------------------------------------------------------------------------
+    def _views(self, flat):
+        views, off = [], 0
+        for p in self.module.parameters():
+            views.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return views
+
+    def _grad_buffer(self):
+        """Persistent flat fp32 buffer shaped like the parameters: the kernels write into it (its
+        address is baked into the weight-gradient scatter tables); callers get a copy."""
+        n = sum(p.numel() for p in self.module.parameters())
+        if getattr(self, "_gflat", None) is None or self._gflat.device != self.device or self._gflat.numel() != n:
+            self._gflat = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._grad_key = None
+        return self._gflat
+
+    def backward(self, g_out, out, rays, n_samples, saves, absmax, labels=None, t_emb=None, g_sky_ray=None,
+                 sky=None, sky_hidden=None, debug_flags=0):
+        """All parameter gradients (+ d t_emb) from dL/d out.  Returns (flat, views, g_t_emb)."""
+        n_rays = rays.shape[0]
+        n_points = n_rays * n_samples
+        dev = rays.device
+        work = self._grad_buffer()
+        work.zero_()                      # some slots are accumulated into with atomics
+        by_name = dict(zip(self.names, self._views(work)))
+        gsaves = torch.empty(self.grad_save_bytes(n_points), dtype=torch.uint8, device=dev)
+        scale = torch.empty(1, dtype=torch.float32, device=dev)
+        small_bias = torch.zeros(16, dtype=torch.float32, device=dev)
+        g_t = torch.zeros(n_rays, self.cfg.t_dim, dtype=torch.float32, device=dev) if t_emb is not None else None
+        a = _cabi.MlpBwd()
+        a.cfg = self.cfg
+        a.g_out, a.out, a.rays, a.labels, a.t_emb = _p(g_out), _p(out), _p(rays), _p(labels), _p(t_emb)
+        a.n_rays, a.n_samples, a.n_steps = n_rays, n_samples, self.sizes.bwd_steps
+        a.blob, a.steps, a.small = _p(self.bwd_blob), _p(self.bwd_steps), _p(self.small)
+        a.saves, a.grad_saves, a.g_absmax, a.scale_out = _p(saves), _p(gsaves), _p(absmax), _p(scale)
+        a.g_emb = _p(by_name.get("semantic_embedding.weight"))
+        a.g_small_bias, a.g_t_emb, a.debug_flags = _p(small_bias), _p(g_t), debug_flags
+        _cabi.check(_cabi.lib().spnerf_mlp_bwd_data(ctypes.byref(a), _stream()), "spnerf_mlp_bwd_data")
+
+        w = _cabi.MlpWgrad()
+        w.cfg = self.cfg
+        w.n_points, w.saves, w.grad_saves, w.scale = n_points, _p(saves), _p(gsaves), _p(scale)
+        table = (ctypes.c_void_p * _cabi.NUM_PARAMS)()
+        for name, v in by_name.items():
+            table[_cabi.PARAM_SLOTS[name]] = v.data_ptr()
+        w.grads_host = table
+        w.workspace, w.workspace_bytes = _p(self.wgrad_ws), self.wgrad_ws.numel()
+        # the scatter tables embed the gradient pointers: uploaded once per gradient buffer
+        key = (work.data_ptr(), self.wgrad_ws.data_ptr())
+        if key != self._grad_key:
+            _cabi.check(_cabi.lib().spnerf_mlp_wgrad_prepare(ctypes.byref(w), _stream()), "spnerf_mlp_wgrad_prepare")
+            self._grad_key = key
+        _cabi.check(_cabi.lib().spnerf_mlp_bwd_weights(ctypes.byref(w), _stream()), "spnerf_mlp_bwd_weights")
+
+        # biases of the tiny last layers were reduced by the backward-data kernel
+        by_name["rgb_from_xyzdir.2.bias"].copy_(small_bias[0:3])
+        by_name["sun_v_net.6.bias"].copy_(small_bias[3:4])
+        by_name["sigma_from_xyz.0.bias"].copy_(small_bias[4:5])
+        if self.module.beta:
+            by_name["beta_from_xyz.2.bias"].copy_(small_bias[5:6])
+        if self.module.sem:
+            by_name["logit_from_label.2.bias"].copy_(small_bias[6:6 + self.n_sem])
+        if g_sky_ray is not None:
+            _cabi.check(_cabi.lib().spnerf_sky_bwd(
+                _p(self.small), ctypes.byref(self.cfg), _p(rays), _p(sky), _p(sky_hidden), _p(g_sky_ray), n_rays,
+                _p(by_name["sky_color.0.weight"]), _p(by_name["sky_color.0.bias"]),
+                _p(by_name["sky_color.2.weight"]), _p(by_name["sky_color.2.bias"]), _stream()), "spnerf_sky_bwd")
+        flat = work.clone()
+        return flat, self._views(flat), g_t
