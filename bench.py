@@ -1,0 +1,348 @@
+"""Benchmark of the SP-NeRF ray-rendering hot path (BASELINE.json metric: render_rays fwd+bwd rays/s
+at 1/2/4/8 B200, + fraction of the MLP tensor-core and compositing HBM rooflines).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload at every N: BASELINE config 2 per GPU — a training step (forward + backward, --depth --sem,
+3 semantic classes, dense labels) on a JAX_269-shaped synthetic batch of 8192 rays x 64 samples
+(weak scaling: 8192 rays per rank).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 8192
+N_SAMPLES = 64
+# algorithmic work of the point network (in=6, C=3): FLOP per sample point
+FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 5_264_384, 5_249_024, 5_264_384
+# algorithmic bytes per ray of compositing (N=64, C=3, fp32)
+BYTES_COMP_FWD, BYTES_COMP_BWD = 3612, 5660
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][2]) if self.rows and self.rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_args():
+    from oracle import spnerf_oracle as O     # configuration container only
+    return types.SimpleNamespace(**vars(O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)))
+
+
+def build_model(args, device):
+    import torch
+    from spnerf_b200.models import load_model
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():                      # "trained-like" density so the transmittance scan is exercised
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(8.0)
+    return model.to(device)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port), bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(P, cfg, batch, O, torch):
+    b, n = batch["rays"].shape[0], cfg.n_samples
+    draws = O.Draws([torch.rand(b, n)], [torch.randn(b, n)])
+    res = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
+                   batch["depth_std"], draws)
+    loss = O.colour_loss(res, batch["rgbs"])[0] + O.depth_loss(
+        res, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0] \
+        + O.semantic_loss(res, batch["sems"], 1.0)[0]
+    grads = torch.autograd.grad(loss, list(P.values()))
+    return float(loss), grads
+
+
+def time_cpu_reference(rays, steps, warmup):
+    import torch
+    from oracle import spnerf_oracle as O
+    from spnerf_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)
+    P = {k: v.requires_grad_(True) for k, v in O.random_parameters(cfg, seed=0, sigma_bias=3.0).items()}
+    batch = synthetic.make_batch(rays, seed=269)
+    for _ in range(warmup):
+        cpu_reference_step(P, cfg, batch, O, torch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(P, cfg, batch, O, torch)
+    dt = time.perf_counter() - t0
+    return rays * steps / dt, dt / steps, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_rays = 512
+    steps, warmup = max(1, min(a.steps, 6)), max(1, min(a.warmup, 2))
+    rps, sec, cores = time_cpu_reference(sample_rays, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "render_rays_fwd_bwd_rays_per_s", "value": rps, "unit": "rays/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: training step fwd+bwd, --depth --sem C=3, 64 samples, fc 8x512; "
+                               f"reference CPU path on a bounded sample of {sample_rays} rays per step",
+                   "rays_per_step": sample_rays},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {sample_rays} rays x {N_SAMPLES} samples, fwd+losses+bwd, torch "
+                                   f"fp32 on {cores} host threads (oracle restatement of the reference; the Python "
+                                   "reference itself cannot travel to the GPU box)"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this framework
+# --------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import spnerf_b200
+    from spnerf_b200 import engine as E, parallel, synthetic, train_step
+    from spnerf_b200.modules import metrics
+    from spnerf_b200.modules.rendering import render_rays
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    args = make_args()
+    model = build_model(args, dev)
+    host_batch = {k: v.pin_memory() for k, v in synthetic.make_batch(RAYS_PER_GPU, seed=269 + rank).items()}
+    batch = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
+    reduce_fn = parallel.allreduce_mean_ if world > 1 else None
+
+    def step(timer=None):
+        return train_step.fused_step(model, args, batch, repack=True, timer=timer, allreduce=reduce_fn)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        _, _, scalars, launches = step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        _, _, scalars, launches = step()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    value = world * RAYS_PER_GPU * a.steps / (ms_total / 1e3)
+    loss_vals = [float(x) for x in scalars[:3]]
+
+    # ---- per-kernel durations (CUDA events on the launching stream), same steps ----
+    kern = {}
+    prof_steps = max(3, min(a.steps, 10))
+    for _ in range(prof_steps):
+        t = train_step.StepTimer(True)
+        step(t)
+        torch.cuda.synchronize()
+        for k, v in t.durations_ms().items():
+            kern[k] = kern.get(k, 0.0) + v / prof_steps
+    points = RAYS_PER_GPU * N_SAMPLES
+    flop = {"mlp_fwd": FLOP_FWD * points, "mlp_bwd_data": FLOP_DGRAD * points, "mlp_bwd_weights": FLOP_WGRAD * points}
+    tc = {k: flop[k] / (kern[k] * 1e-3) / 1e12 for k in flop}
+    dominant = max(flop, key=lambda k: kern[k])
+    mlp_ms = sum(kern[k] for k in flop)
+    mlp_tflops = sum(flop.values()) / (mlp_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dominant)
+    roofline = {"bound": "tensor", "kernel": dominant, "achieved": tc[dominant], "peak": pk["tc_sustained"],
+                "unit": "TFLOP/s", "frac": tc[dominant] / pk["tc_sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + ": sustained fp16/bf16 dense GEMM (kernel timed inside a long step)",
+                "frac_of_burst_peak": tc[dominant] / pk["tc_burst"],
+                "mlp_all_kernels": {"achieved": mlp_tflops, "frac": mlp_tflops / pk["tc_sustained"],
+                                    "frac_of_burst_peak": mlp_tflops / pk["tc_burst"], "ms": mlp_ms,
+                                    "flop_per_step": sum(flop.values())},
+                "per_kernel_tflops": tc}
+
+    line = {
+        "metric": "render_rays_fwd_bwd_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: SP-NeRF training step (fwd+bwd), JAX_269-shaped batch, "
+                               "--depth --sem --num_sem_classes 3 --dense_ss, fc 8x512, 64 samples, n_importance 0",
+                   "rays_per_gpu": RAYS_PER_GPU, "global_rays": world * RAYS_PER_GPU, "n_samples": N_SAMPLES,
+                   "parallelism": f"ray-sharded dp{world}, one NCCL all-reduce of the flat fp32 gradient per step",
+                   "l2": "each step streams ~23 GB of saved activations / gradient tiles (>> 126 MB L2); no flush needed",
+                   "step": "weight repack, sampling, fused MLP fwd, compositing, losses, adjoints, dgrad, wgrad"
+                           + (", gradient all-reduce" if world > 1 else "")},
+        "gpu_launches": launches * a.steps,
+        "loss": {"color": loss_vals[0], "depth": loss_vals[1], "semantic": loss_vals[2]},
+        "kernels_ms": kern,
+        "roofline": roofline,
+        "clocks": sampler.summary(),
+    }
+
+    if rank == 0 and world == 1:
+        # ---- compositing against the HBM roofline, on a batch large enough to leave L2 ----
+        nr = 262144
+        out = torch.rand(nr * N_SAMPLES, 11, device=dev)
+        out[:, 3] *= 30
+        z = torch.sort(torch.rand(nr, N_SAMPLES, device=dev) * 0.2, -1).values.contiguous()
+        g_rgb, g_depth, g_sem = (torch.randn(nr, 3, device=dev), torch.randn(nr, device=dev),
+                                 torch.randn(nr, 3, device=dev))
+        for _ in range(3):
+            w, t_, rgb, raw, depth, sem = E.composite_fwd(out, z, 11, 8, 3)
+            E.composite_bwd(out, z, w, t_, raw, 11, 8, 3, g_rgb=g_rgb, g_depth=g_depth, g_sem=g_sem)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reps = 5
+        ev[0].record()
+        for _ in range(reps):
+            w, t_, rgb, raw, depth, sem = E.composite_fwd(out, z, 11, 8, 3)
+        ev[1].record()
+        for _ in range(reps):
+            E.composite_bwd(out, z, w, t_, raw, 11, 8, 3, g_rgb=g_rgb, g_depth=g_depth, g_sem=g_sem)
+        ev[2].record()
+        torch.cuda.synchronize()
+        f_ms, b_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        f_gbs, b_gbs = BYTES_COMP_FWD * nr / f_ms / 1e6, BYTES_COMP_BWD * nr / b_ms / 1e6
+        line["roofline_compositing"] = {
+            "bound": "hbm", "achieved": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr / (f_ms + b_ms) / 1e6,
+            "peak": pk["hbm"], "unit": "GB/s",
+            "frac": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr / (f_ms + b_ms) / 1e6 / pk["hbm"], "traffic": None,
+            "fwd": {"achieved": f_gbs, "frac": f_gbs / pk["hbm"], "ms": f_ms},
+            "bwd": {"achieved": b_gbs, "frac": b_gbs / pk["hbm"], "ms": b_ms},
+            "rays": nr, "peak_source": pk["source"] + ": copy bandwidth (kernels timed alone)"}
+        del out, z, w, t_
+
+    if True:
+        # ---- end to end through the public API, host buffers, H2D + D2H inside the timed region ----
+        loss_fn, dl, sl = metrics.SNerfLoss(0.0), metrics.DepthLoss(1.0, usealldepth=False), metrics.SemanticLoss(1.0)
+
+        def e2e_step():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
+            res = render_rays({"coarse": model}, args, d["rays"], None, semantics=d["sems"], mode="train",
+                              valid_depth=d["valid_depth"], target_depths=d["depths"], target_std=d["depth_std"])
+            loss = loss_fn(res, d["rgbs"])[0] + dl(res, d["depths"][:, 0], d["depths"][:, 1],
+                                                   target_valid_depth=d["valid_depth"],
+                                                   target_std=d["depth_std"])[0] + sl(res, d["sems"])[0]
+            for p in model.parameters():
+                p.grad = None
+            loss.backward()
+            if world > 1:                # one all-reduce of the flattened gradients
+                gl = [p.grad for p in model.parameters()]
+                flat = torch._utils._flatten_dense_tensors(gl)
+                parallel.allreduce_mean_(flat)
+                for g_, f_ in zip(gl, torch._utils._unflatten_dense_tensors(flat, gl)):
+                    g_.copy_(f_)
+            return float(loss)           # device -> host read of the step's result
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt_t = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t)
+        line["e2e"] = {"value": world * RAYS_PER_GPU * n_e2e / dt, "unit": "rays/s",
+                       "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_batch.values())),
+                       "d2h_bytes_per_step": 4, "ms_per_step": dt / n_e2e * 1e3,
+                       "api": "render_rays + SNerfLoss + DepthLoss + SemanticLoss + loss.backward()"}
+
+    if rank == 0 and world == 1:
+        # ---- the reference's CPU path on this box's host cores (bounded sample) ----
+        try:
+            rps, sec, cores = time_cpu_reference(1024, 3, 1)
+            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "sample": "3 steps x 1024 rays x 64 samples (BASELINE config 1 shape), fwd + "
+                                              "losses + bwd, torch fp32 oracle restatement of the reference"}
+        except Exception as ex:          # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

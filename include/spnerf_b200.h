@@ -109,10 +109,17 @@ typedef struct SpnerfNetSizes {
 /* host only; no device work */
 int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* sizes_host);
 
-/* fp32 parameters -> packed operands.  params_host[k] is a device pointer (or NULL for absent
- * heads).  Must be re-run after every parameter update. */
-int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* params_host, void* fwd_blob,
-                    void* bwd_blob, float* small, void* fwd_steps, void* bwd_steps, void* stream);
+/* Packing the fp32 parameters into tensor-core operands, in two steps:
+ *  spnerf_net_prepare  once per (configuration, parameter pointers, buffers): uploads the pack
+ *                      tables into `pack_ws` and the step tables, zeroes operand padding;
+ *                      params_host[k] is a device pointer (NULL for absent heads); synchronises.
+ *  spnerf_net_pack     after every parameter update: three small kernels, fully asynchronous. */
+int64_t spnerf_net_pack_workspace_bytes(const SpnerfNetConfig* cfg);
+int spnerf_net_prepare(const SpnerfNetConfig* cfg, const float* const* params_host, void* pack_ws,
+                       int64_t pack_ws_bytes, void* fwd_blob, void* bwd_blob, float* small, void* fwd_steps,
+                       void* bwd_steps, void* stream);
+int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, void* fwd_blob, void* bwd_blob,
+                    float* small, void* stream);
 
 /* sky_color(sun_dir) per ray (models/spnerf.py:355, 244-249; constant along a ray).
  * sky (n_rays,3); hidden (n_rays,256) post-ReLU or NULL. */

@@ -150,10 +150,11 @@ def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
     ref_grads = torch.autograd.grad(ref_loss, params, allow_unused=True)
 
     # ---- oracle ----
+    trace = {}
     ora_out = O.render(P, cfg, batch["rays"], ts, batch["sems"] if cfg.sem else None, mode,
                        batch["valid_depth"] if train else None, batch["depths"] if train else None,
                        batch["depth_std"] if train else None, O.Draws([u.clone() for u in uni], [n.clone() for n in nor]),
-                       t_table=t_table)
+                       t_table=t_table, trace=trace)
     ora_loss, ora_ld = O.colour_loss(ora_out, batch["rgbs"], cfg.sc_lambda, cfg.beta)
     if train:
         l2, d2 = O.depth_loss(ora_out, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"],
@@ -191,6 +192,10 @@ def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
         store[f"out_{k}"] = v.detach().numpy()
     for k, v in ref_ld.items():
         store[f"loss_{k}"] = v.detach().reshape(-1).numpy()
+    # sampler intermediates (first-pass weights / depth and the searchsorted indices): inputs and
+    # expected outputs of the guided sampler taken in isolation, where bit-exactness is required
+    for k, v in trace.items():
+        store[f"mid_{k}"] = v.detach().numpy().astype(np.int32 if k == "inds" else np.float32)
     names = [n_ for n_, _ in ref_model.named_parameters()] + (["t_table"] if t_table is not None else [])
     g = torch.Generator().manual_seed(99)
     for n_, gr in zip(names, ref_grads):

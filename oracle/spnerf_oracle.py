@@ -208,25 +208,30 @@ def three_sigma_draw(lo, hi, n, near0, far0, u):
     return inverse_cdf_draw(edges, bw, u)
 
 
-def guided_z(res, z, n, near, far, mode, valid_depth, target_depths, target_std, draws):
-    """modules/rendering.py:76-116 GenerateGuidedSamples (+ compute_samples_around_depth)."""
+def guided_z(res, z, n, near, far, mode, valid_depth, target_depths, target_std, draws, trace=None):
+    """modules/rendering.py:76-116 GenerateGuidedSamples (+ compute_samples_around_depth).
+    `trace` (tests only) receives the searchsorted indices of rendering.py:38 per ray."""
     depth, w = res["depth"], res["weights"]
     std = (((z - depth.unsqueeze(-1)).pow(2) * w).sum(-1)).sqrt()                       # :81
-    z2, _ = three_sigma_draw(depth - 3. * std, depth + 3. * std, n, near[0, 0], far[0, 0],
-                             draws.uniform((z.shape[0], n)))                            # :83-87
+    z2, inds = three_sigma_draw(depth - 3. * std, depth + 3. * std, n, near[0, 0], far[0, 0],
+                                draws.uniform((z.shape[0], n)))                         # :83-87
     if mode == "train":                                                                 # :98-114
         assert valid_depth is not None, 'valid_depth missing in training batch!'
         sel = valid_depth > 0
         td = torch.flatten(target_depths[:, 0][sel])
         ts = torch.flatten(target_std[sel])
-        gt, _ = three_sigma_draw(td - 3. * ts, td + 3. * ts, n, near[0, 0], far[0, 0],
-                                 draws.uniform((int(sel.sum()), n)))
+        gt, inds_gt = three_sigma_draw(td - 3. * ts, td + 3. * ts, n, near[0, 0], far[0, 0],
+                                       draws.uniform((int(sel.sum()), n)))
         z2[sel] = gt
+        inds = inds.clone()
+        inds[sel] = inds_gt
+    if trace is not None:
+        trace["inds"] = inds
     return z2
 
 
 def render(P, cfg, rays, ts=None, labels=None, mode="test", valid_depth=None, target_depths=None,
-           target_std=None, draws=None, t_table=None):
+           target_std=None, draws=None, t_table=None, trace=None):
     """modules/rendering.py:119-183 render_rays (coarse only; n_importance=0 in every config)."""
     if cfg.model != "sp-nerf":
         raise ValueError(f"model {cfg.model} is not valid")                             # :179
@@ -239,7 +244,9 @@ def render(P, cfg, rays, ts=None, labels=None, mode="test", valid_depth=None, ta
         t_emb = F.embedding(ts, t_table)
     res = inference(P, cfg, xyz, z, sun_d, labels, t_emb, draws)                        # :157
     if cfg.guidedsample:                                                                # :159-170
-        z2 = guided_z(res, z, n, near, far, mode, valid_depth, target_depths, target_std, draws).detach()
+        if trace is not None:
+            trace.update(z1=z, weights1=res["weights"].detach(), depth1=res["depth"].detach())
+        z2 = guided_z(res, z, n, near, far, mode, valid_depth, target_depths, target_std, draws, trace).detach()
         z2, _ = torch.sort(z2, -1)
         z_unsort = torch.cat([z, z2], -1)
         z, _ = torch.sort(torch.cat([z, z2], -1), -1)

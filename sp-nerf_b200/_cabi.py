@@ -118,9 +118,13 @@ class MlpFwd(ctypes.Structure):
 def _declare_net(L):
     L.spnerf_net_sizes.restype = ctypes.c_int
     L.spnerf_net_sizes.argtypes = [ctypes.POINTER(NetConfig), ctypes.POINTER(NetSizes)]
+    L.spnerf_net_pack_workspace_bytes.restype = ctypes.c_int64
+    L.spnerf_net_pack_workspace_bytes.argtypes = [ctypes.POINTER(NetConfig)]
+    L.spnerf_net_prepare.restype = ctypes.c_int
+    L.spnerf_net_prepare.argtypes = [ctypes.POINTER(NetConfig), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                     ctypes.c_int64] + [ctypes.c_void_p] * 6
     L.spnerf_net_pack.restype = ctypes.c_int
-    L.spnerf_net_pack.argtypes = [ctypes.POINTER(NetConfig), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
-                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.spnerf_net_pack.argtypes = [ctypes.POINTER(NetConfig)] + [ctypes.c_void_p] * 5
     L.spnerf_sky_fwd.restype = ctypes.c_int
     L.spnerf_sky_fwd.argtypes = [ctypes.c_void_p, ctypes.POINTER(NetConfig), ctypes.c_void_p, ctypes.c_int64,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]

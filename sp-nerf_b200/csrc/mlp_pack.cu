@@ -203,38 +203,24 @@ extern "C" int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* s) {
   return 0;
 }
 
-// Temporary device tables live at the tail of the step buffers' allocation?  No: the caller's
-// buffers hold only results.  The pack tables are staged through a small static device scratch
-// owned by this translation unit (allocated once, 64 KB), which keeps the call allocation-free
-// after the first use.
 namespace {
-void* g_scratch = nullptr;
-constexpr size_t kScratchBytes = 256 * 1024;
-}
-
-extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* P, void* fwd_blob, void* bwd_blob,
-                               float* small, void* fwd_steps, void* bwd_steps, void* stream_) {
-  int rc = validate(cfg);
-  if (rc) return rc;
-  if (!P || !fwd_blob || !small || !fwd_steps) return SPNERF_ERR_BAD_ARG;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!g_scratch) {
-    cudaError_t e = cudaMalloc(&g_scratch, kScratchBytes);
-    if (e != cudaSuccess) return -(int)e;
-  }
+struct PackPlan {
   Builder f;
-  build_forward(*cfg, P, f);
   std::vector<MmaStep> bsteps;
   std::vector<PackItem> bitems;
   uint32_t boff = 0;
-  if (bwd_blob && bwd_steps) build_backward(*cfg, P, bsteps, &bitems, &boff);
-
-  // small fp32 block
-  const SmallOffsets o = make_small_offsets(*cfg);
   std::vector<CopyItem> cp;
+  SmallOffsets o;
+  size_t bytes_f, bytes_b, bytes_c;
+};
+
+void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan& pl) {
+  build_forward(*cfg, P, pl.f);
+  build_backward(*cfg, P, pl.bsteps, &pl.bitems, &pl.boff);
+  const SmallOffsets o = make_small_offsets(*cfg);
+  pl.o = o;
   auto add = [&](int slot, int dst, int rows, int cols, int ld, int col0 = 0, int transpose = 0) {
-    if (!P[slot]) return;
-    cp.push_back({P[slot] + col0, dst, rows, cols, ld, transpose});
+    pl.cp.push_back({P[slot] ? P[slot] + col0 : nullptr, dst, rows, cols, ld, transpose});
   };
   for (int i = 0; i < 8; ++i) add(SPNERF_P_FC_W0 + 2 * i + 1, o.fc_b[i], 1, kFeat, kFeat);
   add(SPNERF_P_SIGMA_B, o.sigma_b, 1, 1, 1);
@@ -264,34 +250,64 @@ extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const float* const* P
   add(SPNERF_P_SKY0_B, o.sky0_b, 1, kHalf, kHalf);
   add(SPNERF_P_SKY2_W, o.sky2_w, 3, kHalf, kHalf);
   add(SPNERF_P_SKY2_B, o.sky2_b, 1, 3, 3);
+  pl.bytes_f = pl.f.items.size() * sizeof(PackItem);
+  pl.bytes_b = pl.bitems.size() * sizeof(PackItem);
+  pl.bytes_c = pl.cp.size() * sizeof(CopyItem);
+}
+}  // namespace
 
-  const size_t bytes_f = f.items.size() * sizeof(PackItem), bytes_b = bitems.size() * sizeof(PackItem),
-               bytes_c = cp.size() * sizeof(CopyItem);
-  if (bytes_f + bytes_b + bytes_c + 64 > kScratchBytes) return SPNERF_ERR_WORKSPACE;
-  uint8_t* sc = static_cast<uint8_t*>(g_scratch);
-  cudaError_t e;
-  // The tables come from pageable host vectors: these copies complete before returning, and the
-  // previous pack's kernels on this stream must be done with the scratch first.
-  e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) return -(int)e;
-  e = cudaMemcpyAsync(sc, f.items.data(), bytes_f, cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return -(int)e;
-  if (bytes_b) cudaMemcpyAsync(sc + bytes_f, bitems.data(), bytes_b, cudaMemcpyHostToDevice, stream);
-  cudaMemcpyAsync(sc + bytes_f + bytes_b, cp.data(), bytes_c, cudaMemcpyHostToDevice, stream);
-  cudaMemcpyAsync(fwd_steps, f.steps.data(), f.steps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
-  if (bytes_b)
-    cudaMemcpyAsync(bwd_steps, bsteps.data(), bsteps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
-  cudaMemsetAsync(fwd_blob, 0, (size_t)f.off16 * 16, stream);
-  if (bytes_b) cudaMemsetAsync(bwd_blob, 0, (size_t)boff * 16, stream);
-  cudaMemsetAsync(small, 0, (size_t)o.total * sizeof(float), stream);
-  pack_kernel<<<dim3((unsigned)f.items.size(), 2), 256, 0, stream>>>(reinterpret_cast<const PackItem*>(sc),
-                                                                     static_cast<uint8_t*>(fwd_blob));
-  if (bytes_b)
-    pack_kernel<<<dim3((unsigned)bitems.size(), 2), 256, 0, stream>>>(
-        reinterpret_cast<const PackItem*>(sc + bytes_f), static_cast<uint8_t*>(bwd_blob));
-  small_copy_kernel<<<(unsigned)cp.size(), 256, 0, stream>>>(
-      reinterpret_cast<const CopyItem*>(sc + bytes_f + bytes_b), small);
-  e = cudaGetLastError();
+extern "C" int64_t spnerf_net_pack_workspace_bytes(const SpnerfNetConfig* cfg) {
+  if (validate(cfg)) return -1;
+  const float* P[SPNERF_NUM_PARAMS] = {};
+  PackPlan pl;
+  make_pack_plan(cfg, P, pl);
+  return (int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c + 256);
+}
+
+// Uploads the pack tables (they embed the parameter pointers) and the two step tables, and zeroes
+// the padding of the operand buffers.  Once per (configuration, parameter pointers, buffers);
+// synchronises the stream because the tables come from pageable host memory.
+extern "C" int spnerf_net_prepare(const SpnerfNetConfig* cfg, const float* const* P, void* pack_ws,
+                                  int64_t pack_ws_bytes, void* fwd_blob, void* bwd_blob, float* small,
+                                  void* fwd_steps, void* bwd_steps, void* stream_) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!P || !pack_ws || !fwd_blob || !bwd_blob || !small || !fwd_steps || !bwd_steps) return SPNERF_ERR_BAD_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PackPlan pl;
+  make_pack_plan(cfg, P, pl);
+  if ((int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c) > pack_ws_bytes) return SPNERF_ERR_WORKSPACE;
+  uint8_t* sc = static_cast<uint8_t*>(pack_ws);
+  cudaMemcpyAsync(sc, pl.f.items.data(), pl.bytes_f, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(sc + pl.bytes_f, pl.bitems.data(), pl.bytes_b, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(sc + pl.bytes_f + pl.bytes_b, pl.cp.data(), pl.bytes_c, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(fwd_steps, pl.f.steps.data(), pl.f.steps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(bwd_steps, pl.bsteps.data(), pl.bsteps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
+  cudaMemsetAsync(fwd_blob, 0, (size_t)pl.f.off16 * 16, stream);
+  cudaMemsetAsync(bwd_blob, 0, (size_t)pl.boff * 16, stream);
+  cudaMemsetAsync(small, 0, (size_t)pl.o.total * sizeof(float), stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// fp32 parameters -> packed operands (three small kernels, no host synchronisation).
+extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, void* fwd_blob, void* bwd_blob,
+                               float* small, void* stream_) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!pack_ws || !fwd_blob || !bwd_blob || !small) return SPNERF_ERR_BAD_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const float* P[SPNERF_NUM_PARAMS] = {};
+  PackPlan pl;                       // host-side counts only
+  make_pack_plan(cfg, P, pl);
+  const uint8_t* sc = static_cast<const uint8_t*>(pack_ws);
+  pack_kernel<<<dim3((unsigned)pl.f.items.size(), 2), 256, 0, stream>>>(reinterpret_cast<const PackItem*>(sc),
+                                                                        static_cast<uint8_t*>(fwd_blob));
+  pack_kernel<<<dim3((unsigned)pl.bitems.size(), 2), 256, 0, stream>>>(
+      reinterpret_cast<const PackItem*>(sc + pl.bytes_f), static_cast<uint8_t*>(bwd_blob));
+  small_copy_kernel<<<(unsigned)pl.cp.size(), 256, 0, stream>>>(
+      reinterpret_cast<const CopyItem*>(sc + pl.bytes_f + pl.bytes_b), small);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
 

@@ -185,10 +185,13 @@ class NetEngine:
         self.fwd_steps = torch.empty(int(s.steps_bytes), **u8)
         self.bwd_steps = torch.empty(int(s.steps_bytes), **u8)
         self.wgrad_ws = torch.empty(int(_cabi.lib().spnerf_mlp_wgrad_workspace_bytes(ctypes.byref(self.cfg))), **u8)
+        self.pack_ws = torch.empty(int(_cabi.lib().spnerf_net_pack_workspace_bytes(ctypes.byref(self.cfg))), **u8)
         self._packed_key = None
+        self._prepared_key = None
         self._grad_key = None
+        self.n_packs = 0
 
-    def ensure_packed(self):
+    def ensure_packed(self, force=False):
         """(Re)pack the fp32 parameters if any of them changed since the last pack."""
         params = dict(self.module.named_parameters())
         dev = next(iter(params.values())).device
@@ -197,17 +200,24 @@ class NetEngine:
         if self.device != dev:
             self._alloc(dev)
         key = tuple((p.data_ptr(), p._version) for p in params.values())
-        if key == self._packed_key:
+        if key == self._packed_key and not force:
             return
-        table = (ctypes.c_void_p * _cabi.NUM_PARAMS)()
-        for name, p in params.items():
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise _cabi.SpnerfError(f"parameter {name} must be contiguous fp32")
-            table[_cabi.PARAM_SLOTS[name]] = p.data_ptr()
-        _cabi.check(_cabi.lib().spnerf_net_pack(
-            ctypes.byref(self.cfg), table, _p(self.fwd_blob), _p(self.bwd_blob), _p(self.small), _p(self.fwd_steps),
-            _p(self.bwd_steps), _stream()), "spnerf_net_pack")
+        ptrs = tuple(p.data_ptr() for p in params.values())
+        if ptrs != self._prepared_key:          # tables embed the parameter addresses
+            table = (ctypes.c_void_p * _cabi.NUM_PARAMS)()
+            for name, p in params.items():
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise _cabi.SpnerfError(f"parameter {name} must be contiguous fp32")
+                table[_cabi.PARAM_SLOTS[name]] = p.data_ptr()
+            _cabi.check(_cabi.lib().spnerf_net_prepare(
+                ctypes.byref(self.cfg), table, _p(self.pack_ws), self.pack_ws.numel(), _p(self.fwd_blob),
+                _p(self.bwd_blob), _p(self.small), _p(self.fwd_steps), _p(self.bwd_steps), _stream()),
+                "spnerf_net_prepare")
+            self._prepared_key = ptrs
+        _cabi.check(_cabi.lib().spnerf_net_pack(ctypes.byref(self.cfg), _p(self.pack_ws), _p(self.fwd_blob),
+                                                _p(self.bwd_blob), _p(self.small), _stream()), "spnerf_net_pack")
         self._packed_key = key
+        self.n_packs += 1
 
     def save_bytes(self, n_points):
         return ((n_points + TILE - 1) // TILE) * self.sizes.save_slabs_per_tile * SLAB_BYTES
@@ -262,7 +272,7 @@ class NetEngine:
         return self._gflat
 
     def backward(self, g_out, out, rays, n_samples, saves, absmax, labels=None, t_emb=None, g_sky_ray=None,
-                 sky=None, sky_hidden=None, debug_flags=0):
+                 sky=None, sky_hidden=None, debug_flags=0, timer=None):
         """All parameter gradients (+ d t_emb) from dL/d out.  Returns (flat, views, g_t_emb)."""
         n_rays = rays.shape[0]
         n_points = n_rays * n_samples
@@ -283,6 +293,8 @@ class NetEngine:
         a.g_emb = _p(by_name.get("semantic_embedding.weight"))
         a.g_small_bias, a.g_t_emb, a.debug_flags = _p(small_bias), _p(g_t), debug_flags
         _cabi.check(_cabi.lib().spnerf_mlp_bwd_data(ctypes.byref(a), _stream()), "spnerf_mlp_bwd_data")
+        if timer is not None:
+            timer.mark("mlp_bwd_data")
 
         w = _cabi.MlpWgrad()
         w.cfg = self.cfg
@@ -298,6 +310,8 @@ class NetEngine:
             _cabi.check(_cabi.lib().spnerf_mlp_wgrad_prepare(ctypes.byref(w), _stream()), "spnerf_mlp_wgrad_prepare")
             self._grad_key = key
         _cabi.check(_cabi.lib().spnerf_mlp_bwd_weights(ctypes.byref(w), _stream()), "spnerf_mlp_bwd_weights")
+        if timer is not None:
+            timer.mark("mlp_bwd_weights")
 
         # biases of the tiny last layers were reduced by the backward-data kernel
         by_name["rgb_from_xyzdir.2.bias"].copy_(small_bias[0:3])
@@ -313,4 +327,6 @@ class NetEngine:
                 _p(by_name["sky_color.0.weight"]), _p(by_name["sky_color.0.bias"]),
                 _p(by_name["sky_color.2.weight"]), _p(by_name["sky_color.2.bias"]), _stream()), "spnerf_sky_bwd")
         flat = work.clone()
+        if timer is not None:
+            timer.mark("grad_tail")
         return flat, self._views(flat), g_t

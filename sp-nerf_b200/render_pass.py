@@ -18,8 +18,7 @@ class _Pass(torch.autograd.Function):
         eng = module.engine
         eng.ensure_packed()
         n = z.shape[1]
-        need_grad = any(p.requires_grad for p in params) or (t_emb is not None and t_emb.requires_grad)
-        need_grad = need_grad and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad)     # False under no_grad or with frozen parameters
         sky, sky_hidden = eng.sky(rays)
         t_emb_c = None if t_emb is None else t_emb.detach().float().contiguous()
         out, saves = eng.forward(rays, n, z=None if xyz is not None else z, xyz=xyz, dir_override=dir_override,
@@ -104,8 +103,7 @@ class _Rows(torch.autograd.Function):
     def forward(ctx, module, rays, xyz, labels, t_emb, *params):
         eng = module.engine
         eng.ensure_packed()
-        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
-                                                 (t_emb is not None and t_emb.requires_grad))
+        need_grad = any(ctx.needs_input_grad)
         sky, sky_hidden = eng.sky(rays)
         t_c = None if t_emb is None else t_emb.detach().float().contiguous()
         out, saves = eng.forward(rays, 1, xyz=xyz, labels=labels, t_emb=t_c, sky=sky, save=need_grad)

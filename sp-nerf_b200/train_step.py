@@ -1,0 +1,79 @@
+"""One fused training step of the hot path, kernel by kernel, without the autograd machinery:
+sampling -> point network -> volume integration -> losses -> adjoints -> parameter gradients.
+
+This is the path bench.py times (inputs resident in HBM) and the core of a Lightning-free
+trainer.  It is numerically the same computation as
+``render_rays(...)`` + ``SNerfLoss`` + ``DepthLoss`` + ``SemanticLoss`` + ``loss.backward()``
+(main.py:125-174 with --depth --sem), minus Python graph bookkeeping.
+"""
+import torch
+
+from . import engine as E
+
+
+class StepTimer:
+    """Optional CUDA-event timing of each kernel group on the launching stream."""
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def durations_ms(self):
+        out = {}
+        for (_, e0), (name, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def fused_step(model, args, batch, lambda_ds=1.0, lambda_ss=1.0, use_all_depth=False, repack=True, timer=None,
+               allreduce=None):
+    """batch: dict with the reference's keys (rays, rgbs, sems, valid_depth, depths, depth_std), on the device.
+    Returns (flat gradient buffer, per-parameter views, loss scalars (8,) on the device, launches).
+    `allreduce(flat)` is called on the flat gradient buffer when given (data parallel)."""
+    if args.guidedsample or args.sc_lambda > 0 or args.beta:
+        raise NotImplementedError("fused_step covers the --depth --sem configuration; use render_rays otherwise")
+    eng = model.engine
+    t = timer or StepTimer(False)
+    rays = batch["rays"]
+    b, n = rays.shape[0], args.n_samples
+    labels = batch["sems"].reshape(-1) if model.sem else None
+    launches = 0
+    t.mark("start")
+    eng.ensure_packed(force=repack)            # parameters change every optimiser step
+    launches += 3 if repack else 0
+    t.mark("pack")
+    u = torch.rand(b, n, dtype=torch.float32, device=rays.device)
+    z = E.sample_coarse(rays, u, n)
+    sky, sky_hidden = eng.sky(rays)
+    launches += 2
+    t.mark("sample")
+    out, saves = eng.forward(rays, n, z=z, labels=labels, sky=sky, save=True)
+    launches += 1
+    t.mark("mlp_fwd")
+    weights, trans, rgb, rgb_raw, depth, sem = E.composite_fwd(out, z, eng.n_out, eng.col_sem, eng.n_sem)
+    launches += 1
+    t.mark("composite_fwd")
+    scalars, g_rgb, g_depth, g_sem = E.losses(
+        b, rgb=rgb, rgb_target=batch["rgbs"], depth=depth, z=z, weights=weights,
+        target_depth=batch["depths"][:, 0].contiguous(), target_weight=batch["depths"][:, 1].contiguous(),
+        target_std=batch["depth_std"], valid_depth=batch["valid_depth"], lambda_ds=lambda_ds,
+        use_all_depth=use_all_depth, sem_logits=sem, labels=labels, lambda_ss=lambda_ss)
+    launches += 2 if sem is not None else 1
+    t.mark("losses")
+    g_out, g_sky_ray, absmax = E.composite_bwd(out, z, weights, trans, rgb_raw, eng.n_out, eng.col_sem, eng.n_sem,
+                                               g_rgb=g_rgb, g_depth=g_depth, g_sem=g_sem)
+    launches += 1
+    t.mark("composite_bwd")
+    flat, views, _ = eng.backward(g_out, out, rays, n, saves, absmax, labels=labels, g_sky_ray=g_sky_ray, sky=sky,
+                                  sky_hidden=sky_hidden, timer=t)
+    launches += 4          # backward-data, weight GEMMs, reduce, sky backward
+    if allreduce is not None:
+        allreduce(flat)
+        t.mark("allreduce")
+    return flat, views, scalars, launches

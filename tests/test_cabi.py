@@ -1,0 +1,66 @@
+"""The C-ABI library: loads, exports every symbol include/spnerf_b200.h declares, and its structs
+match the ctypes mirrors.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import spnerf_b200
+from spnerf_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "spnerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spnerf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.lib()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/spnerf_b200.h but not exported"
+
+
+def test_abi_version_and_struct_sizes():
+    lib = _cabi.lib()          # _declare() raises on a struct size mismatch
+    assert lib.spnerf_abi_version() == 1
+    sizes = (ctypes.c_int32 * len(_cabi.STRUCTS))()
+    lib.spnerf_struct_sizes(sizes)
+    assert [ctypes.sizeof(s) for s in _cabi.STRUCTS] == list(sizes)
+
+
+def test_plan_sizes_host_only():
+    lib = _cabi.lib()
+    cfg = _cabi.NetConfig(feat=512, layers=8, skip_layer=4, mapping=1, sem=1, num_sem_classes=3, emb_dim=3, beta=0,
+                          t_dim=4)
+    s = _cabi.NetSizes()
+    assert lib.spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 0
+    assert (s.n_out, s.in_dim, s.tile_points) == (11, 63, 128)
+    assert s.fwd_steps > 100 and s.bwd_steps > 100 and s.fwd_blob_bytes > 5_000_000
+    # the weight stream covers every MAC of the network at least once: 2.69 M weights in fp16
+    assert s.fwd_blob_bytes >= 2 * 2_690_000
+    assert lib.spnerf_mlp_wgrad_workspace_bytes(ctypes.byref(cfg)) > 0
+
+
+@pytest.mark.parametrize("kw", [dict(feat=256), dict(layers=6), dict(skip_layer=3), dict(num_sem_classes=9, emb_dim=9),
+                                dict(mapping=1, num_sem_classes=5, emb_dim=5)])
+def test_unsupported_configurations_are_refused(kw):
+    base = dict(feat=512, layers=8, skip_layer=4, mapping=0, sem=1, num_sem_classes=3, emb_dim=3, beta=0, t_dim=4)
+    base.update(kw)
+    cfg = _cabi.NetConfig(**base)
+    s = _cabi.NetSizes()
+    assert _cabi.lib().spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 2     # SPNERF_ERR_UNSUPPORTED
+
+
+def test_bad_arguments_are_refused_without_a_device():
+    lib = _cabi.lib()
+    assert lib.spnerf_net_sizes(None, None) == 1
+    assert lib.spnerf_sample_coarse(None, None, None, 4, 64, None, None) == 1
+    assert lib.spnerf_composite_fwd(None, None) == 1
+    assert lib.spnerf_losses(None, None) == 1
+    assert lib.spnerf_mlp_fwd(None, None) == 1

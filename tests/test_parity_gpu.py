@@ -1,0 +1,304 @@
+"""Parity tests proper: the CUDA product path, called through the reference-shaped Python surface
+(which binds the C ABI of include/spnerf_b200.h), against
+  * the golden vectors produced from the unmodified reference (tests/golden, oracle/make_golden.py),
+  * the oracle evaluated on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full batch size.
+Stated tolerances (north_star): rgb max-abs 1e-3, depth 1e-2 m; sample depths / indices bit-exact."""
+import ctypes
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import spnerf_b200
+from oracle import spnerf_oracle as O
+from parity_common import TOL, Draws, build_model, load_case, run_case
+from spnerf_b200 import _cabi, engine as E, slab, synthetic
+from spnerf_b200.models import inference, load_model
+from spnerf_b200.modules import metrics
+from spnerf_b200.modules.rendering import render_rays
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _no_watchdog():
+    yield
+    torch.cuda.synchronize()
+    assert _cabi.lib().spnerf_watchdog_code() == 0, "a bounded device-side wait expired"
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core plumbing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,n,k", [("k", 256, 128), ("k", 16, 64), ("mn", 256, 128), ("mn", 64, 64)])
+def test_umma_descriptors(mode, n, k):
+    rng = np.random.default_rng(7)
+    a = rng.integers(-4, 5, size=(128, k)).astype(np.float16)
+    b = rng.integers(-4, 5, size=(n, k)).astype(np.float16)
+    ksteps = k // 16
+    if mode == "k":
+        a_img, b_img = slab.pack_matrix(a), slab.pack_matrix(b)
+        a_off = [(s // 4) * 128 * 128 + (s % 4) * 32 for s in range(ksteps)]
+        b_off = [(s // 4) * n * 128 + (s % 4) * 32 for s in range(ksteps)]
+        a_t = b_t = slab.smem_desc_template(16, 1024)
+        idesc = slab.idesc_f16(128, n, 0, 0)
+    else:
+        a_img, b_img = slab.pack_matrix(np.ascontiguousarray(a.T)), slab.pack_matrix(np.ascontiguousarray(b.T))
+        a_off = b_off = [s * 2048 for s in range(ksteps)]
+        a_t = b_t = slab.smem_desc_template(k * 128, 1024)
+        idesc = slab.idesc_f16(128, n, 1, 1)
+    ta, tb = torch.from_numpy(a_img.copy()).to(DEV), torch.from_numpy(b_img.copy()).to(DEV)
+    td = torch.full((128, n), float("nan"), device=DEV)
+    args = _cabi.UmmaSelftest()
+    args.a_img, args.b_img, args.d_out = ta.data_ptr(), tb.data_ptr(), td.data_ptr()
+    args.a_bytes, args.b_bytes, args.n, args.ksteps, args.idesc = ta.numel(), tb.numel(), n, ksteps, idesc
+    args.a_desc_template, args.b_desc_template = a_t, b_t
+    for i in range(ksteps):
+        args.a_off[i], args.b_off[i] = a_off[i], b_off[i]
+    rc = _cabi.lib().spnerf_selftest_umma(ctypes.byref(args), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert np.array_equal(td.cpu().numpy(), a.astype(np.float32) @ b.astype(np.float32).T)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors from the reference
+# ------------------------------------------------------------------------------------------------
+GOLDEN_CASES = ["c1_test_sem", "c2_train_depth_sem", "guided_test_nosem", "c3_train_guided_mapping_sc"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_render_rays_against_reference_golden(name):
+    rep = run_case(name, DEV, with_backward=True)
+    assert rep["state_ok"] and rep["keys_ok"]
+    guided = "guided" in name
+    for key, e in rep["out"].items():
+        base = key[:-len("_coarse")]
+        if base.startswith("z_vals"):
+            # with guided sampling the second-pass depths depend on first-pass network outputs, so they
+            # are only bit-exact at sampler level (test_guided_sampler_bit_exact); coarse depths always are
+            assert e["bit_equal"] or (guided and e["max_abs"] < 5e-4), (key, e)
+            continue
+        assert e["nan"] == 0, key
+        tol = TOL[base.replace("_sc", "")]
+        assert e["max_abs"] <= tol, (key, e, tol)
+    for key, e in rep["loss"].items():
+        assert abs(e["got"] - e["want"]) <= 2e-3 * max(abs(e["want"]), 1e-3), (key, e)
+    top = max(e["want_norm"] for e in rep["grad"].values() if "want_norm" in e)
+    for pname, e in rep["grad"].items():
+        assert not e.get("missing") and not e.get("unexpected_grad"), pname
+        assert e["nan"] == 0, pname
+        if e["want_norm"] < 1e-3 * top:
+            continue      # vanishing gradient: relative error is noise
+        assert abs(e["norm"] - e["want_norm"]) <= 1e-2 * e["want_norm"], (pname, e)
+        assert e["rel_dot_err"] <= 1e-2, (pname, e)
+        if "rel_l2" in e:
+            assert e["rel_l2"] <= 1e-2, (pname, e)
+
+
+@pytest.mark.parametrize("name", ["guided_test_nosem", "c3_train_guided_mapping_sc"])
+def test_guided_sampler_bit_exact(name):
+    """Same first-pass weights / depth / uniforms as the reference -> identical searchsorted indices,
+    guided depths and merged depths (modules/rendering.py:14-116,165-167)."""
+    g, meta = load_case(name)
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    rays, z1, w1, d1 = t("in_rays"), t("mid_z1"), t("mid_weights1"), t("mid_depth1")
+    train = meta["mode"] == "train"
+    u_pred = t("uniform_1")
+    kw = {}
+    if train:
+        valid = t("in_valid_depth")
+        u_gt = torch.zeros_like(u_pred)
+        u_gt[valid > 0] = t("uniform_2")
+        kw = dict(valid_depth=valid, target_depths=t("in_depths"), target_std=t("in_depth_std"), u_gt=u_gt)
+    z_unsort, z_sorted, inds = E.sample_guided(rays, z1, w1, d1, u_pred, want_indices=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(inds.cpu(), torch.from_numpy(g["mid_inds"]).int())
+    assert torch.equal(z_unsort.cpu(), torch.from_numpy(g["out_z_vals_unsort_coarse"]))
+    assert torch.equal(z_sorted.cpu(), torch.from_numpy(g["out_z_vals_coarse"]))
+
+
+def test_coarse_sampler_bit_exact_and_ragged():
+    for b in (1, 7, 1000):
+        batch = synthetic.make_batch(b, seed=b)
+        u = torch.rand(b, 64, generator=torch.Generator().manual_seed(b))
+        want = O.stratified_z(batch["rays"], 64, u)
+        got = E.sample_coarse(batch["rays"].to(DEV), u.to(DEV), 64)
+        assert torch.equal(got.cpu(), want)
+        assert bool((got[:, 1:] >= got[:, :-1]).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# volume integration and losses against the oracle on seeded inputs
+# ------------------------------------------------------------------------------------------------
+def _fake_out(b, n, n_out, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = torch.rand(b * n, n_out, generator=g)
+    out[:, 3] = torch.rand(b * n, generator=g) * 40      # densities that exercise the scan
+    if n_out > 8:
+        out[:, 8:] = torch.randn(b * n, n_out - 8, generator=g)
+    return out
+
+
+@pytest.mark.parametrize("b,n,c,noise", [(257, 64, 3, 0.0), (33, 128, 3, 0.5), (5, 64, 0, 0.0), (1, 3, 2, 0.0),
+                                         (64, 200, 8, 0.0)])
+def test_compositing_forward_backward(b, n, c, noise):
+    n_out = 8 + c
+    out = _fake_out(b, n, n_out, b + n).to(DEV).requires_grad_(True)
+    batch = synthetic.make_batch(b, seed=b)
+    z = O.stratified_z(batch["rays"], n, torch.rand(b, n, generator=torch.Generator().manual_seed(1))).to(DEV)
+    nz = torch.randn(b, n, device=DEV) if noise else None
+    want = O.composite(out.view(b, n, n_out), z, noise, nz, False, c > 0)
+    w, t, rgb, rgb_raw, depth, sem = E.composite_fwd(out.detach(), z, n_out, 8, c, noise=nz, noise_std=noise)
+    for got, key in ((w, "weights"), (t, "transparency"), (rgb, "rgb"), (depth, "depth")):
+        assert torch.allclose(got, want[key].detach(), rtol=1e-5, atol=2e-6), key
+    if c:
+        assert torch.allclose(sem, want["sem_logits"].detach(), rtol=1e-5, atol=1e-6)
+    # adjoint against autograd, with every upstream gradient present
+    gen = torch.Generator().manual_seed(5)
+    up = {k: torch.randn(want[k].shape, generator=gen).to(DEV) for k in ("rgb", "depth", "weights", "transparency")}
+    g_sem = torch.randn(b, c, generator=gen).to(DEV) if c else None
+    g_ext = torch.randn(b * n, n_out, generator=gen).to(DEV)
+    total = sum((want[k] * up[k]).sum() for k in up) + (out * g_ext).sum()
+    if c:
+        total = total + (want["sem_logits"] * g_sem).sum()
+    (g_want,) = torch.autograd.grad(total, out)
+    g_out, g_sky, amax = E.composite_bwd(out.detach(), z, w, t, rgb_raw, n_out, 8, c, g_rgb=up["rgb"],
+                                         g_depth=up["depth"], g_sem=g_sem, g_w=up["weights"], g_t=up["transparency"],
+                                         g_out_ext=g_ext, noise=nz, noise_std=noise)
+    scale = float(g_want.abs().max())
+    assert float((g_out - g_want).abs().max()) <= 2e-5 * scale
+    assert torch.allclose(g_sky, g_want.view(b, n, n_out)[..., 5:8].sum(1), rtol=1e-4, atol=1e-5 * scale)
+    assert abs(float(amax) - float(g_out.abs().max())) <= 1e-6 * scale
+
+
+def test_losses_against_oracle_and_edge_cases():
+    b, n, c = 501, 64, 3
+    gen = torch.Generator().manual_seed(3)
+    batch = synthetic.make_batch(b, seed=9)
+    z = O.stratified_z(batch["rays"], n, torch.rand(b, n, generator=gen))
+    w = torch.softmax(torch.randn(b, n, generator=gen) * 3, -1)
+    res = {"rgb_coarse": torch.rand(b, 3, generator=gen), "depth_coarse": (w * z).sum(-1), "weights_coarse": w,
+           "z_vals_coarse": z, "sem_logits_coarse": torch.randn(b, c, generator=gen)}
+    res = {k: v.requires_grad_(k in ("rgb_coarse", "depth_coarse", "sem_logits_coarse")) for k, v in res.items()}
+    dres = {k: v.detach().to(DEV).requires_grad_(v.requires_grad) for k, v in res.items()}
+    dev = {k: v.to(DEV) for k, v in batch.items()}
+    for usealldepth in (False, True):
+        want = O.colour_loss(res, batch["rgbs"])[0] \
+            + O.depth_loss(res, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 2.0,
+                           usealldepth)[0] + O.semantic_loss(res, batch["sems"], 0.5)[0]
+        got = metrics.SNerfLoss(0.0)(dres, dev["rgbs"])[0] \
+            + metrics.DepthLoss(2.0, usealldepth=usealldepth)(dres, dev["depths"][:, 0], dev["depths"][:, 1],
+                                                               target_valid_depth=dev["valid_depth"],
+                                                               target_std=dev["depth_std"])[0] \
+            + metrics.SemanticLoss(0.5)(dres, dev["sems"])[0]
+        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+        keys = ("rgb_coarse", "depth_coarse", "sem_logits_coarse")
+        gw = torch.autograd.grad(want, [res[k] for k in keys])
+        gg = torch.autograd.grad(got, [dres[k] for k in keys])
+        for a, bb, k in zip(gg, gw, keys):
+            assert torch.allclose(a.cpu(), bb, rtol=1e-4, atol=1e-8), k
+    # no valid depth prior at all -> zero loss, zero gradient (metrics.py:97-100)
+    zero_valid = torch.zeros(b, dtype=torch.long, device=DEV)
+    l, _ = metrics.DepthLoss(1.0, usealldepth=False)(dres, dev["depths"][:, 0], dev["depths"][:, 1],
+                                                     target_valid_depth=zero_valid, target_std=dev["depth_std"])
+    assert float(l) == 0.0
+    # every label ignored -> NaN like torch.nn.CrossEntropyLoss
+    l, _ = metrics.SemanticLoss(1.0)(dres, torch.full((b,), -100, device=DEV))
+    assert bool(torch.isnan(l))
+
+
+# ------------------------------------------------------------------------------------------------
+# point network against the oracle network (torch fp32 on the device) + per-point call surface
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(sem=True, mapping=True), dict(sem=False, mapping=False),
+                                dict(sem=True, beta=True, mapping=True)])
+def test_point_network_forward_rows(kw):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.make_cfg(**kw)
+    torch.manual_seed(0)
+    model = load_model(types.SimpleNamespace(**vars(cfg))).to(DEV)
+    p = 1000                                            # ragged: 7 full tiles + 104 rows
+    gen = torch.Generator().manual_seed(2)
+    xyz = (torch.rand(p, 3, generator=gen) * 2 - 1).to(DEV)
+    sun = torch.nn.functional.normalize(torch.randn(p, 3, generator=gen), dim=1).to(DEV)
+    lab = torch.randint(0, 3, (p,), generator=gen).to(DEV)
+    lab[::17] = -100
+    t_emb = torch.randn(p, cfg.t_embbeding_tau, generator=gen).to(DEV) if cfg.beta else None
+    with torch.no_grad():
+        got = model(xyz, input_sun_dir=sun, input_t=t_emb, input_s=lab if cfg.sem else None)
+        want = O.point_network({k: v for k, v in model.named_parameters()}, cfg, xyz, sun, lab if cfg.sem else None, t_emb)
+    assert got.shape == want.shape
+    err = (got - want).abs().max(0).values
+    assert float(err[:3].max()) <= 1e-3 and float(err[4]) <= 1e-3 and float(err[5:8].max()) <= 1e-5
+    assert float((got[:, 3] - want[:, 3]).abs().max()) <= 2e-3 * float(want[:, 3].abs().max()) + 1e-3
+    assert float(err[8:].max()) <= 5e-3
+    sig = model(xyz, input_sun_dir=sun, input_t=t_emb, input_s=lab if cfg.sem else None, sigma_only=True)
+    assert sig.shape == (p, 1) and torch.equal(sig[:, 0], got[:, 3])
+
+
+def test_inference_mirror_with_explicit_points_matches_ray_form():
+    g, meta = load_case("c1_test_sem")
+    model, _, args = build_model(meta, DEV)
+    rays = torch.from_numpy(g["in_rays"]).to(DEV)
+    sems = torch.from_numpy(g["in_sems"]).to(DEV)
+    z = torch.from_numpy(g["out_z_vals_coarse"]).to(DEV)
+    xyz = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    with torch.no_grad():
+        a = inference(model, args, xyz, z, sun_d=rays[:, 8:11], semantics=sems)
+    assert sorted(a) == ["albedo", "depth", "rgb", "sem_logits", "sky", "sun", "transparency", "weights", "z_vals"]
+    for k in ("rgb", "depth", "weights", "sem_logits"):
+        want = torch.from_numpy(g[f"out_{k}_coarse"]).to(DEV)
+        assert float((a[k] - want).abs().max()) <= TOL[k], k
+    assert a["albedo"].shape == (96, 64, 3) and a["sun"].shape == (96, 64, 1) and a["sky"].shape == (96, 64, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 2 at full size: size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_full_size_training_step_properties():
+    cfg = O.make_cfg(sem=True, num_sem_classes=3)
+    args = types.SimpleNamespace(**vars(cfg))
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(8.0)
+    model = model.to(DEV)
+    b = 8192
+    batch = synthetic.make_batch(b, seed=21, device=DEV)
+
+    def step(loss_scale):
+        torch.manual_seed(123)
+        res = render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="train",
+                          valid_depth=batch["valid_depth"], target_depths=batch["depths"],
+                          target_std=batch["depth_std"])
+        loss = metrics.SNerfLoss(0.0)(res, batch["rgbs"])[0] \
+            + metrics.DepthLoss(1.0, usealldepth=False)(res, batch["depths"][:, 0], batch["depths"][:, 1],
+                                                        target_valid_depth=batch["valid_depth"],
+                                                        target_std=batch["depth_std"])[0] \
+            + metrics.SemanticLoss(1.0)(res, batch["sems"])[0]
+        grads = torch.autograd.grad(loss * loss_scale, list(model.parameters()))
+        return res, loss, grads
+
+    res, loss, g1 = step(1.0)
+    w, t = res["weights_coarse"], res["transparency_coarse"]
+    assert bool(torch.isfinite(loss))
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-4            # last sample absorbs the remaining transmittance
+    assert bool((t[:, 1:] <= t[:, :-1] * (1 + 1e-6) + 1e-9).all())   # transmittance never increases
+    assert float(res["rgb_coarse"].min()) >= 0 and float(res["rgb_coarse"].max()) <= 1
+    sky = res["sky_coarse"]
+    assert float((sky - sky[:, :1]).abs().max()) == 0.0           # sky colour is constant along a ray
+    assert bool((res["z_vals_coarse"][:, 1:] >= res["z_vals_coarse"][:, :-1]).all())
+    assert res["depth_coarse"].requires_grad and not res["z_vals_coarse"].requires_grad
+    # determinism and linearity of the backward (the fp16 gradient scale must cancel exactly: powers of two)
+    _, loss2, g2 = step(1.0)
+    assert float(loss2) == float(loss)
+    _, _, g8 = step(8.0)
+    for a, bb, c in zip(g1, g2, g8):
+        assert bool(torch.isfinite(a).all())
+        assert float((a - bb).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12     # atomics reorder a few sums
+        assert float((c - 8 * a).abs().max()) <= 1e-4 * float((8 * a).abs().max()) + 1e-12
