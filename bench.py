@@ -83,7 +83,7 @@ def build_model(args, device):
     model = load_model(args)
     with torch.no_grad():                      # "trained-like" density so the transmittance scan is exercised
         model.sigma_from_xyz[0].bias.fill_(3.0)
-        model.sigma_from_xyz[0].weight.mul_(8.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
     return model.to(device)
 
 

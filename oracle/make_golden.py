@@ -121,7 +121,7 @@ def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
     if spec.get("trained_like"):
         with torch.no_grad():
             ref_model.sigma_from_xyz[0].bias.fill_(3.0)
-            ref_model.sigma_from_xyz[0].weight.mul_(8.0)
+            ref_model.sigma_from_xyz[0].weight.mul_(4.0)
     P = {k: v for k, v in ref_model.named_parameters()}
 
     uni, nor = make_draws(spec["seed"] + 1000, B, N, cfg.guidedsample, cfg.sc_lambda > 0, n_valid, train)

@@ -227,6 +227,7 @@ def guided_z(res, z, n, near, far, mode, valid_depth, target_depths, target_std,
         inds[sel] = inds_gt
     if trace is not None:
         trace["inds"] = inds
+        trace["std"] = std
     return z2
 
 

@@ -55,7 +55,7 @@ def build_model(meta, device):
     if meta["trained_like"]:
         with torch.no_grad():
             model.sigma_from_xyz[0].bias.fill_(3.0)
-            model.sigma_from_xyz[0].weight.mul_(8.0)
+            model.sigma_from_xyz[0].weight.mul_(4.0)
     model = model.to(device)
     if t_table is not None:
         t_table = t_table.to(device)

@@ -35,7 +35,7 @@ def run(name):
     model = load_model(types.SimpleNamespace(**vars(cfg)))
     with torch.no_grad():
         model.sigma_from_xyz[0].bias.fill_(3.0)
-        model.sigma_from_xyz[0].weight.mul_(8.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
     model = model.to(dev)
     B, N = (8192, 64) if timing else (300, 64)     # 300*64 = 19200 points: 150 tiles -> 2 tiles on some CTAs
     batch = synthetic.make_batch(B, seed=5, device=dev)
