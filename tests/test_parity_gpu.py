@@ -255,7 +255,8 @@ def test_point_network_forward_rows(kw):
     err = (got - want).abs().max(0).values
     assert float(err[:3].max()) <= 1e-3 and float(err[4]) <= 1e-3 and float(err[5:8].max()) <= 1e-5
     assert float((got[:, 3] - want[:, 3]).abs().max()) <= 2e-3 * float(want[:, 3].abs().max()) + 1e-3
-    assert float(err[8:].max()) <= 5e-3
+    if err.numel() > 8:
+        assert float(err[8:].max()) <= 5e-3
     sig = model(xyz, input_sun_dir=sun, input_t=t_emb, input_s=lab if cfg.sem else None, sigma_only=True)
     assert sig.shape == (p, 1) and torch.equal(sig[:, 0], got[:, 3])
 
