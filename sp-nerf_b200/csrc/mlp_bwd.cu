@@ -22,6 +22,7 @@ struct BwdParams {
   const float* absmax; float* scale_out;
   float* g_emb; float* g_small_bias; float* g_t_emb;
   int sem, n_classes, emb_dim, beta, t_dim, n_out, col_beta, col_sem, debug;
+  long long* prof;
 };
 
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -30,25 +31,22 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
-__device__ __forceinline__ uint32_t slab_off(int col, int row) {
-  return (uint32_t)(col >> 6) * kSlabBytes + slab_chunk_offset(row, (col & 63) >> 3);
-}
 
-// G[j] = acc[j] * dact(j) for columns [j0, j0+ncols) of a chunk at TMEM column tcol0;
+// G[j] = acc[j] * dact(j) for columns [j0, j0+ncols) of a chunk at TMEM address taddr;
 // MODE 0: dact = cos(x)  (x = saved fp16 sine argument)     MODE 1: dact = 30 * saved cos     MODE 2: dact = 1
-// result -> fp16 -> shared slab at column dst_col0 + j (+ gradient save area)
+// result -> fp16 -> shared slab at column dst_col0 + j (streamed to the gradient save area afterwards)
 template <int MODE>
-__device__ __forceinline__ void bwd_columns(uint32_t taddr, int tcol0, int j0, int ncols, const uint8_t* xsave,
-                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave, int skip) {
-  if (skip) ncols = 32;
+__device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, const uint8_t* xsave, uint8_t* act,
+                                            int dst_col0, int row) {
+#pragma unroll 1
   for (int jb = j0; jb < j0 + ncols; jb += 32) {
     uint4 xr[4];
     if (MODE != 2) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) xr[c] = ldg16(xsave + slab_off(jb + c * 8, row));
+      for (int c = 0; c < 4; ++c) xr[c] = ldg16(xsave + xsave_off(jb + c * 8, row));
     }
     uint32_t v[32];
-    tmem_ld32(taddr + tcol0 + jb, v);
+    tmem_ld32(taddr + jb, v);
     tmem_wait_ld();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -63,35 +61,33 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int tcol0, int j0, i
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
       }
-      const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
-      const uint32_t off = slab_off(dst_col0 + jb + c * 8, row);
-      *reinterpret_cast<uint4*>(act + off) = gp;
-      if (gsave) *reinterpret_cast<uint4*>(gsave + slab_off(jb + c * 8, row)) = gp;
+      *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
+          make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
     }
   }
 }
 
 // Gradient entering a 256-wide hidden layer from its tiny output layer (CUDA cores):
-//   G[j] = (sum_c coef[c] * W2[c][j]) * cos(x[j])   for j in [j0, j0+ncols)
+//   G[j] = coefw(j) * cos(x[j])   for j in [j0, j0+ncols),  coefw(j) = sum_c g_c * W2[c][j] from shared memory
 // `each(j, G)` lets the caller fold further per-row reductions (t_emb gradient).
-template <int NC, class Each>
-__device__ __forceinline__ void gen_columns(const float* coef, const float* __restrict__ w2, int j0, int ncols,
-                                            const uint8_t* xsave, uint8_t* act, int dst_col0, int row,
-                                            uint8_t* gsave, Each each) {
-  for (int jb = j0; jb < j0 + ncols; jb += 8) {
-    float x[8], g[8];
-    unpack8(ldg16(xsave + slab_off(jb, row)), x);
+template <class CoefW, class Each>
+__device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, const uint8_t* xsave, uint8_t* act,
+                                            int dst_col0, int row, Each each) {
+#pragma unroll 1
+  for (int jb = j0; jb < j0 + ncols; jb += 16) {
+    const uint4 xr0 = ldg16(xsave + xsave_off(jb, row)), xr1 = ldg16(xsave + xsave_off(jb + 8, row));
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float a = 0.f;
+    for (int c = 0; c < 2; ++c) {
+      float x[8], g[8];
+      unpack8(c ? xr1 : xr0, x);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) a = fmaf(coef[c], __ldg(w2 + c * kHalf + jb + e), a);
-      g[e] = a * __cosf(x[e]);
-      each(jb + e, g[e]);
+      for (int e = 0; e < 8; ++e) {
+        g[e] = coefw(jb + c * 8 + e) * __cosf(x[e]);
+        each(jb + c * 8 + e, g[e]);
+      }
+      *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
+          make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
     }
-    const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
-    *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb, row)) = gp;
-    if (gsave) *reinterpret_cast<uint4*>(gsave + slab_off(jb, row)) = gp;
   }
 }
 struct NoEachG { __device__ __forceinline__ void operator()(int, float) const {} };
@@ -106,9 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem sh = carve(smem);
   uint8_t* act = sh.act;
-  float* scratch = reinterpret_cast<float*>(smem + kSlabInpLo * kSlabBytes);   // unused input slab: scratch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup(sh, smem);
+  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
 
   // power-of-two gradient scale keeping fp16 operands in range
@@ -129,12 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   } else if (warp == 1) {
     if (lane == 0) mma_loop(sh, tmem_base, p.steps, p.n_steps, n_tiles, p.debug);
   } else if (warp >= kEpiWarp0) {
-    const int grp = (warp - kEpiWarp0) >> 2;
+    const int cg = (warp - kEpiWarp0) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const float* S = p.small;
-    const int skip = p.debug & 2;
-    EpiSync sync(sh);
+    const float4* Wrgb2 = reinterpret_cast<const float4*>(smem + kOffRgb2);
+    const float4* Wsem2 = reinterpret_cast<const float4*>(smem + kOffSem2);
+    const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
+    const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
+    const int wide_cols = (p.debug & 2) ? 32 : 128;
+    EpiSync sync(sh, p.prof);
+    mbar_wait(sh.bar_par, 0, 31);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t pt = tile * kTileM + row;
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       auto gs = [&](int slab) { return tg + (size_t)slab * kSlabBytes; };
 
       // ---- head-level gradients of this row (fp32, unscaled) ----
+      sync.stamp();
       float g_u[3] = {0.f, 0.f, 0.f}, g_v = 0.f, g_sp = 0.f, g_bp = 0.f, g_lg[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) g_lg[c] = 0.f;
@@ -166,15 +167,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       sync.drain_stores();
       // small-gradient slab [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)] (scaled), the B operand
       // of the tiny last-layer weight gradients; bias gradients of those layers are reduced right here
-      if (grp == 0) {
+      if (cg == 0) {
         uint8_t* d = gs(p.gm.gsmall);
         const float sc = scale;
-        *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, 0)) =
-            make_uint4(pack2(g_u[0] * sc, g_u[1] * sc), pack2(g_u[2] * sc, g_v * sc), pack2(g_sp * sc, g_bp * sc), 0u);
-        *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, 1)) =
-            make_uint4(pack2(g_lg[0] * sc, g_lg[1] * sc), pack2(g_lg[2] * sc, g_lg[3] * sc),
-                       pack2(g_lg[4] * sc, g_lg[5] * sc), pack2(g_lg[6] * sc, g_lg[7] * sc));
-        for (int c = 2; c < 8; ++c) *reinterpret_cast<uint4*>(d + slab_chunk_offset(row, c)) = make_uint4(0, 0, 0, 0);
+        stg16(d + slab_chunk_offset(row, 0),
+              make_uint4(pack2(g_u[0] * sc, g_u[1] * sc), pack2(g_u[2] * sc, g_v * sc), pack2(g_sp * sc, g_bp * sc), 0u));
+        stg16(d + slab_chunk_offset(row, 1),
+              make_uint4(pack2(g_lg[0] * sc, g_lg[1] * sc), pack2(g_lg[2] * sc, g_lg[3] * sc),
+                         pack2(g_lg[4] * sc, g_lg[5] * sc), pack2(g_lg[6] * sc, g_lg[7] * sc)));
+        for (int c = 2; c < 8; ++c) stg16(d + slab_chunk_offset(row, c), make_uint4(0, 0, 0, 0));
         float sums[14] = {g_u[0], g_u[1], g_u[2], g_v, g_sp, g_bp, g_lg[0], g_lg[1], g_lg[2], g_lg[3],
                           g_lg[4], g_lg[5], g_lg[6], g_lg[7]};
 #pragma unroll
@@ -185,85 +186,101 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       }
       // ---- E_in: G_s3 = g_v * W_sun6 * cos(x_s3) -> slabs 0..3 ----
       {
-        const float coef[1] = {g_v * scale};
-        gen_columns<1>(coef, S + p.so.sun6_w, grp * 128, 128, xs(p.sm.sun_x[2]), act, 0, row, gs(p.gm.G_sun[2]),
-                       NoEachG());
+        const float cv = g_v * scale;
+        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * 64, 64, xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
       }
-      sync.end(true, nullptr, 0, 0);
+      sync.end(true);
+      sync.store_slabs(gs(p.gm.G_sun[2]), 0, 4);
       // ---- after sun_v_net.4^T: G_s2 ----
       sync.begin();
-      bwd_columns<0>(taddr, 0, grp * 128, 128, xs(p.sm.sun_x[1]), act, 0, row, gs(p.gm.G_sun[1]), 0);
-      sync.end(true, nullptr, 0, 0);
+      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_x[1]), act, 0, row);
+      sync.end(true);
+      sync.store_slabs(gs(p.gm.G_sun[1]), 0, 4);
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
       sync.begin();
-      bwd_columns<0>(taddr, 0, grp * 128, 128, xs(p.sm.sun_x[0]), act, 0, row, gs(p.gm.G_sun[0]), 0);
+      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_x[0]), act, 0, row);
       {
-        const float coef[3] = {g_u[0] * scale, g_u[1] * scale, g_u[2] * scale};
-        gen_columns<3>(coef, S + p.so.rgb2_w, grp * 128, 128, xs(p.sm.rgb_x), act, kHalf, row, gs(p.gm.G_rgb),
-                       NoEachG());
+        const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
+        gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * 64, 64,
+                    xs(p.sm.rgb_x), act, kHalf, row, NoEachG());
       }
-      sync.end(true, nullptr, 0, 0);
+      sync.end(true);
+      sync.store_slabs(gs(p.gm.G_sun[0]), 0, 4);
+      sync.store_slabs(gs(p.gm.G_rgb), 4, 4);
       if (p.beta) {
         // ---- beta hidden G_b1 -> slabs 0..3 (the sun/albedo GEMMs have retired); d t_emb on the way ----
         sync.begin();
         float tacc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) tacc[e] = 0.f;
-        const float coef[1] = {g_bp * scale};
+        const float cb = g_bp * scale;
         const float* wt = S + p.so.beta0_wt;
-        gen_columns<1>(coef, S + p.so.beta2_w, grp * 128, 128, xs(p.sm.beta_x), act, 0, row, gs(p.gm.G_beta),
-                       [&](int j, float g) {
+        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * 64, 64, xs(p.sm.beta_x), act, 0, row,
+                    [&](int j, float g) {
 #pragma unroll
-                         for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * kHalf + j), tacc[e]);
-                       });
+                      for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * kHalf + j), tacc[e]);
+                    });
         if (p.g_t_emb && valid)
           for (int e = 0; e < p.t_dim; ++e) atomicAdd(p.g_t_emb + ray * p.t_dim + e, tacc[e] * inv_scale);
-        sync.end(true, nullptr, 0, 0);
+        sync.end(true);
+        sync.store_slabs(gs(p.gm.G_beta), 0, 4);
       }
       // ---- g_f (linear) -> slabs 0..7 ----
       sync.begin();
-      bwd_columns<2>(taddr, 0, grp * kHalf, kHalf, nullptr, act, 0, row, gs(p.gm.g_f), skip);
-      sync.end(true, nullptr, 0, 0);
+      bwd_columns<2>(taddr, cg * 128, wide_cols, nullptr, act, 0, row);
+      sync.end(true);
+      sync.store_slabs(gs(p.gm.g_f), 0, 8);
       // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
       sync.begin();
       if (p.sem) {
-        float coef[8];
+        float cf[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) coef[c] = g_lg[c] * scale;
-        gen_columns<8>(coef, S + p.so.sem2_w, grp * 128, 128, xs(p.sm.sem_x), act, 0, row, gs(p.gm.G_sem), NoEachG());
+        for (int c = 0; c < 8; ++c) cf[c] = g_lg[c] * scale;
+        const bool wide = p.n_classes > 4;
+        gen_columns([&](int j) {
+          const float4 w = Wsem2[j * 2];
+          float a = fmaf(cf[0], w.x, fmaf(cf[1], w.y, fmaf(cf[2], w.z, cf[3] * w.w)));
+          if (wide) {
+            const float4 u = Wsem2[j * 2 + 1];
+            a += fmaf(cf[4], u.x, fmaf(cf[5], u.y, fmaf(cf[6], u.z, cf[7] * u.w)));
+          }
+          return a;
+        }, cg * 64, 64, xs(p.sm.sem_x), act, 0, row, NoEachG());
       }
-      if (grp == 0) {
+      if (cg == 3) {
         *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 0)) =
             make_uint4(pack2(g_sp * scale, 0.f), 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
-      sync.end(true, nullptr, 0, 0);
+      sync.end(true);
+      if (p.sem) sync.store_slabs(gs(p.gm.G_sem), 0, 4);
       // ---- G_7 = g_h * cos(x_7), then the trunk ----
       float gemb[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) gemb[e] = 0.f;
       auto emb_phase = [&](bool signal) {      // 16-wide product with the embedding columns of a weight
         sync.begin();
-        if (grp == 0) {
+        if (cg == 0) {
           uint32_t v[16];
           tmem_ld16(taddr, v);
           tmem_wait_ld();
 #pragma unroll
           for (int e = 0; e < 8; ++e) gemb[e] += __uint_as_float(v[e]);
         }
-        if (signal) sync.end(true, nullptr, 0, 0);
+        if (signal) sync.end(true);
       };
       for (int L = 7; L >= 0; --L) {
         sync.begin();
-        if (L > 0) bwd_columns<0>(taddr, 0, grp * kHalf, kHalf, xs(p.sm.x[L]), act, 0, row, gs(p.gm.G[L]), skip);
-        else       bwd_columns<1>(taddr, 0, grp * kHalf, kHalf, xs(p.sm.x[0]), act, 0, row, gs(p.gm.G[0]), skip);
+        if (L > 0) bwd_columns<0>(taddr, cg * 128, wide_cols, xs(p.sm.x[L]), act, 0, row);
+        else       bwd_columns<1>(taddr, cg * 128, wide_cols, xs(p.sm.x[0]), act, 0, row);
         const bool more = (L > 0) || p.sem;
-        if (more) sync.end(true, nullptr, 0, 0);
+        sync.end(more);
+        sync.store_slabs(gs(p.gm.G[L]), 0, 8);
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }
       // ---- label-embedding gradient: rows of one warp share a ray (hence a label) when n_samples % 32 == 0 ----
-      if (p.sem && grp == 0 && p.g_emb) {
+      if (p.sem && cg == 0 && p.g_emb) {
         int lab = -1;
         if (valid && p.labels) { const int64_t l = p.labels[ray]; lab = (l == -100) ? -1 : (int)l; }   // padding row: no grad
         const int lab0 = __shfl_sync(0xffffffffu, lab, 0);
@@ -284,11 +301,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
     }
     sync.finish();
   }
-  (void)scratch;
   teardown(tmem_base);
 }
 
 }  // namespace
+
+static long long* g_prof_bwd = nullptr;
+extern "C" void spnerf_debug_phase_clocks_bwd(long long* dev_buf256) { g_prof_bwd = dev_buf256; }
 
 extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   if (!a || !a->g_out || !a->out || !a->rays || !a->blob || !a->steps || !a->small || !a->saves || !a->grad_saves ||
@@ -311,6 +330,7 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   p.sem = a->cfg.sem; p.n_classes = a->cfg.num_sem_classes; p.emb_dim = a->cfg.emb_dim; p.beta = a->cfg.beta;
   p.t_dim = a->cfg.t_dim; p.n_out = d.n_out; p.col_beta = d.col_beta; p.col_sem = d.col_sem;
   p.debug = a->debug_flags;
+  p.prof = g_prof_bwd;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);

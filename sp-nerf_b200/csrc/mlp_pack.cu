@@ -49,7 +49,8 @@ __global__ void pack_kernel(const PackItem* __restrict__ items, uint8_t* __restr
 
 struct CopyItem {
   const float* src;
-  int dst, rows, cols, ld, transpose;   // dst[r*cols+c] = src[r*ld+c]  (transpose: dst[c*rows+r])
+  int dst, rows, cols, ld, transpose;   // dst[r*cols+c] = src[r*ld+c]  (transpose: dst[c*dst_ld+r])
+  int dst_ld;
 };
 
 __global__ void small_copy_kernel(const CopyItem* __restrict__ items, float* __restrict__ small) {
@@ -59,13 +60,50 @@ __global__ void small_copy_kernel(const CopyItem* __restrict__ items, float* __r
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const int r = t / it.cols, c = t % it.cols;
     const float v = it.src[(size_t)r * it.ld + c];
-    small[it.dst + (it.transpose ? c * it.rows + r : t)] = v;
+    small[it.dst + (it.transpose ? c * it.dst_ld + r : t)] = v;
   }
 }
+
+// B tile of an aux step (net_plan.h): 16 columns per output unit, no-swizzle K-major.
+struct AuxItem {
+  const float* bias; int bias_n;          // bias[row0 + i], valid while row0 + i < bias_n
+  const float* wx; int wx_ld, wx_rows, wx_col0, wx_ncols, dst_col;   // B[i][dst_col+e] = wx[row0+i][wx_col0+e]
+  int row0, n;
+  uint32_t dst_off16;
+};
+
+__global__ void aux_pack_kernel(const AuxItem* __restrict__ items, uint8_t* __restrict__ blob) {
+  const AuxItem it = items[blockIdx.x];
+  for (int i = threadIdx.x; i < it.n; i += blockDim.x) {
+    __half h[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) h[e] = __float2half_rn(0.f);
+    const int r = it.row0 + i;
+    if (it.bias && r < it.bias_n) {
+      const float b = it.bias[r];
+      const __half hi = __float2half_rn(b);
+      h[kAuxColOne] = hi;
+      h[kAuxColOneLo] = __float2half_rn(b - __half2float(hi));
+    }
+    if (it.wx && r < it.wx_rows)
+      for (int e = 0; e < it.wx_ncols; ++e) h[it.dst_col + e] = __float2half_rn(it.wx[(size_t)r * it.wx_ld + it.wx_col0 + e]);
+    uint8_t* dst = blob + (size_t)it.dst_off16 * 16;
+    *reinterpret_cast<uint4*>(dst + aux_offset(i, 0)) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(dst + aux_offset(i, 8)) = *reinterpret_cast<const uint4*>(h + 8);
+  }
+}
+
+struct AuxSpec {
+  bool on = false;
+  const float* bias = nullptr; int bias_n = 0;
+  const float* wx = nullptr; int wx_ld = 0, wx_rows = 0, wx_col0 = 0, wx_ncols = 0, dst_col = 0;
+};
+inline AuxSpec aux_bias(const float* b, int n) { AuxSpec a; a.on = true; a.bias = b; a.bias_n = n; return a; }
 
 struct Builder {
   std::vector<MmaStep> steps;
   std::vector<PackItem> items;
+  std::vector<AuxItem> aux_items;
   uint32_t off16 = 0;
 
   // one accumulation chunk: D[:, tmem_col : tmem_col+n] (+)= sum over the listed sources.
@@ -75,7 +113,7 @@ struct Builder {
   // Backward (transpose=true): B tile row i <-> W col row0+i (an input unit), col k <-> W row col0+k.
   struct Src { int a_slab, col0, ksteps, mode; const float* W = nullptr; int rows = 0, cols = 0; };
   void chunk(const float* W, int rows, int cols, int row0, int n, int tmem_col, const std::vector<Src>& srcs,
-             bool transpose = false, bool accumulate_all = false) {
+             bool transpose = false, bool accumulate_all = false, const AuxSpec& aux = AuxSpec()) {
     bool first = !accumulate_all;
     for (const Src& s : srcs) {
       MmaStep st{};
@@ -86,6 +124,7 @@ struct Builder {
       st.ksteps = (uint8_t)s.ksteps;
       st.first = first ? 1 : 0;
       st.last = 0;
+      st.bytes16 = (uint16_t)(n * 128 / 16);
       steps.push_back(st);
       PackItem it{};
       const bool own = s.rows > 0;
@@ -98,11 +137,30 @@ struct Builder {
       off16 += (uint32_t)(n * 128 / 16);
       first = false;
     }
+    if (aux.on) {      // bias (+ per-ray input columns) as one more K=16 step
+      MmaStep st{};
+      st.w_off16 = off16;
+      st.n = (uint16_t)n;
+      st.tmem_col = (uint16_t)tmem_col;
+      st.a_slab = (uint8_t)kAuxSlab;
+      st.ksteps = 1;
+      st.first = first ? 1 : 0;
+      st.bytes16 = (uint16_t)(n * 32 / 16);
+      steps.push_back(st);
+      AuxItem it{};
+      it.bias = aux.bias; it.bias_n = aux.bias_n;
+      it.wx = aux.wx; it.wx_ld = aux.wx_ld; it.wx_rows = aux.wx_rows; it.wx_col0 = aux.wx_col0;
+      it.wx_ncols = aux.wx_ncols; it.dst_col = aux.dst_col;
+      it.row0 = row0; it.n = n; it.dst_off16 = off16;
+      aux_items.push_back(it);
+      off16 += (uint32_t)(n * 32 / 16);
+    }
   }
   void end_phase() { steps.back().last = 1; }
 };
 
-// Forward order; must match the phase sequence of mlp_fwd.cu.
+// Forward order; must match the phase sequence of mlp_fwd.cu.  Every chunk ends with an aux step
+// that adds the layer's bias (and, for the sun / beta heads, the per-ray input columns).
 void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) {
   const NetDims d = make_dims(c);
   const int ink = d.in_ksteps;
@@ -114,7 +172,8 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   // layer 0: split-precision product  in_hi*W_hi + in_lo*W_hi + in_hi*W_lo   (models/spnerf.py:202)
   for (int g = 0; g < 2; ++g)
     b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, g * kHalf, kHalf, g * kHalf,
-            {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}});
+            {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}}, false, false,
+            aux_bias(P[SPNERF_P_FC_W0 + 1], kFeat));
   b.end_phase();
   for (int i = 1; i < 8; ++i) {   // models/spnerf.py:203-208, skip concat [h, input] at :327
     const bool skip = (i == c.skip_layer);
@@ -122,17 +181,19 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     for (int g = 0; g < 2; ++g) {
       auto srcs = act8(kFeat);
       if (skip) srcs.push_back({kSlabInpHi, kFeat, ink, 0});
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs);
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs, false, false,
+              aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], kFeat));
     }
     b.end_phase();
   }
   // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212)
-  if (c.sem) b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat));
+  if (c.sem) b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat), false, false,
+                     aux_bias(P[SPNERF_P_SEM0_B], kHalf));
   {
     // sigma: B row 0 = fp16(w), row 1 = residual; the epilogue adds the two accumulator columns
     auto srcs = act8(kFeat);
     const size_t i0 = b.items.size();
-    b.chunk(P[SPNERF_P_SIGMA_W], 1, kFeat, 0, 16, kHalf, srcs);
+    b.chunk(P[SPNERF_P_SIGMA_W], 1, kFeat, 0, 16, kHalf, srcs, false, false, aux_bias(P[SPNERF_P_SIGMA_B], 1));
     const size_t i1 = b.items.size();
     for (size_t i = i0; i < i1; ++i) {
       b.items[i].n = 1;
@@ -143,21 +204,31 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   }
   b.end_phase();
   for (int g = 0; g < 2; ++g)   // feats_from_xyz (:215)
-    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, act8(kFeat));
+    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, act8(kFeat), false, false,
+            aux_bias(P[SPNERF_P_FEATS_B], kFeat));
   b.end_phase();
-  b.chunk(P[SPNERF_P_RGB0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat));                 // :226-231
+  AuxSpec sun0 = aux_bias(P[SPNERF_P_SUN0_W + 1], kHalf);          // + sun direction columns (:351)
+  sun0.wx = P[SPNERF_P_SUN0_W]; sun0.wx_ld = kFeat + 3; sun0.wx_rows = kHalf; sun0.wx_col0 = kFeat;
+  sun0.wx_ncols = 3; sun0.dst_col = kAuxColSun;
+  b.chunk(P[SPNERF_P_RGB0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat), false, false,
+          aux_bias(P[SPNERF_P_RGB0_B], kHalf));                                           // :226-231
   if (c.beta) {
-    b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, 0, kHalf, kHalf, act8(kFeat));   // :258-264
+    AuxSpec beta0 = aux_bias(P[SPNERF_P_BETA0_B], kHalf);          // + transient embedding columns (:360)
+    beta0.wx = P[SPNERF_P_BETA0_W]; beta0.wx_ld = kFeat + c.t_dim; beta0.wx_rows = kHalf; beta0.wx_col0 = kFeat;
+    beta0.wx_ncols = c.t_dim; beta0.dst_col = kAuxColT;
+    b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, 0, kHalf, kHalf, act8(kFeat), false, false, beta0);   // :258-264
     b.end_phase();
-    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, 0, act8(kFeat));              // :234-241
+    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, 0, act8(kFeat), false, false, sun0);               // :234-241
     b.end_phase();
   } else {
-    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, kHalf, act8(kFeat));
+    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, kHalf, act8(kFeat), false, false, sun0);
     b.end_phase();
   }
-  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, act8(kHalf));
+  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, act8(kHalf), false, false,
+          aux_bias(P[SPNERF_P_SUN0_W + 3], kHalf));
   b.end_phase();
-  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, act8(kHalf));
+  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, act8(kHalf), false, false,
+          aux_bias(P[SPNERF_P_SUN0_W + 5], kHalf));
   b.end_phase();
 }
 
@@ -211,7 +282,7 @@ struct PackPlan {
   uint32_t boff = 0;
   std::vector<CopyItem> cp;
   SmallOffsets o;
-  size_t bytes_f, bytes_b, bytes_c;
+  size_t bytes_f, bytes_b, bytes_c, bytes_a;
 };
 
 void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan& pl) {
@@ -219,8 +290,8 @@ void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan&
   build_backward(*cfg, P, pl.bsteps, &pl.bitems, &pl.boff);
   const SmallOffsets o = make_small_offsets(*cfg);
   pl.o = o;
-  auto add = [&](int slot, int dst, int rows, int cols, int ld, int col0 = 0, int transpose = 0) {
-    pl.cp.push_back({P[slot] ? P[slot] + col0 : nullptr, dst, rows, cols, ld, transpose});
+  auto add = [&](int slot, int dst, int rows, int cols, int ld, int col0 = 0, int transpose = 0, int dst_ld = 0) {
+    pl.cp.push_back({P[slot] ? P[slot] + col0 : nullptr, dst, rows, cols, ld, transpose, dst_ld ? dst_ld : rows});
   };
   for (int i = 0; i < 8; ++i) add(SPNERF_P_FC_W0 + 2 * i + 1, o.fc_b[i], 1, kFeat, kFeat);
   add(SPNERF_P_SIGMA_B, o.sigma_b, 1, 1, 1);
@@ -250,9 +321,15 @@ void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan&
   add(SPNERF_P_SKY0_B, o.sky0_b, 1, kHalf, kHalf);
   add(SPNERF_P_SKY2_W, o.sky2_w, 3, kHalf, kHalf);
   add(SPNERF_P_SKY2_B, o.sky2_b, 1, 3, 3);
+  // image of the shared-memory parameter region (net_plan.h kOffRgb2..): [j][4] / [j][8] / [j] / [j]
+  add(SPNERF_P_RGB2_W, o.smallw, 3, kHalf, kHalf, 0, 1, 4);
+  if (cfg->sem) add(SPNERF_P_SEM2_W, o.smallw + 1024, cfg->num_sem_classes, kHalf, kHalf, 0, 1, 8);
+  add(SPNERF_P_SUN0_W + 6, o.smallw + 3072, 1, kHalf, kHalf);
+  if (cfg->beta) add(SPNERF_P_BETA2_W, o.smallw + 3328, 1, kHalf, kHalf);
   pl.bytes_f = pl.f.items.size() * sizeof(PackItem);
   pl.bytes_b = pl.bitems.size() * sizeof(PackItem);
   pl.bytes_c = pl.cp.size() * sizeof(CopyItem);
+  pl.bytes_a = pl.f.aux_items.size() * sizeof(AuxItem);
 }
 }  // namespace
 
@@ -261,7 +338,7 @@ extern "C" int64_t spnerf_net_pack_workspace_bytes(const SpnerfNetConfig* cfg) {
   const float* P[SPNERF_NUM_PARAMS] = {};
   PackPlan pl;
   make_pack_plan(cfg, P, pl);
-  return (int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c + 256);
+  return (int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c + pl.bytes_a + 256);
 }
 
 // Uploads the pack tables (they embed the parameter pointers) and the two step tables, and zeroes
@@ -276,11 +353,13 @@ extern "C" int spnerf_net_prepare(const SpnerfNetConfig* cfg, const float* const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PackPlan pl;
   make_pack_plan(cfg, P, pl);
-  if ((int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c) > pack_ws_bytes) return SPNERF_ERR_WORKSPACE;
+  if ((int64_t)(pl.bytes_f + pl.bytes_b + pl.bytes_c + pl.bytes_a) > pack_ws_bytes) return SPNERF_ERR_WORKSPACE;
   uint8_t* sc = static_cast<uint8_t*>(pack_ws);
   cudaMemcpyAsync(sc, pl.f.items.data(), pl.bytes_f, cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(sc + pl.bytes_f, pl.bitems.data(), pl.bytes_b, cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(sc + pl.bytes_f + pl.bytes_b, pl.cp.data(), pl.bytes_c, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(sc + pl.bytes_f + pl.bytes_b + pl.bytes_c, pl.f.aux_items.data(), pl.bytes_a, cudaMemcpyHostToDevice,
+                  stream);
   cudaMemcpyAsync(fwd_steps, pl.f.steps.data(), pl.f.steps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(bwd_steps, pl.bsteps.data(), pl.bsteps.size() * sizeof(MmaStep), cudaMemcpyHostToDevice, stream);
   cudaMemsetAsync(fwd_blob, 0, (size_t)pl.f.off16 * 16, stream);
@@ -307,6 +386,9 @@ extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, 
       reinterpret_cast<const PackItem*>(sc + pl.bytes_f), static_cast<uint8_t*>(bwd_blob));
   small_copy_kernel<<<(unsigned)pl.cp.size(), 256, 0, stream>>>(
       reinterpret_cast<const CopyItem*>(sc + pl.bytes_f + pl.bytes_b), small);
+  if (!pl.f.aux_items.empty())
+    aux_pack_kernel<<<(unsigned)pl.f.aux_items.size(), 256, 0, stream>>>(
+        reinterpret_cast<const AuxItem*>(sc + pl.bytes_f + pl.bytes_b + pl.bytes_c), static_cast<uint8_t*>(fwd_blob));
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

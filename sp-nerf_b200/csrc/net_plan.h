@@ -13,29 +13,52 @@ namespace net {
 constexpr int kTileM = 128;          // points per tile (= accumulator rows = TMEM lanes)
 constexpr int kSlabBytes = 16384;    // 128 rows x 64 halves, 128B-swizzled (sm100.cuh)
 constexpr int kActSlabs = 8;         // 512-wide activation tile
-constexpr int kSlabInpHi = 8;        // encoded input (fp16 high part)
-constexpr int kSlabInpLo = 9;        // encoded input (fp16 residual); scratch after layer 0
-constexpr int kNumSlabs = 10;
+constexpr int kSlabInpHi = 8;        // encoded input (fp16 high part); scratch after the skip layer
+constexpr int kSlabInpLo = 0;        // encoded input (fp16 residual): aliases activation slab 0, which is
+                                     // dead until the first layer's epilogue overwrites it
+constexpr int kNumSlabs = 9;
+// parameter region: the 16-column "aux" operand + the tiny last-layer weights (resident for the
+// whole kernel, read by the epilogue with broadcast shared-memory loads)
+constexpr int kOffAux = kNumSlabs * kSlabBytes;      // 128 rows x 16 halves, no-swizzle K-major (4 KB)
+constexpr int kOffRgb2 = kOffAux + 4096;             // float4[256]: rgb_from_xyzdir.2 rows (3) per hidden unit
+constexpr int kOffSem2 = kOffRgb2 + 4096;            // float4[256][2]: logit_from_label.2 rows (<= 8)
+constexpr int kOffWst = kOffSem2 + 8192;
 constexpr int kWStageBytes = 32768;  // one weight item: up to 256 rows x 64 k
 constexpr int kNumWStages = 2;
-constexpr int kSmemBars = kNumSlabs * kSlabBytes + kNumWStages * kWStageBytes;
-constexpr int kSmemTotal = kSmemBars + 256;
+constexpr int kSmemBars = kOffWst + kNumWStages * kWStageBytes;
+constexpr int kOffSun6 = kSmemBars + 256;            // float[256] sun_v_net.6 row
+constexpr int kOffBeta2 = kOffSun6 + 1024;           // float[256] beta_from_xyz.2 row
+constexpr int kSmemTotal = kOffBeta2 + 1024;
+static_assert(kSmemTotal <= 232448, "shared memory budget");
+// fp32 block mirrored into the parameter region at kernel start (floats): rgb2 | sem2 | sun6 | beta2
+constexpr int kSmallWFloats = 1024 + 2048 + 256 + 256;
 
 constexpr int kFeat = 512;
 constexpr int kHalf = 256;
-constexpr int kMaxSteps = 320;
+constexpr int kMaxSteps = 384;
+constexpr int kAuxSlab = 255;        // MmaStep::a_slab value naming the aux operand
 
-// One weight item = one 64-wide K slab of one accumulation chunk.
+// One weight item = one 64-wide K slab of one accumulation chunk (or its 16-wide aux step).
 struct __align__(16) MmaStep {
   uint32_t w_off16;   // offset of the packed B tile in the weight blob, in 16-byte units
   uint16_t n;         // B rows (accumulator columns) of this item
   uint16_t tmem_col;  // first accumulator column
-  uint8_t a_slab;     // shared-memory slab holding the A operand
+  uint8_t a_slab;     // shared-memory slab holding the A operand, or kAuxSlab
   uint8_t ksteps;     // K=16 instructions to issue from this slab (1..4)
   uint8_t first;      // 1: overwrite the accumulator (first item of a chunk)
   uint8_t last;       // 1: last item of a phase -> signal the epilogue
-  uint32_t _pad;
+  uint16_t bytes16;   // item size in 16-byte units
+  uint16_t _pad;
 };
+
+// The aux operand: per point [1, sun_dir(3), t_emb(<=8), 1, 0, 0, 0].  Multiplying it by a B tile
+// that holds [fp16(b), W[:, sun columns], W[:, t columns], b - fp16(b)] folds the bias and the
+// per-ray input columns of a layer into its GEMM (models/spnerf.py:351,360 concatenations).
+constexpr int kAuxColOne = 0, kAuxColSun = 1, kAuxColT = 4, kAuxColOneLo = 12;
+// byte offset of element (row, col) inside a no-swizzle K-major 16-column operand
+__host__ __device__ constexpr uint32_t aux_offset(uint32_t row, uint32_t col) {
+  return (row >> 3) * 256u + (col >> 3) * 128u + (row & 7u) * 16u + (col & 7u) * 2u;
+}
 
 // Offsets (in floats) into the small fp32 parameter block copied by the pack kernel.
 struct SmallOffsets {
@@ -47,6 +70,7 @@ struct SmallOffsets {
   int beta0_b, beta0_wt, beta2_w, beta2_b;
   int emb;       // (C+1, emb_dim)
   int sky0_w, sky0_b, sky2_w, sky2_b;
+  int smallw;    // image of the shared-memory parameter region: rgb2 f4[256] | sem2 f4[256][2] | sun6 | beta2
   int total;
 };
 
@@ -133,6 +157,7 @@ inline SmallOffsets make_small_offsets(const SpnerfNetConfig& c) {
   o.beta0_b = take(kHalf); o.beta0_wt = take(8 * kHalf); o.beta2_w = take(kHalf); o.beta2_b = take(1);
   o.emb = take(9 * 8);
   o.sky0_w = take(3 * kHalf); o.sky0_b = take(kHalf); o.sky2_w = take(3 * kHalf); o.sky2_b = take(3);
+  o.smallw = take(kSmallWFloats);
   o.total = s;
   (void)c;
   return o;

@@ -21,6 +21,11 @@ CASES = {
     "mnmajor_n64_k64": ("mn", 64, 64, "std"),
     "mnmajor_n256_k128_swapped": ("mn", 256, 128, "swap"),
     "amn_bk_n128_k64": ("amn_bk", 128, 64, "std"),
+    # no-swizzle K-major core-matrix layout (8 rows x 16 B contiguous), used for the 16-column aux operand
+    "kns_n256_k16": ("kns", 256, 16, "std"),
+    "kns_n256_k64": ("kns", 256, 64, "std"),
+    "kns_n16_k16": ("kns", 16, 16, "std"),
+    "a_sw128_b_kns_n256_k64": ("a_sw_b_kns", 256, 64, "std"),
 }
 
 
@@ -55,7 +60,22 @@ def run_case(name):
             return img, offs, slab.smem_desc_template(1024, slab_bytes)
         return img, offs, slab.smem_desc_template(slab_bytes, 1024)
 
-    if mode == "k":
+    def kns(x):
+        # no swizzle: [row/8][k/8][8 rows][8 halves]; LBO = 128 (next core matrix along K), SBO = (K/8)*128
+        rows, kk = x.shape
+        img = np.ascontiguousarray(x.reshape(rows // 8, 8, kk // 8, 8).transpose(0, 2, 1, 3)).view(np.uint8).reshape(-1)
+        offs = [s * 256 for s in range(ksteps)]
+        return img, offs, slab.smem_desc_template(128, (kk // 8) * 128, swizzle=0)
+
+    if mode == "kns":
+        a_img, a_off, a_t = kns(a)
+        b_img, b_off, b_t = kns(b)
+        idesc = slab.idesc_f16(128, n, 0, 0)
+    elif mode == "a_sw_b_kns":
+        a_img, a_off, a_t = kmajor(a, 128)
+        b_img, b_off, b_t = kns(b)
+        idesc = slab.idesc_f16(128, n, 0, 0)
+    elif mode == "k":
         a_img, a_off, a_t = kmajor(a, 128)
         b_img, b_off, b_t = kmajor(b, n)
         idesc = slab.idesc_f16(128, n, 0, 0)
