@@ -7,6 +7,7 @@
 //   * left in shared memory as the A operand of the next (earlier) layer's GEMM, and
 //   * streamed to the gradient save area, where the weight-gradient GEMMs (mlp_wgrad.cu) read it.
 // Same roles / handshake as mlp_fwd.cu; step order from build_backward() in mlp_pack.cu.
+#include <cstdlib>
 #include "mlp_roles.cuh"
 
 using namespace roles;
@@ -16,7 +17,7 @@ namespace {
 struct BwdParams {
   const float* g_out; const float* out; const float* rays; const int64_t* labels; const float* t_emb;
   int64_t n_rays; int64_t n_points; int n_samples;
-  const uint8_t* blob; const MmaStep* steps; int n_steps;
+  const uint8_t* blob; int64_t blob_stride; int blob_copies; StepTable tab;
   const float* small; SmallOffsets so; SaveMap sm; GradMap gm;
   const uint8_t* saves; uint8_t* gsaves;
   const float* absmax; float* scale_out;
@@ -32,18 +33,27 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
+// derivative of a sine layer from its saved output: |cos| = sqrt(1 - y^2), sign from the saved bit
+__device__ __forceinline__ float dsin(float y, uint32_t sb, int k) {
+  float c;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(__saturatef(fmaf(-y, y, 1.f))));     // one MUFU
+  return __uint_as_float(__float_as_uint(c) ^ ((sb >> k) << 31));
+}
+
 // G[j] = acc[j] * dact(j) for columns [j0, j0+ncols) of a chunk at TMEM address taddr;
-// MODE 0: dact = cos(x)  (x = saved fp16 sine argument)     MODE 1: dact = 30 * saved cos     MODE 2: dact = 1
-// result -> fp16 -> shared slab at column dst_col0 + j (streamed to the gradient save area afterwards)
+// MODE 0: dact = cos(x) rebuilt from (ysave, ssave)     MODE 1: dact = 30 cos(30 x), same     MODE 2: dact = 1
+// result -> fp16 -> shared slab at column dst_col0 + j (copied to the gradient save area afterwards)
 template <int MODE>
-__device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, const uint8_t* xsave, uint8_t* act,
-                                            int dst_col0, int row) {
+__device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, const uint8_t* ysave, const uint8_t* ssave,
+                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave = nullptr) {
 #pragma unroll 1
   for (int jb = j0; jb < j0 + ncols; jb += 32) {
-    uint4 xr[4];
+    uint4 yr[4];
+    uint32_t sb = 0;
     if (MODE != 2) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) xr[c] = ldg16(xsave + xsave_off(jb + c * 8, row));
+      for (int c = 0; c < 4; ++c) yr[c] = ldg16(ysave + xsave_off(jb + c * 8, row));
+      sb = __ldg(reinterpret_cast<const uint32_t*>(ssave + sbit_off(jb, row)));
     }
     uint32_t v[32];
     tmem_ld32(taddr + jb, v);
@@ -52,17 +62,20 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, c
     for (int c = 0; c < 4; ++c) {
       float g[8];
       if (MODE != 2) {
-        float x[8];
-        unpack8(xr[c], x);
+        float y[8];
+        unpack8(yr[c], y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? __cosf(x[e]) : 30.f * x[e]);
+        for (int e = 0; e < 8; ++e) {
+          const float d = dsin(y[e], sb, c * 8 + e);
+          g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? d : 30.f * d);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
       }
-      *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
-          make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+      const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+      *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
+      if (gsave) stg16(gsave + xsave_off(jb + c * 8, row), gp);
     }
   }
 }
@@ -71,18 +84,21 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, c
 //   G[j] = coefw(j) * cos(x[j])   for j in [j0, j0+ncols),  coefw(j) = sum_c g_c * W2[c][j] from shared memory
 // `each(j, G)` lets the caller fold further per-row reductions (t_emb gradient).
 template <class CoefW, class Each>
-__device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, const uint8_t* xsave, uint8_t* act,
-                                            int dst_col0, int row, Each each) {
+__device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, const uint8_t* ysave, const uint8_t* ssave,
+                                            uint8_t* act, int dst_col0, int row, Each each) {
 #pragma unroll 1
-  for (int jb = j0; jb < j0 + ncols; jb += 16) {
-    const uint4 xr0 = ldg16(xsave + xsave_off(jb, row)), xr1 = ldg16(xsave + xsave_off(jb + 8, row));
+  for (int jb = j0; jb < j0 + ncols; jb += 32) {
+    uint4 yr[4];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float x[8], g[8];
-      unpack8(c ? xr1 : xr0, x);
+    for (int c = 0; c < 4; ++c) yr[c] = ldg16(ysave + xsave_off(jb + c * 8, row));
+    const uint32_t sb = __ldg(reinterpret_cast<const uint32_t*>(ssave + sbit_off(jb, row)));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float y[8], g[8];
+      unpack8(yr[c], y);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        g[e] = coefw(jb + c * 8 + e) * __cosf(x[e]);
+        g[e] = coefw(jb + c * 8 + e) * dsin(y[e], sb, c * 8 + e);
         each(jb + c * 8 + e, g[e]);
       }
       *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
@@ -98,13 +114,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem sh = carve(smem);
   uint8_t* act = sh.act;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw);
+  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, p.debug);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
   // power-of-two gradient scale keeping fp16 operands in range
   float scale = 1.f;
@@ -120,9 +137,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   const float inv_scale = 1.f / scale;
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(sh, p.blob, p.steps, p.n_steps, n_tiles, p.debug);
-  } else if (warp == 1) {
-    if (lane == 0) mma_loop(sh, tmem_base, p.steps, p.n_steps, n_tiles, p.debug);
+    producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
+  } else if (warp == 1 || warp == 2) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
+    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
   } else if (warp >= kEpiWarp0) {
     const int cg = (warp - kEpiWarp0) >> 2;
     const int row = (warp & 3) * 32 + lane;
@@ -134,16 +152,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
     const int wide_cols = (p.debug & 2) ? 32 : 128;
     EpiSync sync(sh, p.prof);
-    mbar_wait(sh.bar_par, 0, 31);
+    if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
+    __syncwarp();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < n_iters; ++it) {
+      // this CTA's tile of the pair; an odd tile count leaves rank 1 a phantom tile: it reads tile 0's
+      // saves (finite values, multiplied by zero gradients) and stores nothing
+      const int64_t tile = 2 * ((blockIdx.x >> 1) + it * (gridDim.x >> 1)) + sh.rank;
+      const bool tile_ok = tile < n_tiles;
       const int64_t pt = tile * kTileM + row;
       const bool valid = pt < p.n_points;
       const int64_t ray = valid ? pt / p.n_samples : 0;
-      const uint8_t* tsave = p.saves + (size_t)tile * p.sm.total * kSlabBytes;
-      uint8_t* tg = p.gsaves + (size_t)tile * p.gm.total * kSlabBytes;
+      const uint8_t* tsave = p.saves + (size_t)(tile_ok ? tile : 0) * p.sm.total * kSlabBytes;
+      uint8_t* tg = tile_ok ? p.gsaves + (size_t)tile * p.gm.total * kSlabBytes : nullptr;
       auto xs = [&](int slab) { return tsave + (size_t)slab * kSlabBytes; };
-      auto gs = [&](int slab) { return tg + (size_t)slab * kSlabBytes; };
+      auto gs = [&](int slab) -> uint8_t* { return tg ? tg + (size_t)slab * kSlabBytes : nullptr; };
 
       // ---- head-level gradients of this row (fp32, unscaled) ----
       sync.stamp();
@@ -167,15 +190,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       sync.drain_stores();
       // small-gradient slab [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)] (scaled), the B operand
       // of the tiny last-layer weight gradients; bias gradients of those layers are reduced right here
-      if (cg == 0) {
+      if (cg == 0 && tile_ok) {
         uint8_t* d = gs(p.gm.gsmall);
         const float sc = scale;
-        stg16(d + slab_chunk_offset(row, 0),
+        stg16(d + xsave_off(0, row),
               make_uint4(pack2(g_u[0] * sc, g_u[1] * sc), pack2(g_u[2] * sc, g_v * sc), pack2(g_sp * sc, g_bp * sc), 0u));
-        stg16(d + slab_chunk_offset(row, 1),
+        stg16(d + xsave_off(8, row),
               make_uint4(pack2(g_lg[0] * sc, g_lg[1] * sc), pack2(g_lg[2] * sc, g_lg[3] * sc),
                          pack2(g_lg[4] * sc, g_lg[5] * sc), pack2(g_lg[6] * sc, g_lg[7] * sc)));
-        for (int c = 2; c < 8; ++c) stg16(d + slab_chunk_offset(row, c), make_uint4(0, 0, 0, 0));
         float sums[14] = {g_u[0], g_u[1], g_u[2], g_v, g_sp, g_bp, g_lg[0], g_lg[1], g_lg[2], g_lg[3],
                           g_lg[4], g_lg[5], g_lg[6], g_lg[7]};
 #pragma unroll
@@ -187,26 +209,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       // ---- E_in: G_s3 = g_v * W_sun6 * cos(x_s3) -> slabs 0..3 ----
       {
         const float cv = g_v * scale;
-        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * 64, 64, xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
+        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * 64, 64, xs(p.sm.sun_y[2]), xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
       }
       sync.end(true);
-      sync.store_slabs(gs(p.gm.G_sun[2]), 0, 4);
+      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[2]));
       // ---- after sun_v_net.4^T: G_s2 ----
       sync.begin();
-      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_x[1]), act, 0, row);
+      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row);
       sync.end(true);
-      sync.store_slabs(gs(p.gm.G_sun[1]), 0, 4);
+      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[1]));
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
       sync.begin();
-      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_x[0]), act, 0, row);
+      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row);
       {
         const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
         gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * 64, 64,
-                    xs(p.sm.rgb_x), act, kHalf, row, NoEachG());
+                    xs(p.sm.rgb_y), xs(p.sm.rgb_x), act, kHalf, row, NoEachG());
       }
       sync.end(true);
-      sync.store_slabs(gs(p.gm.G_sun[0]), 0, 4);
-      sync.store_slabs(gs(p.gm.G_rgb), 4, 4);
+      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[0]));
+      copy_slabs_out(act, 4, 4, gs(p.gm.G_rgb));
       if (p.beta) {
         // ---- beta hidden G_b1 -> slabs 0..3 (the sun/albedo GEMMs have retired); d t_emb on the way ----
         sync.begin();
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         for (int e = 0; e < 8; ++e) tacc[e] = 0.f;
         const float cb = g_bp * scale;
         const float* wt = S + p.so.beta0_wt;
-        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * 64, 64, xs(p.sm.beta_x), act, 0, row,
+        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * 64, 64, xs(p.sm.beta_y), xs(p.sm.beta_x), act, 0, row,
                     [&](int j, float g) {
 #pragma unroll
                       for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * kHalf + j), tacc[e]);
@@ -223,13 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         if (p.g_t_emb && valid)
           for (int e = 0; e < p.t_dim; ++e) atomicAdd(p.g_t_emb + ray * p.t_dim + e, tacc[e] * inv_scale);
         sync.end(true);
-        sync.store_slabs(gs(p.gm.G_beta), 0, 4);
+        copy_slabs_out(act, 0, 4, gs(p.gm.G_beta));
       }
       // ---- g_f (linear) -> slabs 0..7 ----
       sync.begin();
-      bwd_columns<2>(taddr, cg * 128, wide_cols, nullptr, act, 0, row);
+      bwd_columns<2>(taddr, cg * 128, wide_cols, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr);
       sync.end(true);
-      sync.store_slabs(gs(p.gm.g_f), 0, 8);
+      copy_slabs_out(act, 4, 4, gs(p.gm.g_f + 4));
       // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
       sync.begin();
       if (p.sem) {
@@ -245,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             a += fmaf(cf[4], u.x, fmaf(cf[5], u.y, fmaf(cf[6], u.z, cf[7] * u.w)));
           }
           return a;
-        }, cg * 64, 64, xs(p.sm.sem_x), act, 0, row, NoEachG());
+        }, cg * 64, 64, xs(p.sm.sem_y), xs(p.sm.sem_x), act, 0, row, NoEachG());
       }
       if (cg == 3) {
         *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 0)) =
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
       sync.end(true);
-      if (p.sem) sync.store_slabs(gs(p.gm.G_sem), 0, 4);
+      if (p.sem) copy_slabs_out(act, 0, 4, gs(p.gm.G_sem));
       // ---- G_7 = g_h * cos(x_7), then the trunk ----
       float gemb[8];
 #pragma unroll
@@ -271,11 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       };
       for (int L = 7; L >= 0; --L) {
         sync.begin();
-        if (L > 0) bwd_columns<0>(taddr, cg * 128, wide_cols, xs(p.sm.x[L]), act, 0, row);
-        else       bwd_columns<1>(taddr, cg * 128, wide_cols, xs(p.sm.x[0]), act, 0, row);
+        // half of the gradient tile leaves from registers now, half from shared memory during the next MMAs
+        uint8_t* gdirect = cg < 2 ? gs(p.gm.G[L]) : nullptr;
+        if (L > 0) bwd_columns<0>(taddr, cg * 128, wide_cols, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect);
+        else       bwd_columns<1>(taddr, cg * 128, wide_cols, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
-        sync.store_slabs(gs(p.gm.G[L]), 0, 8);
+        copy_slabs_out(act, 4, 4, gs(p.gm.G[L] + 4));
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }
@@ -320,8 +344,18 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   BwdParams p;
   p.g_out = a->g_out; p.out = a->out; p.rays = a->rays; p.labels = a->labels; p.t_emb = a->t_emb;
   p.n_rays = a->n_rays; p.n_samples = a->n_samples; p.n_points = a->n_rays * a->n_samples;
-  p.blob = static_cast<const uint8_t*>(a->blob); p.steps = static_cast<const MmaStep*>(a->steps);
-  p.n_steps = a->n_steps; p.small = a->small;
+  p.blob = static_cast<const uint8_t*>(a->blob);
+  const StepTable* tab = step_table(a->cfg, 1);
+  if (!tab) return SPNERF_ERR_UNSUPPORTED;
+  p.tab = *tab;
+  {
+    const char* e = getenv("SPNERF_BLOB_COPIES");      // experiment: replicas of the weight stream (engine.py allocates them)
+    p.blob_copies = e ? atoi(e) : 1;
+    if (p.blob_copies < 1) p.blob_copies = 1;
+    SpnerfNetSizes sz;
+    spnerf_net_sizes(&a->cfg, &sz);
+    p.blob_stride = sz.bwd_blob_bytes;
+  } p.small = a->small;
   p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg); p.gm = make_grad_map(a->cfg);
   p.saves = static_cast<const uint8_t*>(a->saves); p.gsaves = static_cast<uint8_t*>(a->grad_saves);
   p.absmax = a->g_absmax; p.scale_out = a->scale_out;
@@ -340,8 +374,10 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
-  mlp_bwd_kernel<<<(unsigned)(n_tiles < sms ? n_tiles : sms), kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  const int64_t n_pairs = ((p.n_points + kTileM - 1) / kTileM + 1) / 2;
+  const int64_t clusters = sms / 2;
+  mlp_bwd_kernel<<<2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters), kThreads, kSmemTotal,
+                   static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

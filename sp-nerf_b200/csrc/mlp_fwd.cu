@@ -13,6 +13,7 @@
 // slabs, sine arguments through row-interleaved coalesced stores.
 // Phases alternate MMA and epilogue (handshake on two mbarriers); the step list built by
 // mlp_pack.cu fixes the order on both sides.
+#include <cstdlib>
 #include "mlp_roles.cuh"
 
 using namespace roles;
@@ -23,7 +24,7 @@ struct FwdParams {
   const float* rays; const float* z; const float* xyz; const float* dir_override;
   const int64_t* labels; const float* t_emb; const float* sky;
   int64_t n_rays; int64_t n_points; int n_samples;
-  const uint8_t* blob; const MmaStep* steps; int n_steps;
+  const uint8_t* blob; int64_t blob_stride; int blob_copies; StepTable tab;
   const float* small; SmallOffsets so; SaveMap sm;
   float* out; uint8_t* saves;
   int mapping, sem, n_classes, emb_dim, beta, t_dim, in_dim, n_out, col_beta, col_sem;
@@ -33,37 +34,40 @@ struct FwdParams {
 
 // 32 accumulator columns [j0, j0+32) of one chunk (column 0 of the chunk at TMEM address `taddr`)
 // for this thread's row:  y = ACT(acc) ; y -> fp16 -> shared slab(s) at column dst_col0 + j
-// ACT 0: y = sin(x)      x (fp16) -> xsave, row-interleaved
-// ACT 1: y = sin(30 x)   cos(30 x) -> xsave                        (first layer, Siren w0 = 30)
-// ACT 2: y = x                                                      (feats_from_xyz)
-// ysave: direct (uncoalesced) copy of y in slab layout, for tiles that cannot pass through shared memory
+// ACT 0: y = sin(x)      ACT 1: y = sin(30 x)  (first layer, Siren w0 = 30)      ACT 2: y = x  (feats_from_xyz)
+// ssave: sign of the derivative cos(argument), one bit per column (the backward rebuilds
+//        |cos| = sqrt(1 - y^2)); the sign is the parity of rint(argument / pi), read off the mantissa
+//        LSB after adding 1.5 * 2^23
+// ysave: copy of y (fp16) in the row-interleaved layout, which the weight-gradient GEMMs read as a
+//        no-swizzle MN-major operand (mlp_wgrad.cu); used where y does not pass through shared memory
 // `each(j, y)` is called for every output (tiny last layers).
 template <int ACT, bool TO_SMEM, class Each>
-__device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, int dst_col0, int row, uint8_t* xsave,
+__device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, int dst_col0, int row, uint8_t* ssave,
                                           uint8_t* ysave, Each each) {
   uint32_t v[32];
   tmem_ld32(taddr + j0, v);
   tmem_wait_ld();
+  uint32_t sb = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int j = j0 + c * 8;
-    float y[8], s[8];
+    float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float x = __uint_as_float(v[c * 8 + e]);
-      if (ACT == 0) { y[e] = __sinf(x); s[e] = x; }
-      else if (ACT == 1) { const float a = 30.f * x; y[e] = __sinf(a); s[e] = __cosf(a); }
-      else { y[e] = x; s[e] = 0.f; }
+      if (ACT == 2) y[e] = x;
+      else {
+        const float a = (ACT == 1) ? 30.f * x : x;
+        y[e] = __sinf(a);
+        sb = __funnelshift_r(sb, __float_as_uint(fmaf(a, 0.318309886f, 12582912.f)), 1);   // bit (c*8+e) <- parity
+      }
       each(j + e, y[e]);
     }
     const uint4 yp = make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
-    const uint32_t off = slab_off(dst_col0 + j, row);
-    if (TO_SMEM) *reinterpret_cast<uint4*>(act + off) = yp;
-    if (ysave) stg16(ysave + slab_off(j, row), yp);
-    if (ACT != 2 && xsave)
-      stg16(xsave + xsave_off(j, row),
-            make_uint4(pack2(s[0], s[1]), pack2(s[2], s[3]), pack2(s[4], s[5]), pack2(s[6], s[7])));
+    if (TO_SMEM) *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + j, row)) = yp;
+    if (ysave) stg16(ysave + xsave_off(j, row), yp);
   }
+  if (ACT != 2 && ssave) *reinterpret_cast<uint32_t*>(ssave + sbit_off(j0, row)) = sb;
 }
 
 template <int ACT, bool TO_SMEM, class Each>
@@ -78,18 +82,20 @@ struct NoEach { __device__ __forceinline__ void operator()(int, float) const {} 
 __device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem sh = carve(smem);
   uint8_t* act = sh.act;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw);
+  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, p.debug);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(sh, p.blob, p.steps, p.n_steps, n_tiles, p.debug);
-  } else if (warp == 1) {
-    if (lane == 0) mma_loop(sh, tmem_base, p.steps, p.n_steps, n_tiles, p.debug);
+    producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
+  } else if (warp == 1 || warp == 2) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
+    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
   } else if (warp >= kEpiWarp0) {
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
     const int row = (warp & 3) * 32 + lane;    // TMEM lane quarter = warp % 4
@@ -102,13 +108,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
     float* scratch = reinterpret_cast<float*>(smem + kSlabInpHi * kSlabBytes);
     EpiSync sync(sh, p.prof);
-    mbar_wait(sh.bar_par, 0, 31);
+    if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
+    __syncwarp();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < n_iters; ++it) {
+      // this CTA's tile of the pair; an odd tile count leaves rank 1 a phantom tile (no rows, no stores)
+      const int64_t tile = 2 * ((blockIdx.x >> 1) + it * (gridDim.x >> 1)) + sh.rank;
       const int64_t pt = tile * kTileM + row;
       const bool valid = pt < p.n_points;
       const int64_t ray = valid ? pt / p.n_samples : 0;
-      uint8_t* tsave = p.saves ? p.saves + (size_t)tile * p.sm.total * kSlabBytes : nullptr;
+      uint8_t* tsave = (p.saves && tile < n_tiles) ? p.saves + (size_t)tile * p.sm.total * kSlabBytes : nullptr;
       auto sv = [&](int slab) -> uint8_t* { return (tsave && slab >= 0) ? tsave + (size_t)slab * kSlabBytes : nullptr; };
       float* orow = p.out + pt * p.n_out;
 
@@ -170,6 +179,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
               make_uint4(hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]);
           *reinterpret_cast<uint4*>(act + kSlabInpLo * kSlabBytes + off) =
               make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
+          if (tsave) stg16(sv(p.sm.inp) + xsave_off(cg * 16 + c * 8, row),
+                           make_uint4(hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]));
         }
         if (cg == 1 || (tsave && cg == 2)) {     // aux: [1, sun(3), t_emb, 1(lo), 0...]
           float a[16];
@@ -186,13 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
             *reinterpret_cast<uint4*>(sh.aux + aux_offset(row, 8)) =
                 make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15]));
-          } else {                               // saved copy (slab layout): operand of the weight-gradient GEMMs
+          } else {                               // saved copy: operand of the weight-gradient GEMMs (16 columns)
             uint8_t* ax = sv(p.sm.aux);
-            stg16(ax + slab_chunk_offset(row, 0),
+            stg16(ax + xsave_off(0, row),
                   make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7])));
-            stg16(ax + slab_chunk_offset(row, 1),
+            stg16(ax + xsave_off(8, row),
                   make_uint4(pack2(a[8], a[9]), pack2(a[10], a[11]), pack2(a[12], a[13]), pack2(a[14], a[15])));
-            for (int c = 2; c < 8; ++c) stg16(ax + slab_chunk_offset(row, c), make_uint4(0, 0, 0, 0));
           }
         }
         if (valid && cg == 3) {     // sky colour is constant along the ray
@@ -200,19 +210,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
         }
       }
       sync.end(true);
-      sync.store_slabs(sv(p.sm.inp), kSlabInpHi, 1);
 
       // ---- trunk layer 0: sin(30 (W0 x + b0))  (spnerf.py:202, Siren w0=30) ----
       sync.begin();
-      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]), nullptr, NoEach());
+      // half of the tile leaves from registers during the epilogue, the other half from shared memory
+      // during the next MMA phase: global stores are the scarce resource (~13 B/cycle/SM chip-wide)
+      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]), cg < 2 ? sv(p.sm.y[0]) : nullptr,
+                        NoEach());
       sync.end(true);
-      sync.store_slabs(sv(p.sm.y[0]), 0, 8);
+      copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
       // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]), nullptr, NoEach());
+        epi_cols<0, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
+                          cg < 2 ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
-        sync.store_slabs(sv(p.sm.y[i]), 0, 8);
+        copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
       }
       // ---- heads on h: semantic hidden (accumulator columns 0..255) and sigma (256, 257) ----
       sync.begin();
@@ -243,9 +256,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
       sync.begin();
-      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr, nullptr, NoEach());
+      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr, cg < 2 ? sv(p.sm.f) : nullptr, NoEach());
       sync.end(true);
-      sync.store_slabs(sv(p.sm.f), 0, 8);
+      copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
 
       // ---- albedo hidden layer (columns 0..255) + first sun layer or beta hidden layer (256..511) ----
       sync.begin();
@@ -256,9 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
           c3[0] = fmaf(w.x, y, c3[0]); c3[1] = fmaf(w.y, y, c3[1]); c3[2] = fmaf(w.z, y, c3[2]);
         };
         if (!p.beta) {
-          // every input of this phase has been consumed: stage the albedo activations in slabs 4..7 and
-          // put the sun activations (next layer's operand) in slabs 0..3
-          epi_cols<0, true>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), nullptr, rgb_each);
+          // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs 0..3
+          epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
           epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), nullptr, NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
@@ -277,32 +289,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
             orow[c] = sigmoid_ref(c3[c] + S[p.so.rgb2_b + c]) * 1.002f - 0.001f;
       }
       sync.end(true);
-      if (!p.beta) {
-        sync.store_slabs(sv(p.sm.sun_y[0]), 0, 4);
-        sync.store_slabs(sv(p.sm.rgb_y), 4, 4);
-      } else {
+      if (p.beta) {
         sync.begin();
         epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), nullptr, NoEach());
         sync.end(true);
-        sync.store_slabs(sv(p.sm.sun_y[0]), 0, 4);
       }
+      copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[0]));
       // ---- sun layer 1 ----
       sync.begin();
       epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[1]), nullptr, NoEach());
       sync.end(true);
-      sync.store_slabs(sv(p.sm.sun_y[1]), 0, 4);
+      copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[1]));
       // ---- sun layer 2 + output unit (256 -> 1, sigmoid) ----
       sync.begin();
       {
         float part[1] = {0.f};
-        epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[2]), nullptr,
-                          [&](int j, float y) { part[0] = fmaf(Wsun6[j], y, part[0]); });
+        epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
+                           [&](int j, float y) { part[0] = fmaf(Wsun6[j], y, part[0]); });
         reduce_groups<1>(scratch, part, cg, row);
         if (cg == 0 && valid) orow[4] = sigmoid_ref(part[0] + S[p.so.sun6_b]);   // spnerf.py:352
       }
       // no signal: the next tile's input phase releases the MMA warp
       sync.end(false);
-      sync.store_slabs(sv(p.sm.sun_y[2]), 0, 4);
     }
     sync.finish();
   }
@@ -325,8 +333,18 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.rays = a->rays; p.z = a->z; p.xyz = a->xyz; p.dir_override = a->dir_override;
   p.labels = a->labels; p.t_emb = a->t_emb; p.sky = a->sky;
   p.n_rays = a->n_rays; p.n_samples = a->n_samples; p.n_points = a->n_rays * a->n_samples;
-  p.blob = static_cast<const uint8_t*>(a->blob); p.steps = static_cast<const MmaStep*>(a->steps);
-  p.n_steps = a->n_steps;
+  p.blob = static_cast<const uint8_t*>(a->blob);
+  const StepTable* tab = step_table(a->cfg, 0);
+  if (!tab) return SPNERF_ERR_UNSUPPORTED;
+  p.tab = *tab;
+  {
+    const char* e = getenv("SPNERF_BLOB_COPIES");      // experiment: replicas of the weight stream (engine.py allocates them)
+    p.blob_copies = e ? atoi(e) : 1;
+    if (p.blob_copies < 1) p.blob_copies = 1;
+    SpnerfNetSizes sz;
+    spnerf_net_sizes(&a->cfg, &sz);
+    p.blob_stride = sz.fwd_blob_bytes;
+  }
   p.small = a->small; p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg);
   p.out = a->out; p.saves = static_cast<uint8_t*>(a->saves);
   const NetDims d = make_dims(a->cfg);
@@ -346,8 +364,10 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
-  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+  const int64_t n_pairs = ((p.n_points + kTileM - 1) / kTileM + 1) / 2;
+  int64_t clusters = sms / 2;
+  if (const char* e = getenv("SPNERF_MAX_CLUSTERS")) { const int v = atoi(e); if (v > 0 && v < clusters) clusters = v; }
+  const unsigned grid = 2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters);
   mlp_fwd_kernel<<<grid, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;

@@ -112,8 +112,11 @@ struct Builder {
   // Forward (transpose=false): B tile row i <-> W row row0+i, tile col k <-> W col col0+k.
   // Backward (transpose=true): B tile row i <-> W col row0+i (an input unit), col k <-> W row col0+k.
   struct Src { int a_slab, col0, ksteps, mode; const float* W = nullptr; int rows = 0, cols = 0; };
+  std::vector<size_t> chunk_begin;      // first step of every chunk of the open phase
+  size_t phase_begin = 0;
   void chunk(const float* W, int rows, int cols, int row0, int n, int tmem_col, const std::vector<Src>& srcs,
              bool transpose = false, bool accumulate_all = false, const AuxSpec& aux = AuxSpec()) {
+    chunk_begin.push_back(steps.size());
     bool first = !accumulate_all;
     for (const Src& s : srcs) {
       MmaStep st{};
@@ -156,7 +159,30 @@ struct Builder {
       off16 += (uint32_t)(n * 32 / 16);
     }
   }
-  void end_phase() { steps.back().last = 1; }
+  // Closes a phase.  Its chunks (independent accumulator column ranges) are dealt to the two issuer
+  // lanes, balancing step counts, and the ring order interleaves the lanes so that both issuers
+  // always have an item in flight.  The order of the steps inside a chunk is preserved.
+  void end_phase() {
+    const size_t e = steps.size();
+    chunk_begin.push_back(e);
+    std::vector<MmaStep> lane_steps[2];
+    for (size_t c = 0; c + 1 < chunk_begin.size(); ++c) {
+      const int lane = lane_steps[0].size() <= lane_steps[1].size() ? 0 : 1;
+      for (size_t i = chunk_begin[c]; i < chunk_begin[c + 1]; ++i) {
+        MmaStep st = steps[i];
+        st.lane = (uint8_t)lane;
+        lane_steps[lane].push_back(st);
+      }
+    }
+    size_t o = phase_begin, a = 0, b = 0;
+    while (a < lane_steps[0].size() || b < lane_steps[1].size()) {
+      if (a < lane_steps[0].size()) steps[o++] = lane_steps[0][a++];
+      if (b < lane_steps[1].size()) steps[o++] = lane_steps[1][b++];
+    }
+    steps[e - 1].last = 1;
+    chunk_begin.clear();
+    phase_begin = e;
+  }
 };
 
 // Forward order; must match the phase sequence of mlp_fwd.cu.  Every chunk ends with an aux step
@@ -224,12 +250,12 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, kHalf, act8(kFeat), false, false, sun0);
     b.end_phase();
   }
-  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, act8(kHalf), false, false,
-          aux_bias(P[SPNERF_P_SUN0_W + 3], kHalf));
-  b.end_phase();
-  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, act8(kHalf), false, false,
-          aux_bias(P[SPNERF_P_SUN0_W + 5], kHalf));
-  b.end_phase();
+  for (int j = 1; j <= 2; ++j) {      // sun layers 1, 2: two 128-wide chunks, one per issuer lane
+    for (int g = 0; g < 2; ++g)
+      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, act8(kHalf), false, false,
+              aux_bias(P[SPNERF_P_SUN0_W + 2 * j + 1], kHalf));
+    b.end_phase();
+  }
 }
 
 int validate(const SpnerfNetConfig* c) {
@@ -246,6 +272,39 @@ int validate(const SpnerfNetConfig* c) {
 
 void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
                     std::vector<PackItem>* items, uint32_t* off16);   // mlp_pack_bwd section below
+
+// cached per configuration; entries are never freed or moved (callers keep the pointer for a launch)
+#include <map>
+#include <mutex>
+#include <array>
+#include <memory>
+const net::StepTable* net::step_table(const SpnerfNetConfig& cfg, int backward) {
+  static std::mutex mu;
+  static std::map<std::array<int32_t, 10>, std::unique_ptr<StepTable>> cache;
+  std::array<int32_t, 10> key{cfg.feat, cfg.layers, cfg.skip_layer, cfg.mapping, cfg.sem, cfg.num_sem_classes,
+                              cfg.emb_dim, cfg.beta, cfg.t_dim, backward};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second.get();
+  const float* P[SPNERF_NUM_PARAMS] = {};
+  std::vector<MmaStep> steps;
+  if (backward) {
+    uint32_t off = 0;
+    build_backward(cfg, P, steps, nullptr, &off);
+  } else {
+    Builder f;
+    build_forward(cfg, P, f);
+    steps = f.steps;
+  }
+  if ((int)steps.size() > kMaxSteps) return nullptr;
+  std::unique_ptr<StepTable> t(new StepTable());
+  std::memset(t.get(), 0, sizeof(StepTable));
+  t->n = (int)steps.size();
+  std::memcpy(t->s, steps.data(), steps.size() * sizeof(MmaStep));
+  const StepTable* r = t.get();
+  cache[key] = std::move(t);
+  return r;
+}
 
 extern "C" int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* s) {
   int rc = validate(cfg);
@@ -463,10 +522,11 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     return v;
   };
   // sun_v_net.4 and .2 (256x256): G_s3 -> g_s2 -> g_s1
-  b.chunk(P[SPNERF_P_SUN0_W + 4], kHalf, kHalf, 0, kHalf, 0, ks(0, 4), true);
-  b.end_phase();
-  b.chunk(P[SPNERF_P_SUN0_W + 2], kHalf, kHalf, 0, kHalf, 0, ks(0, 4), true);
-  b.end_phase();
+  for (int j = 2; j >= 1; --j) {      // two 128-wide chunks, one per issuer lane
+    for (int g = 0; g < 2; ++g)
+      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, ks(0, 4), true);
+    b.end_phase();
+  }
   // g_f = G_s1 * W_sun0[:, :512] + G_r1 * W_rgb0 (+ G_b1 * W_beta0[:, :512] in a second phase)
   for (int g = 0; g < 2; ++g) {
     std::vector<Src> v;

@@ -1,10 +1,18 @@
 // Warp roles shared by the forward and backward-data point-network kernels: the weight producer
 // and the MMA issuer, both driven by the step list of mlp_pack.cu, and the epilogue-side handshake.
 //
+// The kernels run as CTA pairs (cluster of 2, tcgen05 cta_group::2): each CTA owns a tile of 128
+// points (its activations are the A rows 128*rank.. of an M = 256 MMA) and streams only half of
+// every weight tile (B rows (n/2)*rank..), so a weight byte fetched from L2 feeds 256 points.
 // 640 threads per CTA, one CTA per SM:
-//   warp 0        weight producer (one lane): 1-D bulk copies of pre-packed fp16 B tiles, 2-stage ring
-//   warp 1        MMA issuer (one lane): tcgen05.mma M=128, N<=256, K=16, fp16 x fp16 -> fp32 in TMEM
-//   warps 2-3     idle (keep the epilogue warps aligned to TMEM lane quarters)
+//   warp 0        weight producer (one lane): 1-D bulk copies of this CTA's half of the pre-packed
+//                 fp16 B tiles into a 4-stage ring
+//   warps 1, 2    rank 0: the two MMA issuers (tcgen05.mma M=256, N<=256, K=16, fp16 -> fp32 in TMEM).
+//                 Every phase is split into accumulator chunks owned by one issuer each (MmaStep::lane),
+//                 interleaved in ring order: one thread cannot issue 4 MMAs + a commit + a barrier
+//                 wait in the 512 cycles the tensor pipe needs for them (measured ~710).
+//                 rank 1, warp 1: relay, forwards "my ring stage landed" to the issuers
+//   warp 3        idle (keeps the epilogue warps aligned to TMEM lane quarters)
 //   warps 4-19    epilogue: warp w reads TMEM lanes 32*(w%4).., i.e. point row 32*(w%4)+lane, and
 //                 column group (w-4)/4 of the phase's accumulator
 #pragma once
@@ -24,12 +32,13 @@ struct Smem {
   uint8_t* act;
   uint8_t* aux;
   uint8_t* wst;
-  uint64_t* bar_full;    // [2] weight stage landed
-  uint64_t* bar_empty;   // [2] weight stage consumed
-  uint64_t* bar_mma;     // MMA phase retired -> epilogue
-  uint64_t* bar_epi;     // epilogue phase done -> MMA
+  uint64_t* bar_full;    // [4] weight stage landed (rank 0: both halves, see setup)
+  uint64_t* bar_empty;   // [4] weight stage consumed (arrives from the issuer's commit, both CTAs)
+  uint64_t* bar_mma;     // MMA phase retired -> epilogue (both CTAs)
+  uint64_t* bar_epi;     // rank 0 only: both epilogues done -> MMA
   uint64_t* bar_par;     // parameter region landed (once)
   uint32_t* tmem_slot;
+  uint32_t rank;
 };
 
 __device__ __forceinline__ Smem carve(uint8_t* smem) {
@@ -38,98 +47,150 @@ __device__ __forceinline__ Smem carve(uint8_t* smem) {
   s.aux = smem + kOffAux;
   s.wst = smem + kOffWst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
-  s.bar_full = bars; s.bar_empty = bars + 2; s.bar_mma = bars + 4; s.bar_epi = bars + 5; s.bar_par = bars + 6;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  s.bar_full = bars; s.bar_empty = bars + 4;
+  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  s.rank = cluster_ctarank();
   return s;
 }
 
-// all threads; returns the TMEM base address.  `smallw` (global image of the parameter region) is
-// copied into shared memory once; consumers wait on bar_par (parity 0).
-__device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const float* smallw) {
+// all threads of both CTAs; returns the TMEM base address.  `smallw` (global image of the parameter
+// region) is copied into shared memory once; consumers wait on bar_par (parity 0).
+__device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const float* smallw, int debug = 0) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { atomicCAS(&g_watchdog_code, 0u, 900u); __trap(); }
-    mbar_init(&s.bar_full[0], 1); mbar_init(&s.bar_full[1], 1);
-    mbar_init(&s.bar_empty[0], 1); mbar_init(&s.bar_empty[1], 1);
-    mbar_init(s.bar_mma, 1); mbar_init(s.bar_epi, 1); mbar_init(s.bar_par, 1);
+    for (int i = 0; i < kNumWStages; ++i) {
+      // issuer CTA: its own copy (arrive.expect_tx) + the peer's relay; peer CTA: its own copy only
+      mbar_init(&s.bar_full[i], (s.rank == 0 && !(debug & 8)) ? 2 : 1); mbar_init(&s.bar_empty[i], 1);
+    }
+    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1);
     fence_mbar_init();
     mbar_expect_tx(s.bar_par, kSmallWFloats * 4);
     bulk_g2s(smem + kOffRgb2, smallw, 3072 * 4, s.bar_par);              // rgb2 | sem2
     bulk_g2s(smem + kOffSun6, smallw + 3072, 512 * 4, s.bar_par);        // sun6 | beta2
   }
-  if (warp == 1) { tmem_alloc(s.tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc2(s.tmem_slot, 512); tmem_relinquish2(); }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   return *s.tmem_slot;
 }
 
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 1) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();      // the peer may still be signalling this CTA's barriers / reading its operands
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc2(tmem_base, 512);
 }
 
-// one lane of warp 0
-__device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob, const MmaStep* steps, int n_steps,
-                                              int64_t n_tiles, int debug) {
+// number of tile pairs this cluster processes
+__device__ __forceinline__ int64_t my_pairs(int64_t n_pairs) {
+  const int64_t c = blockIdx.x >> 1, nc = gridDim.x >> 1;
+  return c < n_pairs ? (n_pairs - c + nc - 1) / nc : 0;
+}
+
+// warp 0 of both CTAs (all lanes run the loop; one elected lane issues the copies)
+__device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob, const StepTable& tab,
+                                              int64_t n_iters, int debug, long long* prof = nullptr) {
   uint32_t stage = 0, phase = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    MmaStep nxt = steps[0];
+  const int n_steps = tab.n;
+  for (int64_t it = 0; it < n_iters; ++it) {
     for (int i = 0; i < n_steps; ++i) {
-      const MmaStep st = nxt;
-      if (i + 1 < n_steps) nxt = steps[i + 1];        // in flight while this lane waits below
+      const uint32_t w_off16 = tab.s[i].w_off16;
+      const uint32_t bytes = (uint32_t)tab.s[i].bytes16 * 8u;     // half of the item
       mbar_wait(&s.bar_empty[stage], phase ^ 1, 10);
-      const uint32_t bytes = (uint32_t)st.bytes16 * 16u;
-      if (debug & 1) { mbar_arrive(&s.bar_full[stage]); }
-      else {
-        mbar_expect_tx(&s.bar_full[stage], bytes);
-        bulk_g2s(s.wst + stage * kWStageBytes, blob + (size_t)st.w_off16 * 16, bytes, &s.bar_full[stage]);
+      if (prof && it == 2 && i >= 40 && i < 72 && blockIdx.x == 0 && (threadIdx.x & 31) == 0) prof[300 + (i - 40)] = clock64();
+      if (elect_one()) {
+        if (debug & 1) { mbar_arrive(&s.bar_full[stage]); }
+        else {
+          mbar_expect_tx(&s.bar_full[stage], bytes);
+          bulk_g2s(s.wst + stage * kWStageBytes, blob + (size_t)w_off16 * 16 + (size_t)s.rank * bytes, bytes,
+                   &s.bar_full[stage]);
+        }
       }
-      stage ^= 1; if (stage == 0) phase ^= 1;
+      __syncwarp();
+      if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
     }
   }
+  (void)prof;
 }
 
-// one lane of warp 1
-__device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, const MmaStep* steps, int n_steps,
-                                         int64_t n_tiles, int debug) {
+// warp 1, rank 1: tell the issuer that this CTA's half of each item has landed (second arrival on
+// the issuer's stage barrier)
+__device__ __forceinline__ void relay_loop(const Smem& s, int n_steps, int64_t n_iters, int debug = 0) {
+  uint32_t stage = 0, phase = 0;
+  if (debug & 8) return;      // timing experiment: the issuer does not wait for this CTA's operands
+  const uint32_t remote0 = mapa_shared(smem_u32(&s.bar_full[0]), 0);
+  for (int64_t it = 0; it < n_iters; ++it)
+    for (int i = 0; i < n_steps; ++i) {
+      mbar_wait(&s.bar_full[stage], phase, 22);
+      if (elect_one()) mbar_arrive_remote(remote0 + stage * 8u);
+      __syncwarp();
+      if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
+    }
+}
+
+// warps 1 and 2 of rank 0 (all lanes run the loop; one elected lane issues the MMAs and the commits).
+// Both issuers walk the whole step list in ring order and act on the items of their own lane.
+__device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, const StepTable& tab, int my_lane,
+                                         int64_t n_iters, int debug, long long* prof = nullptr) {
+  const int n_steps = tab.n;
   constexpr uint64_t tmpl = make_smem_desc_template(16, 1024, kSwizzle128B);
   constexpr uint64_t tmpl_aux = make_smem_desc_template(128, 256, kSwizzleNone);   // 16-column no-swizzle operand
   const uint32_t act_addr = smem_u32(s.act), wst_addr = smem_u32(s.wst), aux_addr = smem_u32(s.aux);
   uint32_t stage = 0, phase = 0, epi_par = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  if (my_lane != 0) prof = nullptr;
+  long long w_epi = 0, w_full = 0, t_all = prof ? clock64() : 0;
+  for (int64_t it = 0; it < n_iters; ++it) {
     int i = 0;
-    MmaStep nxt = steps[0];
     while (i < n_steps) {
-      mbar_wait(s.bar_epi, epi_par, 20); epi_par ^= 1;
+      long long t0 = prof ? clock64() : 0;
+      mbar_wait_cluster(s.bar_epi, epi_par, 20); epi_par ^= 1;
+      if (prof) w_epi += clock64() - t0;
       tc_fence_after();
       bool last;
       do {
-        const MmaStep st = nxt;
+        const uint32_t n = tab.s[i].n, tcol = tab.s[i].tmem_col, a_slab = tab.s[i].a_slab, ksteps = tab.s[i].ksteps;
+        const uint32_t first = tab.s[i].first, lane = tab.s[i].lane;
+        last = tab.s[i].last;
         ++i;
-        if (i < n_steps) nxt = steps[i];
-        last = st.last;
-        mbar_wait(&s.bar_full[stage], phase, 21);
-        tc_fence_after();
-        const uint32_t b0 = wst_addr + stage * kWStageBytes;
-        const uint32_t idesc = make_idesc_f16(128, st.n, 0, 0);
-        if (!(debug & 4)) {
-          if (st.a_slab == kAuxSlab) {
-            umma_f16(tmem_base + st.tmem_col, smem_desc(tmpl_aux, aux_addr), smem_desc(tmpl_aux, b0), idesc,
-                     st.first ? 0u : 1u);
-          } else {
-            const uint32_t a0 = act_addr + (uint32_t)st.a_slab * kSlabBytes;
-            for (uint32_t k = 0; k < st.ksteps; ++k)
-              umma_f16(tmem_base + st.tmem_col, smem_desc(tmpl, a0 + k * 32), smem_desc(tmpl, b0 + k * 32), idesc,
-                       (st.first && k == 0) ? 0u : 1u);
+        if ((int)lane == my_lane) {
+          t0 = prof ? clock64() : 0;
+          mbar_wait_cluster(&s.bar_full[stage], phase, 21);      // both halves of the item have landed
+          if (prof) {
+            const long long t1 = clock64();
+            w_full += t1 - t0;
+            if (it == 2 && i > 40 && i <= 72 && blockIdx.x == 0 && (threadIdx.x & 31) == 0) prof[340 + (i - 41)] = t1;
           }
+          tc_fence_after();
+          const uint32_t b0 = wst_addr + stage * kWStageBytes;
+          const uint32_t idesc = make_idesc_f16(256, n, 0, 0);
+          if (elect_one()) {
+            if (!(debug & 4)) {
+              if (a_slab == kAuxSlab) {
+                umma2_f16(tmem_base + tcol, smem_desc(tmpl_aux, aux_addr), smem_desc(tmpl_aux, b0), idesc, first ? 0u : 1u);
+              } else {
+                const uint32_t a0 = act_addr + a_slab * kSlabBytes;
+                for (uint32_t k = 0; k < ksteps; ++k)
+                  umma2_f16(tmem_base + tcol, smem_desc(tmpl, a0 + k * 32), smem_desc(tmpl, b0 + k * 32), idesc,
+                            (first && k == 0) ? 0u : 1u);
+              }
+            }
+            umma2_commit(&s.bar_empty[stage]);
+          }
+          __syncwarp();
+          if (prof && it == 2 && i > 40 && i <= 72 && blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+            prof[420 + (i - 41)] = clock64();       // commit issued
         }
-        umma_commit(&s.bar_empty[stage]);
-        stage ^= 1; if (stage == 0) phase ^= 1;
+        if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
       } while (!last);
-      umma_commit(s.bar_mma);
+      if (elect_one()) umma2_commit(s.bar_mma);      // this issuer's share of the phase (possibly empty) has retired
+      __syncwarp();
     }
+  }
+  if (prof && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    prof[256] = w_epi; prof[257] = w_full; prof[258] = 0; prof[259] = clock64() - t_all;
+    prof[260] = n_iters; prof[261] = n_steps;
   }
 }
 
@@ -143,43 +204,75 @@ struct EpiSync {
   bool stores_pending = false;
   long long* prof;        // optional phase clock log (block 0 only)
   int prof_i = 0;
+  uint32_t epi_remote;    // rank 1: the issuer CTA's bar_epi
   __device__ EpiSync(const Smem& s_, long long* prof_)
-      : s(s_), issuer(threadIdx.x == kEpiWarp0 * 32), prof((blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? prof_ : nullptr) {}
+      : s(s_), issuer(threadIdx.x == kEpiWarp0 * 32),
+        prof((blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? prof_ : nullptr),
+        epi_remote(mapa_shared(smem_u32(s_.bar_epi), 0)) {}
 
   __device__ __forceinline__ void stamp() {
     if (prof && prof_i < 256) prof[prof_i++] = clock64();
   }
-  __device__ __forceinline__ void drain_stores() {   // earlier bulk stores must have read their slabs
+  // Activation slabs leave through bulk stores issued one slab at a time while the issuer thread
+  // waits for the next MMA phase: the copy engine serves loads and stores in order, and a 128 KB
+  // store in front of the weight ring's loads stalled the tensor pipe for thousands of cycles.
+  struct Pending { uint8_t* dst; const uint8_t* src; int n; };
+  Pending q[2];
+  int nq = 0;
+  __device__ __forceinline__ bool issue_one() {      // issuer thread only
+    if (nq == 0) return false;
+    bulk_s2g(q[0].dst, q[0].src, kSlabBytes);
+    bulk_commit();
+    q[0].dst += kSlabBytes; q[0].src += kSlabBytes;
+    if (--q[0].n == 0) { q[0] = q[1]; --nq; }
+    return true;
+  }
+  __device__ __forceinline__ void drain_stores() {   // all pending stores issued and their slabs read
     if (stores_pending) {
-      if (issuer) bulk_wait_read<0>();
+      if (issuer) { while (issue_one()) {} bulk_wait_read<0>(); }
       epi_bar_sync();
       stores_pending = false;
     }
   }
-  __device__ __forceinline__ void begin() {          // wait for the MMA phase that feeds this epilogue
-    mbar_wait(s.bar_mma, mma_par, 30); mma_par ^= 1;
+  // Wait for the MMA phase that feeds this epilogue.  One thread polls the mbarrier and the rest
+  // block on the named barrier: 512 pollers on one mbarrier starve the producer's and the issuer's
+  // own barrier traffic.
+  __device__ __forceinline__ void begin() {
+    if (issuer) {
+      bool done = false;
+      while (!done && issue_one()) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < 600) {
+          if (mbar_try_wait(s.bar_mma, mma_par)) { done = true; break; }
+        }
+      }
+      if (!done) mbar_wait(s.bar_mma, mma_par, 30);
+      if (stores_pending) { while (issue_one()) {} bulk_wait_read<0>(); }
+    }
+    mma_par ^= 1;
+    stores_pending = false;
+    epi_bar_sync();
     tc_fence_after();
     stamp();
-    drain_stores();
   }
   // publish shared-memory writes to the async proxy, order TMEM reads, release the MMA warp
   __device__ __forceinline__ void end(bool signal) {
     fence_proxy_async_smem();
     tc_fence_before();
     epi_bar_sync();
-    if (issuer && signal) mbar_arrive(s.bar_epi);
+    if (issuer && signal) {
+      if (s.rank == 0) mbar_arrive(s.bar_epi);
+      else mbar_arrive_remote(epi_remote);
+    }
     stamp();
   }
-  // after end(): stream `nslabs` activation slabs (starting at slab0) to global memory
+  // after end(): queue `nslabs` activation slabs (starting at slab0) for streaming to global memory
   __device__ __forceinline__ void store_slabs(uint8_t* dst, int slab0, int nslabs) {
     if (!dst) return;
-    if (issuer) {
-      bulk_s2g(dst, s.act + slab0 * kSlabBytes, (uint32_t)nslabs * kSlabBytes);
-      bulk_commit();
-    }
+    if (issuer) { q[nq].dst = dst; q[nq].src = s.act + slab0 * kSlabBytes; q[nq].n = nslabs; ++nq; }
     stores_pending = true;
   }
-  __device__ __forceinline__ void finish() { if (issuer) bulk_wait_all<0>(); }
+  __device__ __forceinline__ void finish() { if (issuer) { while (issue_one()) {} bulk_wait_all<0>(); } }
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -197,6 +290,23 @@ __device__ __forceinline__ uint32_t slab_off(int col, int row) {
 // never by the tensor core): 16-byte chunk c (8 columns) of all 128 rows is contiguous, so a warp's
 // store covers 512 consecutive bytes.  Same size as the slab layout.
 __device__ __forceinline__ uint32_t xsave_off(int col, int row) { return ((uint32_t)(col >> 3) * 128u + row) * 16u; }
+
+// sign-bit save of a sine layer: one uint32 per (32-column batch, point)
+__device__ __forceinline__ uint32_t sbit_off(int col, int row) { return ((uint32_t)(col >> 5) * 128u + row) * 4u; }
+
+// Copy `nslabs` activation slabs (128B-swizzled K-major, as the MMAs read them) to the row-interleaved
+// save layout in global memory.  Called by all epilogue threads right after end(): it runs while the
+// next MMA phase reads the same slabs, so the stores of a layer overlap the tensor-core work of the
+// next one instead of lengthening the epilogue (an SM sustains ~30 B/cycle of global stores).
+__device__ __forceinline__ void copy_slabs_out(const uint8_t* act, int slab0, int nslabs, uint8_t* dst) {
+  if (!dst) return;
+  const int etid = (int)threadIdx.x - kEpiWarp0 * 32;
+  for (int idx = etid; idx < nslabs * 1024; idx += kEpiThreads) {
+    const int r = idx & 127, c = idx >> 7;          // row fastest: a warp stores 512 contiguous bytes
+    const uint4 v = *reinterpret_cast<const uint4*>(act + (size_t)(slab0 + (c >> 3)) * kSlabBytes + slab_chunk_offset(r, c & 7));
+    stg16(dst + ((size_t)c * 128 + r) * 16, v);
+  }
+}
 
 // Sum per-row partial results over the 4 column groups through shared scratch ([i][group][row] floats).
 // After the call the group-0 thread of each row holds the totals.  The caller provides the barrier

@@ -2,8 +2,9 @@
 //
 //   dW[m][n] = sum_points G[point][m] * Y[point][n]
 // G (pre-activation gradient tiles, from mlp_bwd.cu) and Y (the forward's saved layer inputs) are
-// both stored point-major in 128x64 swizzled slabs, which is exactly the MN-major operand form of
-// tcgen05.mma: no transposition, the slabs are bulk-copied to shared memory and multiplied as is.
+// both stored per 128-point tile as 16-byte chunks (8 features) x 128 points, which is exactly the
+// no-swizzle MN-major operand form of tcgen05.mma: no transposition, the tiles are bulk-copied to
+// shared memory and multiplied as is.
 // Bias gradients fall out of the same GEMMs through the constant-one column of the "aux" slab,
 // the sun-direction / transient-embedding input columns through its other columns.
 //
@@ -117,7 +118,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint64_t tmpl = make_smem_desc_template(kSlabBytes, 1024, kSwizzle128B);   // MN-major: LBO = slab stride
+      // saved tiles are row-interleaved: 16-byte chunk (8 features) of all 128 points contiguous, i.e. the
+      // no-swizzle MN-major operand form: core matrices 128 B apart along K (points), 2048 B along M/N
+      constexpr uint64_t tmpl = make_smem_desc_template(128, 2048, kSwizzleNone);
       uint32_t stage = 0, phase = 0, drained_par = 0;
       bool first_gemm = true;
       for (int g = 0; g < p.n_gemms; ++g) {
@@ -135,11 +138,11 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 #pragma unroll
           for (uint32_t s = 0; s < 8; ++s) {                 // 128 points = 8 K-steps of 16 rows
             const uint32_t acc = (k > k0 || s > 0) ? 1u : 0u;
-            umma_f16(tmem_base, smem_desc(tmpl, a0 + s * 2048), smem_desc(tmpl, b0 + s * 2048),
+            umma_f16(tmem_base, smem_desc(tmpl, a0 + s * 256), smem_desc(tmpl, b0 + s * 256),
                      make_idesc_f16(128, n_hi, 1, 1), acc);
             if (n_lo)
-              umma_f16(tmem_base + 256, smem_desc(tmpl, a0 + s * 2048),
-                       smem_desc(tmpl, b0 + 4 * kSlabBytes + s * 2048), make_idesc_f16(128, n_lo, 1, 1), acc);
+              umma_f16(tmem_base + 256, smem_desc(tmpl, a0 + s * 256),
+                       smem_desc(tmpl, b0 + 4 * kSlabBytes + s * 256), make_idesc_f16(128, n_lo, 1, 1), acc);
           }
           umma_commit(&bar_empty[stage]);
           stage ^= 1; if (stage == 0) phase ^= 1;

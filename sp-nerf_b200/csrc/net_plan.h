@@ -23,8 +23,8 @@ constexpr int kOffAux = kNumSlabs * kSlabBytes;      // 128 rows x 16 halves, no
 constexpr int kOffRgb2 = kOffAux + 4096;             // float4[256]: rgb_from_xyzdir.2 rows (3) per hidden unit
 constexpr int kOffSem2 = kOffRgb2 + 4096;            // float4[256][2]: logit_from_label.2 rows (<= 8)
 constexpr int kOffWst = kOffSem2 + 8192;
-constexpr int kWStageBytes = 32768;  // one weight item: up to 256 rows x 64 k
-constexpr int kNumWStages = 2;
+constexpr int kWStageBytes = 16384;  // this CTA's half of one weight item: up to 128 of 256 rows x 64 k
+constexpr int kNumWStages = 4;
 constexpr int kSmemBars = kOffWst + kNumWStages * kWStageBytes;
 constexpr int kOffSun6 = kSmemBars + 256;            // float[256] sun_v_net.6 row
 constexpr int kOffBeta2 = kOffSun6 + 1024;           // float[256] beta_from_xyz.2 row
@@ -46,10 +46,21 @@ struct __align__(16) MmaStep {
   uint8_t a_slab;     // shared-memory slab holding the A operand, or kAuxSlab
   uint8_t ksteps;     // K=16 instructions to issue from this slab (1..4)
   uint8_t first;      // 1: overwrite the accumulator (first item of a chunk)
-  uint8_t last;       // 1: last item of a phase -> signal the epilogue
+  uint8_t last;       // 1: last item of a phase (in ring order) -> both issuers signal the epilogue
   uint16_t bytes16;   // item size in 16-byte units
-  uint16_t _pad;
+  uint8_t lane;       // which of the two MMA issuer warps owns this item (its accumulation chunk)
+  uint8_t _pad;
 };
+
+// The step list travels to the kernels as a launch parameter (constant bank): the producer and the
+// MMA issuer read one entry per item, and a dependent global load per item would cap the issue rate.
+struct StepTable {
+  int n;
+  int _pad[3];
+  MmaStep s[kMaxSteps];
+};
+// host: the forward (backward = 0) or backward-data (1) step list of a configuration (mlp_pack.cu)
+const StepTable* step_table(const SpnerfNetConfig& cfg, int backward);
 
 // The aux operand: per point [1, sun_dir(3), t_emb(<=8), 1, 0, 0, 0].  Multiplying it by a B tile
 // that holds [fp16(b), W[:, sun columns], W[:, t columns], b - fp16(b)] folds the bias and the
@@ -74,15 +85,18 @@ struct SmallOffsets {
   int total;
 };
 
-// Per-tile activation save area, in slabs (training forward -> backward).
+// Per-tile activation save area, in 16 KB units (training forward -> backward).  Activations are
+// stored row-interleaved (roles::xsave_off): 16-byte chunk (8 columns) x 128 points, 64 columns per
+// unit.  The derivative of a sine layer is rebuilt in the backward as +-sqrt(1 - y^2); only its sign
+// is saved, one bit per element ("s" regions: uint32 [column / 32][point], 8 KB for 512 columns).
 struct SaveMap {
-  int inp;         // encoded input (hi)                          1 slab
-  int aux;         // [1, sun_dir(3), t_emb(t_dim), 0...]          1 slab
-  int y[8];        // post-activation of trunk layer i            8 slabs each
-  int x[8];        // sine argument of trunk layer i (x[0]: cos of it, see mlp_fwd.cu)
-  int f;           // feats_from_xyz output                       8 slabs
-  int sem_x, sem_y, rgb_x, rgb_y, beta_x, beta_y;   // 4 slabs each (-1 if absent)
-  int sun_x[3], sun_y[3];                           // 4 slabs each
+  int inp;         // encoded input (hi)                          1 unit
+  int aux;         // [1, sun_dir(3), t_emb(t_dim), 0...]          1 unit (16 columns used)
+  int y[8];        // post-activation of trunk layer i            8 units each
+  int x[8];        // sign bits of cos(sine argument), layer i    1 unit each
+  int f;           // feats_from_xyz output                       8 units
+  int sem_x, sem_y, rgb_x, rgb_y, beta_x, beta_y;   // *_y: 4 units, *_x (sign bits): 1 unit (-1 if absent)
+  int sun_x[3], sun_y[3];
   int total;
 };
 
@@ -119,13 +133,14 @@ inline SaveMap make_save_map(const SpnerfNetConfig& c) {
   int s = 0;
   m.inp = s++;
   m.aux = s++;
-  for (int i = 0; i < 8; ++i) { m.y[i] = s; s += 8; m.x[i] = s; s += 8; }
+  for (int i = 0; i < 8; ++i) { m.y[i] = s; s += 8; m.x[i] = s; s += 1; }
   m.f = s; s += 8;
   auto four = [&](bool on) { int r = on ? s : -1; if (on) s += 4; return r; };
-  m.sem_x = four(c.sem); m.sem_y = four(c.sem);
-  m.rgb_x = four(true); m.rgb_y = four(true);
-  m.beta_x = four(c.beta); m.beta_y = four(c.beta);
-  for (int i = 0; i < 3; ++i) { m.sun_x[i] = four(true); m.sun_y[i] = four(true); }
+  auto one = [&](bool on) { int r = on ? s : -1; if (on) s += 1; return r; };
+  m.sem_x = one(c.sem); m.sem_y = four(c.sem);
+  m.rgb_x = one(true); m.rgb_y = four(true);
+  m.beta_x = one(c.beta); m.beta_y = four(c.beta);
+  for (int i = 0; i < 3; ++i) { m.sun_x[i] = one(true); m.sun_y[i] = four(true); }
   m.total = s;
   return m;
 }

@@ -66,15 +66,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: `code` identifies the wait site in g_watchdog_code if it expires.
+// Bounded wait: `code` identifies the wait site in g_watchdog_code if it expires.  The clock is only
+// consulted every 4096 failed polls (a timer read on every wait would sit on the critical path of
+// every producer / issuer / epilogue hand-off).
+#ifndef SPNERF_WATCHDOG_CYCLES
+#define SPNERF_WATCHDOG_CYCLES 8000000000LL   // ~4 s
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code = 1) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > SPNERF_WATCHDOG_NS) {
-      atomicCAS(&g_watchdog_code, 0u, code);
-      __trap();
+    if ((++spins & 0xfff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPNERF_WATCHDOG_CYCLES) {
+        atomicCAS(&g_watchdog_code, 0u, code);
+        __trap();
+      }
     }
   }
 }
@@ -97,9 +105,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier that lives in another CTA of the cluster
+// arrive on an mbarrier that lives in another CTA of the cluster.  Default (CTA-scope release)
+// semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU, which waits for every
+// outstanding memory operation of the SM (the in-flight weight copies, the activation saves) on
+// each hand-off.  What the consumer reads after this arrive was written by the async proxy (bulk
+// copies, completed on the local mbarrier) or published with fence.proxy.async + bar.sync before.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -112,17 +124,45 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (the result can be consumed later: the issuer overlaps it with MMA issue)
+__device__ __forceinline__ bool mbar_test_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait with cluster-scope acquire (the arrivals come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t code = 2) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > SPNERF_WATCHDOG_NS) {
-      atomicCAS(&g_watchdog_code, 0u, code);
-      __trap();
+    if ((++spins & 0xfff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPNERF_WATCHDOG_CYCLES) {
+        atomicCAS(&g_watchdog_code, 0u, code);
+        __trap();
+      }
     }
   }
+}
+
+// One lane of a fully converged warp.  The single-thread instructions (tcgen05.mma / commit, bulk
+// copies) are issued under this predicate while the surrounding loop stays warp-uniform, so their
+// operands live in uniform registers instead of being broadcast lane by lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA / bulk copy reads)

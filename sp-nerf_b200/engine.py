@@ -179,8 +179,10 @@ class NetEngine:
         s = self.sizes
         self.device = device
         u8 = dict(dtype=torch.uint8, device=device)
-        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16), **u8)
-        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16), **u8)
+        import os
+        self.blob_copies = max(1, int(os.environ.get("SPNERF_BLOB_COPIES", "1")))
+        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16) * self.blob_copies, **u8)
+        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16) * self.blob_copies, **u8)
         self.small = torch.empty(int(s.small_floats), dtype=torch.float32, device=device)
         self.fwd_steps = torch.empty(int(s.steps_bytes), **u8)
         self.bwd_steps = torch.empty(int(s.steps_bytes), **u8)
@@ -216,6 +218,10 @@ class NetEngine:
             self._prepared_key = ptrs
         _cabi.check(_cabi.lib().spnerf_net_pack(ctypes.byref(self.cfg), _p(self.pack_ws), _p(self.fwd_blob),
                                                 _p(self.bwd_blob), _p(self.small), _stream()), "spnerf_net_pack")
+        if self.blob_copies > 1:
+            for blob, nbytes in ((self.fwd_blob, int(self.sizes.fwd_blob_bytes)), (self.bwd_blob, int(self.sizes.bwd_blob_bytes))):
+                v = blob.view(self.blob_copies, nbytes)
+                v[1:] = v[0]
         self._packed_key = key
         self.n_packs += 1
 

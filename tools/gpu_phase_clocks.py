@@ -1,39 +1,48 @@
-"""Per-phase clock log of the fused forward / backward-data kernels (block 0, first tiles):
-prints cycles between consecutive epilogue stamps (begin = MMA phase retired, end = epilogue done)."""
+"""Per-phase clock log of the fused forward kernel (block 0): cycles between consecutive epilogue
+stamps, plus the MMA issuer's accumulated wait times.  usage: gpu_phase_clocks.py [debug_flags...]"""
 import sys, os, types, ctypes, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import bench
 import spnerf_b200
-from spnerf_b200 import synthetic, train_step, _cabi
+from spnerf_b200 import synthetic, _cabi
+from oracle import spnerf_oracle as O
 
 dev = torch.device("cuda:0")
 args = bench.make_args()
 model = bench.build_model(args, dev)
-rays = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-batch = synthetic.make_batch(rays, seed=269, device=dev)
+B, N = int(os.environ.get('PC_RAYS', '8192')), 64
+batch = synthetic.make_batch(B, seed=269, device=dev)
+z = O.stratified_z(batch["rays"], N, torch.rand(B, N, device=dev)).contiguous()
+eng = model.engine
 L = _cabi.lib()
-for fn in (L.spnerf_debug_phase_clocks_fwd, L.spnerf_debug_phase_clocks_bwd):
-    fn.restype = None
-    fn.argtypes = [ctypes.c_void_p]
-for _ in range(2):
-    train_step.fused_step(model, args, batch, repack=True)
-torch.cuda.synchronize()
-bf = torch.zeros(256, dtype=torch.int64, device=dev)
-bb = torch.zeros(256, dtype=torch.int64, device=dev)
-L.spnerf_debug_phase_clocks_fwd(bf.data_ptr())
-L.spnerf_debug_phase_clocks_bwd(bb.data_ptr())
-train_step.fused_step(model, args, batch, repack=True)
-torch.cuda.synchronize()
-L.spnerf_debug_phase_clocks_fwd(None)
-L.spnerf_debug_phase_clocks_bwd(None)
+L.spnerf_debug_phase_clocks_fwd.restype = None
+L.spnerf_debug_phase_clocks_fwd.argtypes = [ctypes.c_void_p]
 out = {}
-for name, b in (("fwd", bf), ("bwd", bb)):
-    t = b.cpu().tolist()
-    t = [x for x in t if x]
-    d = [t[i + 1] - t[i] for i in range(len(t) - 1)]
-    out[name] = d
-    print(name, "stamps", len(t), "total", t[-1] - t[0] if t else 0)
-    print(" deltas:", d[:120])
+for spec in (sys.argv[1:] or ["0s", "0", "7", "5", "1"]):
+    save = spec.endswith("s")
+    flags = int(spec.rstrip("s"))
+    for _ in range(2):
+        eng.forward(batch["rays"], N, z=z, labels=batch["sems"], save=save, debug_flags=flags)
+    torch.cuda.synchronize()
+    buf = torch.zeros(512, dtype=torch.int64, device=dev)
+    L.spnerf_debug_phase_clocks_fwd(buf.data_ptr())
+    eng.forward(batch["rays"], N, z=z, labels=batch["sems"], save=save, debug_flags=flags)
+    torch.cuda.synchronize()
+    L.spnerf_debug_phase_clocks_fwd(None)
+    t = buf.cpu().tolist()
+    st = [x for x in t[:256] if x]
+    d = [st[i + 1] - st[i] for i in range(len(st) - 1)]
+    per_tile = 31
+    print(f"== flags {flags} save {save}: first tile deltas", d[:per_tile])
+    print("   second tile", d[per_tile:2 * per_tile])
+    print("   issuer: wait_epi %d wait_full %d wait_pfull %d total %d iters %d steps %d | producer wait_empty %d" % (
+        t[256], t[257], t[258], t[259], t[260], t[261], t[264]))
+    base = min(x for x in t[300:452] if x)
+    rel = lambda a: [x - base if x else -1 for x in a]
+    print("   steps 40..71: producer empty-seen ", rel(t[300:332]))
+    print("                 issuer full-seen    ", rel(t[340:372]))
+    print("                 issuer commit       ", rel(t[420:452]))
+    out[spec] = {"deltas": d, "issuer": t[256:262], "producer_wait_empty": t[264]}
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "phase_clocks.json"), "w"))

@@ -26,6 +26,16 @@ CASES = {
     "kns_n256_k64": ("kns", 256, 64, "std"),
     "kns_n16_k16": ("kns", 16, 16, "std"),
     "a_sw128_b_kns_n256_k64": ("a_sw_b_kns", 256, 64, "std"),
+    # no-swizzle MN-major ("chunk-major" save layout): [mn/8][k][8 mn halves]; variants swap LBO/SBO
+    "mnns_n256_k128_a": ("mnns", 256, 128, "a"),
+    "mnns_n256_k128_b": ("mnns", 256, 128, "b"),
+    "mnns_n16_k128_a": ("mnns", 16, 128, "a"),
+    "mnns_n16_k128_b": ("mnns", 16, 128, "b"),
+    # CTA pair (cta_group::2, M = 256): B rows split between the CTAs
+    "pair_k_n256_k128": ("pair_k", 256, 128, "std"),
+    "pair_k_n16_k64": ("pair_k", 16, 64, "std"),
+    "pair_kns_n256_k16": ("pair_kns", 256, 16, "std"),
+    "pair_kns_n16_k16": ("pair_kns", 16, 16, "std"),
 }
 
 
@@ -38,7 +48,8 @@ def run_case(name):
 
     mode, n, k, variant = CASES[name]
     rng = np.random.default_rng(7)
-    a = rng.integers(-4, 5, size=(128, k)).astype(np.float16)
+    pair = mode.startswith("pair")
+    a = rng.integers(-4, 5, size=(256 if pair else 128, k)).astype(np.float16)
     b = rng.integers(-4, 5, size=(n, k)).astype(np.float16)
     want = a.astype(np.float32) @ b.astype(np.float32).T
     args = _cabi.UmmaSelftest()
@@ -67,7 +78,36 @@ def run_case(name):
         offs = [s * 256 for s in range(ksteps)]
         return img, offs, slab.smem_desc_template(128, (kk // 8) * 128, swizzle=0)
 
-    if mode == "kns":
+    def mnns(x):
+        # x: (rows = M or N, K).  element (mn, k) at (mn/8)*(K*16) + k*16 + (mn%8)*2
+        rows, kk = x.shape
+        img = np.ascontiguousarray(x.reshape(rows // 8, 8, kk).transpose(0, 2, 1)).view(np.uint8).reshape(-1)
+        offs = [s * 256 for s in range(ksteps)]
+        mn_stride, k_stride = kk * 16, 128
+        if variant == "a":
+            return img, offs, slab.smem_desc_template(mn_stride, k_stride, swizzle=0)
+        return img, offs, slab.smem_desc_template(k_stride, mn_stride, swizzle=0)
+
+    if mode == "mnns":
+        a_img, a_off, a_t = mnns(a)
+        b_img, b_off, b_t = mnns(b)
+        idesc = slab.idesc_f16(128, n, 1, 1)
+    elif pair:
+        f = kmajor if mode == "pair_k" else (lambda x, rows=None: kns(x))
+        if mode == "pair_k":
+            a0_img, a_off, a_t = kmajor(a[:128], 128)
+            a1_img, _, _ = kmajor(a[128:], 128)
+            b0_img, b_off, b_t = kmajor(b[:n // 2], n // 2)
+            b1_img, _, _ = kmajor(b[n // 2:], n // 2)
+        else:
+            a0_img, a_off, a_t = kns(a[:128])
+            a1_img, _, _ = kns(a[128:])
+            b0_img, b_off, b_t = kns(b[:n // 2])
+            b1_img, _, _ = kns(b[n // 2:])
+        a_img = np.concatenate([a0_img, a1_img])
+        b_img = np.concatenate([b0_img, b1_img])
+        idesc = slab.idesc_f16(256, n, 0, 0)
+    elif mode == "kns":
         a_img, a_off, a_t = kns(a)
         b_img, b_off, b_t = kns(b)
         idesc = slab.idesc_f16(128, n, 0, 0)
@@ -91,15 +131,20 @@ def run_case(name):
     dev = torch.device("cuda:0")
     ta = torch.from_numpy(a_img.copy()).to(dev)
     tb = torch.from_numpy(b_img.copy()).to(dev)
-    td = torch.full((128, n), float("nan"), device=dev)
+    td = torch.full((256 if pair else 128, n), float("nan"), device=dev)
     args.a_img, args.b_img, args.d_out = ta.data_ptr(), tb.data_ptr(), td.data_ptr()
-    args.a_bytes, args.b_bytes = ta.numel(), tb.numel()
+    args.a_bytes, args.b_bytes = (ta.numel() // 2, tb.numel() // 2) if pair else (ta.numel(), tb.numel())
     args.n, args.ksteps, args.idesc = n, ksteps, idesc
     args.a_desc_template, args.b_desc_template = a_t, b_t
     for i in range(ksteps):
         args.a_off[i] = a_off[i]
         args.b_off[i] = b_off[i]
-    rc = _cabi.lib().spnerf_selftest_umma(ctypes.byref(args), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    fn = _cabi.lib().spnerf_selftest_umma
+    if pair:
+        fn = _cabi.lib().spnerf_selftest_umma2
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.POINTER(_cabi.UmmaSelftest), ctypes.c_void_p]
+    rc = fn(ctypes.byref(args), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     got = td.cpu().numpy()
     err = float(np.nanmax(np.abs(got - want))) if not np.isnan(got).all() else float("nan")
@@ -110,10 +155,12 @@ def run_case(name):
 
 
 def main():
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] in CASES:
         sys.exit(run_case(sys.argv[1]))
     results = {}
     for name in CASES:
+        if len(sys.argv) > 1 and not name.startswith(sys.argv[1]):
+            continue
         try:
             p = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=120)
             line = [l for l in p.stdout.splitlines() if l.startswith("{")]
