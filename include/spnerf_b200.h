@@ -62,6 +62,13 @@ typedef struct SpnerfUmmaSelftest {
   uint32_t b_off[SPNERF_SELFTEST_MAX_KSTEPS];
 } SpnerfUmmaSelftest;
 int spnerf_selftest_umma(const SpnerfUmmaSelftest* args, void* stream);
+/* CTA-pair form (cluster of 2, cta_group::2, M = 256): a_img holds the two CTAs' A images (a_bytes
+ * each), b_img the two halves of the B rows (b_bytes each), idesc says M = 256, d_out is [256][n]. */
+int spnerf_selftest_umma2(const SpnerfUmmaSelftest* args, void* stream);
+/* Profiling aid: when non-NULL, the next spnerf_mlp_fwd / spnerf_mlp_bwd_data launches log clock64()
+ * stamps of CTA 0's epilogue phases into dev_buf512 (512 int64, device memory). NULL disables. */
+void spnerf_debug_phase_clocks_fwd(long long* dev_buf512);
+void spnerf_debug_phase_clocks_bwd(long long* dev_buf512);
 
 /* ---------------------------------------------------------------------------------------------
  * Point network (replaces models/spnerf.py:162-369 SPNeRF.__init__/forward as executed through
@@ -146,7 +153,7 @@ typedef struct SpnerfMlpFwd {
   int32_t n_samples;
   int32_t n_steps;
   const void* blob;       /* fwd_blob */
-  const void* steps;      /* fwd_steps */
+  const void* steps;      /* fwd_steps (kept for layout; the step list now travels as a launch parameter) */
   const float* small;
   float* out;             /* (n_rays*n_samples, n_out) fp32, reference column order            */
   void* saves;            /* activation save area or NULL (inference)                          */
