@@ -1,19 +1,28 @@
 // Weight / bias gradients of the point network as tensor-core GEMMs over the point dimension.
 //
-//   dW[m][n] = sum_points G[point][m] * Y[point][n]
+//   dW[m][i] = sum_points G[point][m] * Y[point][i]
 // G (pre-activation gradient tiles, from mlp_bwd.cu) and Y (the forward's saved layer inputs) are
 // both stored per 128-point tile as 16-byte chunks (8 features) x 128 points, which is exactly the
 // no-swizzle MN-major operand form of tcgen05.mma: no transposition, the tiles are bulk-copied to
-// shared memory and multiplied as is.
-// Bias gradients fall out of the same GEMMs through the constant-one column of the "aux" slab,
-// the sun-direction / transient-embedding input columns through its other columns.
+// shared memory and multiplied as they are.  Bias gradients and the gradients of the per-ray input
+// columns (sun direction, transient embedding, encoded input of the first / skip layer) fall out of
+// the same GEMMs through the saved "aux" tile [1, sun(3), t(8)] and the saved encoded input.
 //
 // Replaces the wgrad half of autograd through models/spnerf.py:305-369.
 //
-// Schedule: GEMMs are processed one after another by the whole grid.  Within a GEMM, CTA c takes
-// output tile (c mod tiles) and point slice (c div tiles), so the CTAs that share a point slice
-// run side by side and hit each other's operands in L2.  Partial tiles go to a workspace; a
-// reduce kernel sums the slices, un-scales and scatters into the parameter-shaped gradients.
+// Shape of the computation (transposed, so that the wide side is the accumulator's columns):
+//   D^T[i][m] = sum_p A'[p][i] * B'[p][m]        A' = input side (Y / aux / input), B' = G
+// A *job* is one CTA pair (cluster of 2, cta_group::2): M' = 256 rows of A' (128 per CTA) times up to
+// 512 columns of B' (two MMAs of N' <= 256; each CTA holds half of the columns of each), i.e. the
+// whole 512-column TMEM of both CTAs.  Per 128-point K tile a CTA loads 32 KB of A' and 64 KB of B'
+// (2-stage ring) for 2048 cycles of MMA.  Jobs that share B' (the 2-3 pairs of one layer) and a
+// point slice are adjacent in the item list, so they run side by side and the second and third
+// reader of a G tile hit L2.  Every job is cut into point slices of about equal cost; partial
+// tiles go to a workspace and a reduce kernel sums the slices, un-scales and scatters into the
+// parameter-shaped gradients.
+#include <algorithm>
+#include <cstdlib>
+#include <cmath>
 #include <vector>
 #include "sm100.cuh"
 #include "net_plan.h"
@@ -23,360 +32,606 @@ using namespace net;
 
 namespace {
 
-constexpr int kMaxBSlabs = 5;                  // B slabs per output tile (N <= 320)
-constexpr int kStageSlabs = 2 + kMaxBSlabs;    // A: 2 slabs (M = 128)
-constexpr int kStageBytes = kStageSlabs * kSlabBytes;
+constexpr int kChunkBytes = 2048;              // 8 features x 128 points, fp16
+constexpr int kABytes = 16 * kChunkBytes;      // A' part of a stage: 128 rows
+constexpr int kBBytes = 32 * kChunkBytes;      // B' part: 2 x 128 columns
+constexpr int kStageBytes = kABytes + kBBytes; // 96 KB
 constexpr int kStages = 2;
 constexpr int kSmemW = kStages * kStageBytes + 256;
-constexpr int kWThreads = 192;                 // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
-constexpr int kMaxTiles = 160;
-constexpr int kMaxSegs = 400;
+constexpr int kWThreads = 256;                 // warp 0 producer, warp 1 issuer / relay, warps 4-7 epilogue
+constexpr int kTargetItemsPerPair = 8;
 
-struct SlabRef { int16_t from_grads; int16_t slab; };   // slab index inside the per-tile (grad) save area
+// `nchunks` consecutive chunks of one save region -> chunk slot `dst_chunk` of the A' or B' part
+struct Run { int16_t from_grads, unit, chunk0, nchunks, dst_chunk, _pad; };
 
-struct OutTile {                // one 128 x (64*nb) accumulator tile of one GEMM
-  SlabRef a;                    // first of 2 consecutive A slabs
-  SlabRef b[kMaxBSlabs];
-  int nb;
-  int gemm;                     // GEMM index (tiles of a GEMM are contiguous)
-  int ws_off;                   // float offset of this tile inside one slice's workspace block
+struct Job {
+  Run a[2][3]; int na[2];       // per CTA rank: its 128 rows of A'
+  Run b[2][2];                  // per CTA rank: its half of the columns of MMA j (dst_chunk relative to the B' part)
+  int nb;                       // number of MMAs (1 or 2)
+  int n[2];                     // N' of MMA j (multiple of 16, <= 256); accumulator columns 256*j ..
+  int ncols;                    // n[0] + n[1]: columns of the packed partial tile
+  int item0, nitems;            // point slices of this job (job-major copy of the item table, for the reduce)
+  int colsum;                   // 1: also sum the columns of B' over the points (bias gradients), row 128 of the tile
 };
-struct GemmInfo { int tile0, ntiles, nslices, ws_slice_floats; int64_t ws_base; };
+constexpr int kWsRows = 129;    // 128 accumulator rows + the column-sum row
+// One unit of work of a CTA pair: point slice `slice` of `job` (job < 0: padding, nothing to do).
+// [peer0, peer0 + npeers) are the items that read the same B' tiles over the same points: they run
+// on adjacent pairs at the same time and pace each other (see the gate in the producer).
+struct Item { int job, slice, nslices, peer0, npeers, _pad; int64_t ws_off; };      // partial tile: [2][kWsRows][ncols] floats
+constexpr int kGateWindow = 3;     // a pair may run at most this many point tiles ahead of its slowest peer
 
-struct Segment {                // scatter rule for 64 accumulator columns of one tile
-  int tile;                     // OutTile index
-  int col0;                     // first accumulator column (multiple of 64)
-  int src_col, ncols;           // columns [src_col, src_col+ncols) inside the slab are wanted
-  float* dst;                   // dst[m*ld_m + j*ld_j]  for accumulator row m (tile-local + m0) and wanted column j
-  int m0, m_valid, ld_m, ld_j;
+struct Segment {                // scatter rule: rows [row0, row0+nrows) of CTA `rank` x packed columns [col0, col0+ncols)
+  int job, rank, row0, nrows, col0, ncols;
+  float* dst;                   // dst[r * ld_row + c * ld_col]
+  int ld_row, ld_col;
 };
 
 struct WgradParams {
   const uint8_t* saves; const uint8_t* gsaves;
-  int save_stride, grad_stride;          // bytes per point tile
+  int64_t save_stride, grad_stride;      // bytes per point tile
   int64_t n_ptiles;
-  const OutTile* tiles; const GemmInfo* gemms; int n_gemms;
+  const Job* jobs; const Item* items; int n_items;
   float* ws;
+  int* progress;                         // [n_items] point tiles loaded so far (zeroed before the launch)
+  long long* prof;                       // optional counters of pair 0 (debug)
 };
 
-__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+__device__ __forceinline__ void item_range(const Item& it, int64_t n_ptiles, int64_t& k0, int64_t& k1) {
+  k0 = n_ptiles * it.slice / it.nslices;
+  k1 = n_ptiles * (it.slice + 1) / it.nslices;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* bar_full = bars;        // [2]
-  uint64_t* bar_empty = bars + 2;   // [2]
-  uint64_t* bar_acc = bars + 4;     // accumulator complete -> epilogue
-  uint64_t* bar_drained = bars + 5; // accumulator read out  -> MMA
+  uint64_t* bar_full = bars;        // [2]  rank 0: both CTAs' operands landed (own copy + peer relay)
+  uint64_t* bar_empty = bars + 2;   // [2]  stage consumed (multicast commit)
+  uint64_t* bar_acc = bars + 4;     // accumulator complete -> epilogue (multicast commit)
+  uint64_t* bar_drained = bars + 5; // rank 0: both accumulators read out -> issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { atomicCAS(&g_watchdog_code, 0u, 901u); __trap(); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    mbar_init(bar_acc, 1); mbar_init(bar_drained, 1);
+    // a stage is free when its MMAs have retired (commit) and the column-sum warps have read it
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 2); }
+    mbar_init(bar_acc, 1); mbar_init(bar_drained, 2);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work of this CTA inside GEMM g: tile index, point-tile range
-  auto my_work = [&](int g, int& tile, int64_t& k0, int64_t& k1, int& slice) {
-    const GemmInfo gi = p.gemms[g];
-    const int c = (int)blockIdx.x;
-    if (c >= gi.ntiles * gi.nslices) return false;
-    tile = gi.tile0 + c % gi.ntiles;
-    slice = c / gi.ntiles;
-    k0 = p.n_ptiles * slice / gi.nslices;
-    k1 = p.n_ptiles * (slice + 1) / gi.nslices;
-    return true;
-  };
-
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int g = 0; g < p.n_gemms; ++g) {
-        int tile, slice; int64_t k0, k1;
-        if (!my_work(g, tile, k0, k1, slice)) continue;
-        const OutTile t = p.tiles[tile];
-        for (int64_t k = k0; k < k1; ++k) {
-          mbar_wait(&bar_empty[stage], phase ^ 1, 40);
+    // ---- producer: this CTA's rows of A' and its half of B', one stage per 128-point tile ----
+    uint32_t stage = 0, phase = 0;
+    for (int it = pair; it < p.n_items; it += npairs) {
+      const Item item = p.items[it];
+      if (item.job < 0) continue;
+      const Job& job = p.jobs[item.job];
+      int64_t k0, k1;
+      item_range(item, p.n_ptiles, k0, k1);
+      uint32_t bytes = 0;
+      for (int r = 0; r < job.na[rank]; ++r) bytes += (uint32_t)job.a[rank][r].nchunks * kChunkBytes;
+      for (int j = 0; j < job.nb; ++j) bytes += (uint32_t)job.b[rank][j].nchunks * kChunkBytes;
+      for (int64_t k = k0; k < k1; ++k) {
+        // Gate: the peers stream the same G tiles; keeping them within a few tiles of each other makes
+        // the second and third reader hit L2 instead of HBM (the slowest peer never waits).
+        if (rank == 0 && item.npeers > 1 && lane == 0) {
+          volatile int* prog = p.progress;
+          prog[it] = (int)(k - k0);
+          for (int q = item.peer0; q < item.peer0 + item.npeers; ++q) {
+            if (q == it) continue;
+            long long t0 = 0; uint32_t spins = 0;
+            while ((int)(k - k0) - prog[q] > kGateWindow) {
+              if ((++spins & 0xff) == 0) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > SPNERF_WATCHDOG_CYCLES) { atomicCAS(&g_watchdog_code, 0u, 45u); __trap(); }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        mbar_wait(&bar_empty[stage], phase ^ 1, 40);
+        if (elect_one()) {
           uint8_t* dst = smem + stage * kStageBytes;
-          mbar_expect_tx(&bar_full[stage], (uint32_t)(2 + t.nb) * kSlabBytes);
-          const uint8_t* abase = (t.a.from_grads ? p.gsaves + k * (int64_t)p.grad_stride
-                                                 : p.saves + k * (int64_t)p.save_stride);
-          bulk_g2s(dst, abase + (size_t)t.a.slab * kSlabBytes, 2 * kSlabBytes, &bar_full[stage]);
-          for (int j = 0; j < t.nb; ++j) {
-            const uint8_t* bbase = (t.b[j].from_grads ? p.gsaves + k * (int64_t)p.grad_stride
-                                                      : p.saves + k * (int64_t)p.save_stride);
-            bulk_g2s(dst + (2 + j) * kSlabBytes, bbase + (size_t)t.b[j].slab * kSlabBytes, kSlabBytes,
+          mbar_expect_tx(&bar_full[stage], bytes);
+          for (int r = 0; r < job.na[rank]; ++r) {
+            const Run run = job.a[rank][r];
+            const uint8_t* src = (run.from_grads ? p.gsaves + k * p.grad_stride : p.saves + k * p.save_stride) +
+                                 (size_t)run.unit * kSlabBytes + (size_t)run.chunk0 * kChunkBytes;
+            bulk_g2s(dst + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes, &bar_full[stage]);
+          }
+          for (int j = 0; j < job.nb; ++j) {
+            const Run run = job.b[rank][j];
+            const uint8_t* src = (run.from_grads ? p.gsaves + k * p.grad_stride : p.saves + k * p.save_stride) +
+                                 (size_t)run.unit * kSlabBytes + (size_t)run.chunk0 * kChunkBytes;
+            bulk_g2s(dst + kABytes + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes,
                      &bar_full[stage]);
           }
-          stage ^= 1; if (stage == 0) phase ^= 1;
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (rank == 0 && item.npeers > 1 && lane == 0) { volatile int* prog = p.progress; prog[it] = 1 << 30; }   // done: never holds a peer back
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ---- relay: second arrival on the issuer's stage barrier ----
+    uint32_t stage = 0, phase = 0;
+    const uint32_t remote0 = mapa_shared(smem_u32(&bar_full[0]), 0);
+    for (int it = pair; it < p.n_items; it += npairs) {
+      const Item item = p.items[it];
+      if (item.job < 0) continue;
+      int64_t k0, k1;
+      item_range(item, p.n_ptiles, k0, k1);
+      for (int64_t k = k0; k < k1; ++k) {
+        mbar_wait(&bar_full[stage], phase, 44);
+        if (elect_one()) mbar_arrive_remote(remote0 + stage * 8u);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // saved tiles are row-interleaved: 16-byte chunk (8 features) of all 128 points contiguous, i.e. the
-      // no-swizzle MN-major operand form: core matrices 128 B apart along K (points), 2048 B along M/N
-      constexpr uint64_t tmpl = make_smem_desc_template(128, 2048, kSwizzleNone);
-      uint32_t stage = 0, phase = 0, drained_par = 0;
-      bool first_gemm = true;
-      for (int g = 0; g < p.n_gemms; ++g) {
-        int tile, slice; int64_t k0, k1;
-        if (!my_work(g, tile, k0, k1, slice)) continue;
-        const OutTile t = p.tiles[tile];
-        if (!first_gemm) { mbar_wait(bar_drained, drained_par, 41); drained_par ^= 1; tc_fence_after(); }
-        first_gemm = false;
-        const int n_hi = t.nb > 4 ? 256 : t.nb * 64;        // first instruction: up to 4 slabs
-        const int n_lo = t.nb > 4 ? (t.nb - 4) * 64 : 0;    // second: the remaining slab
-        for (int64_t k = k0; k < k1; ++k) {
-          mbar_wait(&bar_full[stage], phase, 42);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + stage * kStageBytes), b0 = a0 + 2 * kSlabBytes;
+    // ---- issuer: 8 K-steps x (1 or 2) pair MMAs per stage ----
+    // saved tiles are row-interleaved: core matrices 128 B apart along K (points), 2048 B along M/N
+    constexpr uint64_t tmpl = make_smem_desc_template(128, kChunkBytes, kSwizzleNone);
+    uint32_t stage = 0, phase = 0, drained_par = 0;
+    bool first_item = true;
+    long long* prof = (lane == 0 && p.prof) ? p.prof + 8 * pair : nullptr;
+    long long w_full = 0, w_drained = 0, t_issue = 0, n_tiles = 0, t_all = prof ? clock64() : 0;
+    for (int it = pair; it < p.n_items; it += npairs) {
+      const Item item = p.items[it];
+      if (item.job < 0) continue;
+      const Job& job = p.jobs[item.job];
+      int64_t k0, k1;
+      item_range(item, p.n_ptiles, k0, k1);
+      const int nb = job.nb;
+      const uint32_t idesc0 = make_idesc_f16(256, job.n[0], 1, 1), idesc1 = make_idesc_f16(256, nb > 1 ? job.n[1] : 16, 1, 1);
+      const uint32_t b1_off = (uint32_t)job.b[0][nb > 1 ? 1 : 0].dst_chunk * kChunkBytes;
+      long long t0 = prof ? clock64() : 0;
+      if (!first_item) { mbar_wait_cluster(bar_drained, drained_par, 41); drained_par ^= 1; tc_fence_after(); }
+      if (prof) w_drained += clock64() - t0;
+      first_item = false;
+      for (int64_t k = k0; k < k1; ++k) {
+        t0 = prof ? clock64() : 0;
+        mbar_wait_cluster(&bar_full[stage], phase, 42);
+        const long long t1 = prof ? clock64() : 0;
+        if (prof) { w_full += t1 - t0; ++n_tiles; }
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + stage * kStageBytes), b0 = a0 + kABytes;
+        if (elect_one()) {
 #pragma unroll
           for (uint32_t s = 0; s < 8; ++s) {                 // 128 points = 8 K-steps of 16 rows
             const uint32_t acc = (k > k0 || s > 0) ? 1u : 0u;
-            umma_f16(tmem_base, smem_desc(tmpl, a0 + s * 256), smem_desc(tmpl, b0 + s * 256),
-                     make_idesc_f16(128, n_hi, 1, 1), acc);
-            if (n_lo)
-              umma_f16(tmem_base + 256, smem_desc(tmpl, a0 + s * 256),
-                       smem_desc(tmpl, b0 + 4 * kSlabBytes + s * 256), make_idesc_f16(128, n_lo, 1, 1), acc);
+            umma2_f16(tmem_base, smem_desc(tmpl, a0 + s * 256), smem_desc(tmpl, b0 + s * 256), idesc0, acc);
+            if (nb > 1)
+              umma2_f16(tmem_base + 256, smem_desc(tmpl, a0 + s * 256), smem_desc(tmpl, b0 + b1_off + s * 256), idesc1, acc);
           }
-          umma_commit(&bar_empty[stage]);
-          stage ^= 1; if (stage == 0) phase ^= 1;
+          umma2_commit(&bar_empty[stage]);
         }
-        umma_commit(bar_acc);
+        __syncwarp();
+        if (prof) t_issue += clock64() - t1;
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma2_commit(bar_acc);
+      __syncwarp();
     }
-  } else {
-    // epilogue: accumulator -> workspace (plain stores; the reduce kernel sums the slices)
-    const int q = warp & 3;                      // TMEM lane quarter of this warp (warps 2,3,4,5 -> 2,3,0,1)
+    if (prof) { prof[0] = w_full; prof[1] = w_drained; prof[2] = t_issue; prof[3] = n_tiles; prof[4] = clock64() - t_all; }
+  } else if (warp >= 4) {
+    // ---- epilogue warps.  While the MMAs run they sum the columns of this CTA's half of B' over the
+    // points (= the bias gradients of the layer, fp32) straight from shared memory; afterwards they
+    // move the CTA's 128 accumulator rows to the workspace (the reduce kernel sums the slices).
+    const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int et = (int)threadIdx.x - 128;          // 0..127
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_par = 0;
-    for (int g = 0; g < p.n_gemms; ++g) {
-      int tile, slice; int64_t k0, k1;
-      if (!my_work(g, tile, k0, k1, slice)) continue;
-      const OutTile t = p.tiles[tile];
-      const GemmInfo gi = p.gemms[g];
-      mbar_wait(bar_acc, acc_par, 43); acc_par ^= 1;
-      tc_fence_after();
-      float* dst = p.ws + gi.ws_base + (int64_t)slice * gi.ws_slice_floats + t.ws_off + (size_t)row * (t.nb * 64);
-      if (k1 > k0) {
-        for (int c0 = 0; c0 < t.nb * 64; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_wait_ld();
+    const uint32_t drained_remote = mapa_shared(smem_u32(bar_drained), 0);
+    uint32_t acc_par = 0, stage = 0, phase = 0;
+    for (int it = pair; it < p.n_items; it += npairs) {
+      const Item item = p.items[it];
+      if (item.job < 0) continue;
+      const Job& job = p.jobs[item.job];
+      int64_t k0, k1;
+      item_range(item, p.n_ptiles, k0, k1);
+      // thread -> chunk (8 columns) et / 4 of the 32 B' chunks, point quarter et % 4
+      float cs[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+      const int ch = et >> 2, pq = et & 3;
+      for (int64_t k = k0; k < k1; ++k) {
+        // always follow the ring (an early second arrival on a stage's empty barrier would complete the
+        // wrong phase); the sums themselves only for the job that owns the layer's bias
+        if (lane == 0) {
+          if (rank == 0) mbar_wait_cluster(&bar_full[stage], phase, 46);
+          else mbar_wait(&bar_full[stage], phase, 46);
         }
+        __syncwarp();
+        if (job.colsum) {
+          const uint8_t* bt = smem + stage * kStageBytes + kABytes + ch * kChunkBytes + pq * 512;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int pp = (i + et) & 31;            // staggered start: 8 consecutive threads hit 8 distinct 16-B slots
+            const uint4 v = *reinterpret_cast<const uint4*>(bt + pp * 16);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h[e]);
+              cs[2 * e] += f.x; cs[2 * e + 1] += f.y;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) mbar_arrive(&bar_empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) mbar_wait(bar_acc, acc_par, 43);
+      __syncwarp();
+      acc_par ^= 1;
+      tc_fence_after();
+      float* tile = p.ws + item.ws_off + (size_t)rank * kWsRows * job.ncols;
+      float* dst = tile + (size_t)row * job.ncols;
+      if (k1 > k0) {
+        int out = 0;
+        for (int j = 0; j < job.nb; ++j)
+          for (int c0 = 0; c0 < job.n[j]; c0 += 16, out += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + 256 * j + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<uint4*>(dst + out + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
       } else {
-        for (int c0 = 0; c0 < t.nb * 64; c0 += 4) *reinterpret_cast<uint4*>(dst + c0) = make_uint4(0, 0, 0, 0);
+        for (int c0 = 0; c0 < job.ncols; c0 += 4) *reinterpret_cast<uint4*>(dst + c0) = make_uint4(0, 0, 0, 0);
+      }
+      if (job.colsum) {
+        // the 4 point quarters of a chunk sit in adjacent lanes
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 1);
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 2);
+        }
+        if (pq == 0) {
+          // chunk ch of the B' part: MMA j = ch / 16, column (ch % 16) * 8 of this CTA's half
+          const int j = ch >> 4;
+          if (j < job.nb && (ch & 15) * 8 < job.n[j] / 2) {
+            float* crow = tile + (size_t)128 * job.ncols + (j == 0 ? 0 : job.n[0]) + rank * (job.n[j] / 2) + (ch & 15) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) crow[e] = cs[e];
+          }
+        }
       }
       tc_fence_before();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) mbar_arrive(bar_drained);
+      if (threadIdx.x == 128) {
+        if (rank == 0) mbar_arrive(bar_drained);
+        else mbar_arrive_remote(drained_remote);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
-// out[m][j] = inv_scale * sum over slices of the workspace partials
-__global__ void wgrad_reduce_kernel(const Segment* __restrict__ segs, const OutTile* __restrict__ tiles,
-                                    const GemmInfo* __restrict__ gemms, const float* __restrict__ ws,
+// dst[r * ld_row + c * ld_col] = inv_scale * sum over the job's slices of the workspace partials
+__global__ void wgrad_reduce_kernel(const Segment* __restrict__ segs, const Job* __restrict__ jobs,
+                                    const Item* __restrict__ items, const float* __restrict__ ws,
                                     const float* __restrict__ scale) {
   const Segment sg = segs[blockIdx.x];
-  const OutTile t = tiles[sg.tile];
-  const GemmInfo gi = gemms[t.gemm];
+  const Job& job = jobs[sg.job];
   const float inv = 1.f / *scale;
-  const int width = t.nb * 64;
-  for (int idx = threadIdx.x; idx < sg.m_valid * sg.ncols; idx += blockDim.x) {
-    const int m = idx / sg.ncols, j = idx % sg.ncols;
-    const float* src = ws + gi.ws_base + t.ws_off + (size_t)m * width + sg.col0 + sg.src_col + j;
+  const int total = sg.nrows * sg.ncols;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+    const int r = idx / sg.ncols, c = idx % sg.ncols;
+    const size_t off = ((size_t)sg.rank * kWsRows + sg.row0 + r) * job.ncols + sg.col0 + c;
     float acc = 0.f;
-    for (int s = 0; s < gi.nslices; ++s) acc += src[(int64_t)s * gi.ws_slice_floats];
-    sg.dst[(size_t)(sg.m0 + m) * sg.ld_m + (size_t)j * sg.ld_j] = acc * inv;
+    for (int s = 0; s < job.nitems; ++s) acc += ws[items[job.item0 + s].ws_off + off];
+    sg.dst[(size_t)r * sg.ld_row + (size_t)c * sg.ld_col] = acc * inv;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// host: the list of GEMMs for a configuration
+// host: the list of jobs for a configuration
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-  std::vector<OutTile> tiles;
-  std::vector<GemmInfo> gemms;
+  std::vector<Job> jobs;
+  std::vector<Item> items;      // launch order, followed by a job-major copy
+  int n_launch = 0;
   std::vector<Segment> segs;
   int64_t ws_floats = 0;
 };
 
-// describes where the 64 columns of one B slab go
-struct BSlab { SlabRef ref; int src_col, ncols; float* dst; int ld_m, ld_j; };
+// one block of 128 A' rows: up to 3 runs + what each row range means
+struct RowRange { int row0, nrows; int kind; int i0; };   // kind 0: layer-input features i0.., 1: bias, 2: sun dir, 3: t_emb, 4: encoded input
+struct Block { std::vector<Run> runs; std::vector<RowRange> rows; };
+// one range of B' columns: columns [c0, c0+ncols) of MMA `mma` are output units m0.. of a layer
+struct ColRange {
+  int mma, c0, ncols;
+  float* W; int ld; int m0;      // weight gradient (rows = output units), row stride
+  float* bias;                   // bias gradient or nullptr
+  int in_cols;                   // width of the layer-input part of W (columns beyond it: sun / t / encoded input)
+  bool take_sun, take_t, take_inp;
+};
+struct BSpec { int from_grads, unit, n; };   // MMA j reads n columns starting at the region's first chunk
 
-void add_gemm(Plan& pl, int n_ctas, SlabRef a0, int m_total, const std::vector<BSlab>& bs) {
-  GemmInfo gi{};
-  gi.tile0 = (int)pl.tiles.size();
-  const int m_tiles = m_total / 128;
-  std::vector<std::vector<BSlab>> chunks;
-  for (size_t i = 0; i < bs.size(); i += kMaxBSlabs)
-    chunks.emplace_back(bs.begin() + i, bs.begin() + std::min(bs.size(), i + kMaxBSlabs));
-  int ws_off = 0;
-  const int g = (int)pl.gemms.size();
-  for (int mt = 0; mt < m_tiles; ++mt)
-    for (const auto& ch : chunks) {
-      OutTile t{};
-      t.a = SlabRef{a0.from_grads, (int16_t)(a0.slab + 2 * mt)};
-      t.nb = (int)ch.size();
-      t.gemm = g;
-      t.ws_off = ws_off;
-      for (int j = 0; j < t.nb; ++j) {
-        t.b[j] = ch[j].ref;
-        if (ch[j].dst && ch[j].ncols > 0) {
+// colsum: the layer has no extras block; its bias gradients come from the column sums of B' computed
+// by the first job of the group (row 128 of that job's partial tiles, each CTA its own half)
+void add_group(Plan& pl, const std::vector<BSpec>& bspec, const std::vector<Block>& blocks,
+               const std::vector<ColRange>& cols, std::vector<std::vector<int>>& groups, bool colsum = false) {
+  std::vector<int> group;
+  for (size_t b0 = 0; b0 < blocks.size(); b0 += 2) {
+    Job job{};
+    job.nb = (int)bspec.size();
+    int dst_chunk = 0;
+    for (int j = 0; j < job.nb; ++j) {
+      job.n[j] = bspec[j].n;
+      const int half_chunks = bspec[j].n / 16;          // (n / 2) columns / 8 per chunk
+      for (int r = 0; r < 2; ++r)
+        job.b[r][j] = Run{(int16_t)bspec[j].from_grads, (int16_t)bspec[j].unit, (int16_t)(r * half_chunks),
+                          (int16_t)half_chunks, (int16_t)dst_chunk, 0};
+      dst_chunk += 16;                                   // the second MMA's half starts at chunk 16
+    }
+    job.ncols = job.n[0] + (job.nb > 1 ? job.n[1] : 0);
+    const int jid = (int)pl.jobs.size();
+    for (int r = 0; r < 2; ++r) {
+      job.na[r] = 0;
+      if (b0 + r >= blocks.size()) continue;
+      const Block& blk = blocks[b0 + r];
+      for (const Run& run : blk.runs) job.a[r][job.na[r]++] = run;
+      for (const RowRange& rr : blk.rows)
+        for (const ColRange& cr : cols) {
+          const int packed = (cr.mma == 0 ? 0 : job.n[0]) + cr.c0;
           Segment s{};
-          s.tile = (int)pl.tiles.size(); s.col0 = 64 * j; s.src_col = ch[j].src_col; s.ncols = ch[j].ncols;
-          s.dst = ch[j].dst; s.m0 = 128 * mt; s.m_valid = 128; s.ld_m = ch[j].ld_m; s.ld_j = ch[j].ld_j;
+          s.job = jid; s.rank = r; s.row0 = rr.row0; s.nrows = rr.nrows; s.col0 = packed; s.ncols = cr.ncols;
+          s.ld_row = 1; s.ld_col = cr.ld;
+          if (rr.kind == 0 && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + rr.i0;
+          else if (rr.kind == 1 && cr.bias) { s.dst = cr.bias + cr.m0; s.ld_col = 1; }
+          else if (rr.kind == 2 && cr.take_sun && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
+          else if (rr.kind == 3 && cr.take_t && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
+          else if (rr.kind == 4 && cr.take_inp && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
+          else continue;
+          pl.segs.push_back(s);
+        }
+    }
+    if (colsum && b0 == 0) {
+      job.colsum = 1;
+      for (const ColRange& cr : cols) {
+        if (!cr.bias) continue;
+        const int nj = job.n[cr.mma], base = (cr.mma == 0 ? 0 : job.n[0]);
+        for (int r = 0; r < 2; ++r) {          // CTA r summed columns [r * nj/2, (r+1) * nj/2) of the MMA
+          const int lo = std::max(cr.c0, r * nj / 2), hi = std::min(cr.c0 + cr.ncols, (r + 1) * nj / 2);
+          if (hi <= lo) continue;
+          Segment s{};
+          s.job = jid; s.rank = r; s.row0 = 128; s.nrows = 1; s.col0 = base + lo; s.ncols = hi - lo;
+          s.dst = cr.bias + cr.m0 + (lo - cr.c0); s.ld_row = 0; s.ld_col = 1;
           pl.segs.push_back(s);
         }
       }
-      ws_off += 128 * 64 * t.nb;
-      pl.tiles.push_back(t);
     }
-  gi.ntiles = (int)pl.tiles.size() - gi.tile0;
-  gi.nslices = std::max(1, n_ctas / gi.ntiles);
-  gi.ws_slice_floats = ws_off;
-  gi.ws_base = pl.ws_floats;
-  pl.ws_floats += (int64_t)ws_off * gi.nslices;
-  pl.gemms.push_back(gi);
+    pl.jobs.push_back(job);
+    group.push_back(jid);
+  }
+  groups.push_back(group);
 }
 
-Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_ctas) {
+Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_pairs) {
   Plan pl;
+  std::vector<std::vector<int>> groups;
   const SaveMap sm = make_save_map(c);
   const GradMap gm = make_grad_map(c);
   const NetDims d = make_dims(c);
-  auto S = [](int slab) { return SlabRef{0, (int16_t)slab}; };
-  auto Gr = [](int slab) { return SlabRef{1, (int16_t)slab}; };
-  // B slabs of a dense layer input `first..first+n` with destination weight (rows x ld), column offset 0
-  auto dense = [&](std::vector<BSlab>& v, int first_slab, int nslabs, float* w, int ld) {
-    for (int k = 0; k < nslabs; ++k) v.push_back(BSlab{S(first_slab + k), 0, 64, w ? w + 64 * k : nullptr, ld, 1});
-  };
   auto W = [&](int slot) { return G[slot]; };
+  // 128-row blocks of a saved activation of `width` features starting at unit `unit`
+  auto act_blocks = [&](int unit, int width, std::vector<Block>& out) {
+    for (int b = 0; b < width / 128; ++b) {
+      Block blk;
+      blk.runs.push_back(Run{0, (int16_t)unit, (int16_t)(16 * b), 16, 0, 0});
+      blk.rows.push_back(RowRange{0, 128, 0, 128 * b});
+      out.push_back(blk);
+    }
+  };
+  // extras block: aux tile [1, sun(3), t(8)] (2 chunks) and optionally the encoded input (8 chunks)
+  auto extras_block = [&](bool with_inp) {
+    Block blk;
+    blk.runs.push_back(Run{0, (int16_t)sm.aux, 0, 2, 0, 0});
+    blk.rows.push_back(RowRange{kAuxColOne, 1, 1, 0});
+    blk.rows.push_back(RowRange{kAuxColSun, 3, 2, 0});
+    if (c.beta) blk.rows.push_back(RowRange{kAuxColT, c.t_dim, 3, 0});
+    if (with_inp) {
+      blk.runs.push_back(Run{0, (int16_t)sm.inp, 0, 8, 2, 0});
+      blk.rows.push_back(RowRange{16, d.in_dim, 4, 0});
+    }
+    return blk;
+  };
+  auto col = [&](int mma, int c0, int ncols, float* w, int ld, int m0, float* bias, int in_cols, bool sun = false,
+                 bool t = false, bool inp = false) {
+    return ColRange{mma, c0, ncols, w, ld, m0, bias, in_cols, sun, t, inp};
+  };
 
   // trunk
   for (int L = 0; L < 8; ++L) {
-    std::vector<BSlab> bs;
     float* w = W(SPNERF_P_FC_W0 + 2 * L);
     float* bptr = W(SPNERF_P_FC_W0 + 2 * L + 1);
-    const int ld = (L == 0) ? d.in_dim : kFeat + (L == c.skip_layer ? d.in_dim : 0);
-    if (L == 0) {
-      bs.push_back(BSlab{S(sm.inp), 0, d.in_dim, w, ld, 1});
-    } else {
-      dense(bs, sm.y[L - 1], 8, w, ld);
-      if (L == c.skip_layer) bs.push_back(BSlab{S(sm.inp), 0, d.in_dim, w + kFeat, ld, 1});
-    }
-    bs.push_back(BSlab{S(sm.aux), 0, 1, bptr, 1, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G[L]), kFeat, bs);
+    const bool skip = (L == c.skip_layer);
+    const int ld = (L == 0) ? d.in_dim : kFeat + (skip ? d.in_dim : 0);
+    std::vector<Block> blocks;
+    if (L > 0) act_blocks(sm.y[L - 1], kFeat, blocks);
+    const bool extras = (L == 0 || skip);           // encoded-input columns need the extras rows
+    if (extras) blocks.push_back(extras_block(true));
+    std::vector<ColRange> cols = {col(0, 0, kHalf, w, ld, 0, bptr, L == 0 ? 0 : kFeat, false, false, true),
+                                  col(1, 0, kHalf, w, ld, kHalf, bptr, L == 0 ? 0 : kFeat, false, false, true)};
+    add_group(pl, {{1, gm.G[L], kHalf}, {1, gm.G[L] + 4, kHalf}}, blocks, cols, groups, !extras);
   }
   {  // feats_from_xyz
-    std::vector<BSlab> bs;
-    dense(bs, sm.y[7], 8, W(SPNERF_P_FEATS_W), kFeat);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_FEATS_B), 1, 1});
-    add_gemm(pl, n_ctas, Gr(gm.g_f), kFeat, bs);
+    std::vector<Block> blocks;
+    act_blocks(sm.y[7], kFeat, blocks);
+    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_FEATS_W), kFeat, 0, W(SPNERF_P_FEATS_B), kFeat),
+                                  col(1, 0, kHalf, W(SPNERF_P_FEATS_W), kFeat, kHalf, W(SPNERF_P_FEATS_B), kFeat)};
+    add_group(pl, {{1, gm.g_f, kHalf}, {1, gm.g_f + 4, kHalf}}, blocks, cols, groups, true);
   }
-  if (c.sem) {  // logit_from_label.0
-    std::vector<BSlab> bs;
-    dense(bs, sm.y[7], 8, W(SPNERF_P_SEM0_W), kFeat);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_SEM0_B), 1, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G_sem), kHalf, bs);
+  {  // heads reading h: logit_from_label.0 (if any) and sigma_from_xyz.0 (column 4 of the small-gradient tile)
+    std::vector<Block> blocks;
+    act_blocks(sm.y[7], kFeat, blocks);
+    std::vector<ColRange> cols;
+    std::vector<BSpec> bs;
+    if (c.sem) {
+      bs.push_back({1, gm.G_sem, kHalf});
+      cols.push_back(col(0, 0, kHalf, W(SPNERF_P_SEM0_W), kFeat, 0, W(SPNERF_P_SEM0_B), kFeat));
+    }
+    const int mma = (int)bs.size();
+    bs.push_back({1, gm.gsmall, 16});
+    cols.push_back(col(mma, 4, 1, W(SPNERF_P_SIGMA_W), kFeat, 0, nullptr, kFeat));
+    add_group(pl, bs, blocks, cols, groups, true);
   }
-  {  // rgb_from_xyzdir.0
-    std::vector<BSlab> bs;
-    dense(bs, sm.f, 8, W(SPNERF_P_RGB0_W), kFeat);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_RGB0_B), 1, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G_rgb), kHalf, bs);
-  }
-  {  // sun_v_net.0: input [feats, sun_dir]; the aux slab is loaded twice (bias column, sun columns)
-    std::vector<BSlab> bs;
-    dense(bs, sm.f, 8, W(SPNERF_P_SUN0_W), kFeat + 3);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_SUN0_W + 1), 1, 1});
-    bs.push_back(BSlab{S(sm.aux), 1, 3, W(SPNERF_P_SUN0_W) + kFeat, kFeat + 3, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G_sun[0]), kHalf, bs);
-  }
-  for (int j = 1; j < 3; ++j) {  // sun_v_net.2 / .4
-    std::vector<BSlab> bs;
-    dense(bs, sm.sun_y[j - 1], 4, W(SPNERF_P_SUN0_W + 2 * j), kHalf);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_SUN0_W + 2 * j + 1), 1, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G_sun[j]), kHalf, bs);
+  {  // heads reading feats: rgb_from_xyzdir.0 and sun_v_net.0 (input [feats, sun_dir])
+    std::vector<Block> blocks;
+    act_blocks(sm.f, kFeat, blocks);
+    blocks.push_back(extras_block(false));
+    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_RGB0_W), kFeat, 0, W(SPNERF_P_RGB0_B), kFeat),
+                                  col(1, 0, kHalf, W(SPNERF_P_SUN0_W), kFeat + 3, 0, W(SPNERF_P_SUN0_W + 1), kFeat, true)};
+    add_group(pl, {{1, gm.G_rgb, kHalf}, {1, gm.G_sun[0], kHalf}}, blocks, cols, groups);
   }
   if (c.beta) {  // beta_from_xyz.0: input [feats, t_emb]
-    std::vector<BSlab> bs;
-    dense(bs, sm.f, 8, W(SPNERF_P_BETA0_W), kFeat + c.t_dim);
-    bs.push_back(BSlab{S(sm.aux), 0, 1, W(SPNERF_P_BETA0_B), 1, 1});
-    bs.push_back(BSlab{S(sm.aux), 4, c.t_dim, W(SPNERF_P_BETA0_W) + kFeat, kFeat + c.t_dim, 1});
-    add_gemm(pl, n_ctas, Gr(gm.G_beta), kHalf, bs);
+    std::vector<Block> blocks;
+    act_blocks(sm.f, kFeat, blocks);
+    blocks.push_back(extras_block(false));
+    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_BETA0_W), kFeat + c.t_dim, 0, W(SPNERF_P_BETA0_B), kFeat,
+                                      false, true)};
+    add_group(pl, {{1, gm.G_beta, kHalf}}, blocks, cols, groups);
   }
-  // tiny last layers, transposed: D[hidden j][small column c] -> W2[c][j]
-  auto small_head = [&](int a_slab, int m_total, int src_col, int ncols, float* w2, int hidden) {
-    std::vector<BSlab> bs;
-    bs.push_back(BSlab{Gr(gm.gsmall), src_col, ncols, w2, 1, hidden});
-    add_gemm(pl, n_ctas, S(a_slab), m_total, bs);
+  for (int j = 1; j < 3; ++j) {  // sun_v_net.2 / .4
+    std::vector<Block> blocks;
+    act_blocks(sm.sun_y[j - 1], kHalf, blocks);
+    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_SUN0_W + 2 * j), kHalf, 0, W(SPNERF_P_SUN0_W + 2 * j + 1), kHalf)};
+    add_group(pl, {{1, gm.G_sun[j], kHalf}}, blocks, cols, groups, true);
+  }
+  // tiny last layers: rows = hidden activations, columns = the small-gradient tile
+  // [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)]
+  auto small_head = [&](int unit, int c0, int ncols, float* w2) {
+    std::vector<Block> blocks;
+    act_blocks(unit, kHalf, blocks);
+    std::vector<ColRange> cols;
+    for (int k = 0; k < ncols; ++k) cols.push_back(col(0, c0 + k, 1, w2 ? w2 + (size_t)k * kHalf : nullptr, 0, 0, nullptr, kHalf));
+    add_group(pl, {{1, gm.gsmall, 16}}, blocks, cols, groups);
   };
-  small_head(sm.rgb_y, kHalf, 0, 3, W(SPNERF_P_RGB2_W), kHalf);
-  small_head(sm.sun_y[2], kHalf, 3, 1, W(SPNERF_P_SUN0_W + 6), kHalf);
-  small_head(sm.y[7], kFeat, 4, 1, W(SPNERF_P_SIGMA_W), kFeat);
-  if (c.beta) small_head(sm.beta_y, kHalf, 5, 1, W(SPNERF_P_BETA2_W), kHalf);
-  if (c.sem) small_head(sm.sem_y, kHalf, 8, c.num_sem_classes, W(SPNERF_P_SEM2_W), kHalf);
+  small_head(sm.rgb_y, 0, 3, W(SPNERF_P_RGB2_W));
+  small_head(sm.sun_y[2], 3, 1, W(SPNERF_P_SUN0_W + 6));
+  if (c.beta) small_head(sm.beta_y, 5, 1, W(SPNERF_P_BETA2_W));
+  if (c.sem) small_head(sm.sem_y, 8, c.num_sem_classes, W(SPNERF_P_SEM2_W));
+
+  // ---- point slices: about kTargetItemsPerPair items of equal cost per pair ----
+  // cost of one 128-point tile of a job in cycles: the larger of its MMA time (8 K-steps of
+  // 128 * n / 256 cycles per MMA) and its operand load time (~40 B/cycle/SM from L2)
+  std::vector<double> gcost(groups.size());
+  double total = 0;
+  for (size_t g = 0; g < groups.size(); ++g) {
+    double cst = 0;
+    for (int jid : groups[g]) {
+      const Job& job = pl.jobs[jid];
+      int chunks = 0;
+      for (int r = 0; r < 2; ++r) {
+        int ch = 0;
+        for (int k = 0; k < job.na[r]; ++k) ch += job.a[r][k].nchunks;
+        for (int j = 0; j < job.nb; ++j) ch += job.b[r][j].nchunks;
+        chunks = std::max(chunks, ch);
+      }
+      double mma = 0;
+      for (int j = 0; j < job.nb; ++j) mma += 4.0 * std::max(job.n[j], 32);
+      cst += std::max(mma, chunks * (double)kChunkBytes / 40.0) + 100.0;
+    }
+    gcost[g] = cst;
+    total += cst;
+  }
+  const double target_items = (double)kTargetItemsPerPair * n_pairs;
+  for (size_t g = 0; g < groups.size(); ++g) {
+    const int nj = (int)groups[g].size();
+    const int slices = std::max(1, (int)std::lround(target_items * gcost[g] / total / nj));
+    for (int jid : groups[g]) pl.jobs[jid].nitems = slices;
+    // slice-major: the jobs of a group that share a slice are adjacent items, all in the same wave
+    // (item i runs on pair i % n_pairs in wave i / n_pairs), padded with empty items where needed
+    for (int s = 0; s < slices; ++s) {
+      while ((int)(pl.items.size() % n_pairs) + nj > n_pairs) {
+        Item pad{};
+        pad.job = -1; pad.nslices = 1;
+        pl.items.push_back(pad);
+      }
+      const int peer0 = (int)pl.items.size();
+      for (int jid : groups[g]) {
+        Item it{};
+        it.job = jid; it.slice = s; it.nslices = slices; it.peer0 = peer0;
+        it.npeers = getenv("SPNERF_WGRAD_GATE") ? nj : 1;     // experiment: pace the peers (slower as measured)
+        it.ws_off = pl.ws_floats;
+        pl.ws_floats += 2 * kWsRows * (int64_t)pl.jobs[jid].ncols;
+        pl.items.push_back(it);
+      }
+    }
+  }
+  pl.n_launch = (int)pl.items.size();
+  // the reduce kernel walks a job's items through item0 + s: append a job-major copy
+  std::vector<Item> by_job;
+  for (size_t jid = 0; jid < pl.jobs.size(); ++jid) {
+    pl.jobs[jid].item0 = pl.n_launch + (int)by_job.size();
+    for (int i = 0; i < pl.n_launch; ++i)
+      if (pl.items[i].job == (int)jid) by_job.push_back(pl.items[i]);
+  }
+  pl.items.insert(pl.items.end(), by_job.begin(), by_job.end());
   return pl;
 }
 
 int n_sms() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
+  return sms > 1 ? sms : 148;
 }
 
+size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 size_t table_bytes(const Plan& pl) {
-  return pl.tiles.size() * sizeof(OutTile) + pl.gemms.size() * sizeof(GemmInfo) + pl.segs.size() * sizeof(Segment) + 64;
+  return align16(pl.jobs.size() * sizeof(Job)) + align16(pl.items.size() * sizeof(Item)) + pl.segs.size() * sizeof(Segment) + 64;
+}
+constexpr int64_t kTableRoom = 262144, kProgressRoom = 16384;
+
+struct Tables { Job* jobs; Item* items; Segment* segs; };
+Tables table_ptrs(const Plan& pl, void* workspace) {
+  uint8_t* tab = static_cast<uint8_t*>(workspace) + (size_t)pl.ws_floats * 4;
+  Tables t;
+  t.jobs = reinterpret_cast<Job*>(tab);
+  tab += align16(pl.jobs.size() * sizeof(Job));
+  t.items = reinterpret_cast<Item*>(tab);
+  tab += align16(pl.items.size() * sizeof(Item));
+  t.segs = reinterpret_cast<Segment*>(tab);
+  return t;
 }
 
 }  // namespace
+
+static long long* g_prof_wgrad = nullptr;
+extern "C" void spnerf_debug_counters_wgrad(long long* dev_buf8_per_pair) { g_prof_wgrad = dev_buf8_per_pair; }
 
 extern "C" int64_t spnerf_mlp_wgrad_workspace_bytes(const SpnerfNetConfig* cfg) {
   if (!cfg) return -1;
   float* G[SPNERF_NUM_PARAMS] = {};
   // the plan depends on the SM count only through the slice counts; query-time device = run-time device
-  Plan pl = make_plan(*cfg, G, n_sms());
-  return (int64_t)pl.ws_floats * 4 + 65536;   // partial tiles + room for the device tables
+  Plan pl = make_plan(*cfg, G, n_sms() / 2);
+  return (int64_t)pl.ws_floats * 4 + kTableRoom + kProgressRoom;   // partial tiles + device tables + progress words
 }
 
-namespace {
-struct Tables { OutTile* tiles; GemmInfo* gemms; Segment* segs; };
-Tables table_ptrs(const Plan& pl, void* workspace) {
-  uint8_t* tab = static_cast<uint8_t*>(workspace) + (size_t)pl.ws_floats * 4;
-  Tables t;
-  t.tiles = reinterpret_cast<OutTile*>(tab);
-  t.gemms = reinterpret_cast<GemmInfo*>(t.tiles + pl.tiles.size());
-  t.segs = reinterpret_cast<Segment*>(t.gemms + pl.gemms.size());
-  return t;
-}
-}  // namespace
-
-// Uploads the GEMM / scatter tables to the tail of the workspace.  Call once per (configuration,
+// Uploads the job / item / scatter tables to the tail of the workspace.  Call once per (configuration,
 // gradient pointers, workspace); synchronises the stream (the tables come from pageable memory).
 extern "C" int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* a, void* stream_) {
   if (!a || !a->grads_host || !a->workspace) return SPNERF_ERR_BAD_ARG;
   if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  Plan pl = make_plan(a->cfg, a->grads_host, n_sms());
+  Plan pl = make_plan(a->cfg, a->grads_host, n_sms() / 2);
   const size_t tb = table_bytes(pl);
-  if ((int64_t)pl.ws_floats * 4 + (int64_t)tb > a->workspace_bytes || tb > 65536) return SPNERF_ERR_WORKSPACE;
+  if ((int64_t)pl.ws_floats * 4 + (int64_t)tb > a->workspace_bytes || (int64_t)tb > kTableRoom) return SPNERF_ERR_WORKSPACE;
   const Tables t = table_ptrs(pl, a->workspace);
-  cudaMemcpyAsync(t.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(OutTile), cudaMemcpyHostToDevice, stream);
-  cudaMemcpyAsync(t.gemms, pl.gemms.data(), pl.gemms.size() * sizeof(GemmInfo), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(t.jobs, pl.jobs.data(), pl.jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(t.items, pl.items.data(), pl.items.size() * sizeof(Item), cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(t.segs, pl.segs.data(), pl.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   return e == cudaSuccess ? 0 : -(int)e;
@@ -387,25 +642,31 @@ extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   if (a->n_points <= 0) return a->n_points == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int ctas = n_sms();
-  Plan pl = make_plan(a->cfg, a->grads_host, ctas);     // host-side counts only; tables were uploaded by _prepare
-  if ((int64_t)pl.ws_floats * 4 + (int64_t)table_bytes(pl) > a->workspace_bytes) return SPNERF_ERR_WORKSPACE;
+  const int pairs = n_sms() / 2;
+  Plan pl = make_plan(a->cfg, a->grads_host, pairs);     // host-side counts only; tables were uploaded by _prepare
+  if ((int64_t)pl.ws_floats * 4 + kTableRoom + kProgressRoom > a->workspace_bytes ||
+      (int64_t)pl.n_launch * 4 > kProgressRoom)
+    return SPNERF_ERR_WORKSPACE;
   const Tables t = table_ptrs(pl, a->workspace);
   WgradParams p;
   p.saves = static_cast<const uint8_t*>(a->saves); p.gsaves = static_cast<const uint8_t*>(a->grad_saves);
-  p.save_stride = make_save_map(a->cfg).total * kSlabBytes;
-  p.grad_stride = make_grad_map(a->cfg).total * kSlabBytes;
+  p.save_stride = (int64_t)make_save_map(a->cfg).total * kSlabBytes;
+  p.grad_stride = (int64_t)make_grad_map(a->cfg).total * kSlabBytes;
   p.n_ptiles = (a->n_points + kTileM - 1) / kTileM;
-  p.tiles = t.tiles; p.gemms = t.gemms; p.n_gemms = (int)pl.gemms.size();
+  p.jobs = t.jobs; p.items = t.items;
+  p.n_items = pl.n_launch;                                // the job-major copy behind them is for the reduce kernel
   p.ws = static_cast<float*>(a->workspace);
+  p.progress = reinterpret_cast<int*>(static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4 + kTableRoom);
+  p.prof = g_prof_wgrad;
+  cudaMemsetAsync(p.progress, 0, (size_t)pl.n_launch * sizeof(int), stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW);
     if (e != cudaSuccess) return -(int)e;
     attr_set = true;
   }
-  wgrad_kernel<<<ctas, kWThreads, kSmemW, stream>>>(p);
-  wgrad_reduce_kernel<<<(unsigned)pl.segs.size(), 256, 0, stream>>>(t.segs, t.tiles, t.gemms, p.ws, a->scale);
+  wgrad_kernel<<<2 * std::min(pairs, pl.n_launch), kWThreads, kSmemW, stream>>>(p);
+  wgrad_reduce_kernel<<<dim3((unsigned)pl.segs.size(), 4), 256, 0, stream>>>(t.segs, t.jobs, t.items, p.ws, a->scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
