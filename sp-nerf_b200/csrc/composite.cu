@@ -10,38 +10,77 @@
 // HBM-bound: forward moves 4*N*(n_out+1 read + 2 write) + 4*(3+1+C) bytes per ray.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "../../include/spnerf_b200.h"
+#include "sm100.cuh"
 
 namespace {
+using sm100::mbar_init; using sm100::mbar_wait; using sm100::mbar_expect_tx; using sm100::bulk_g2s;
+using sm100::fence_proxy_async_smem; using sm100::fence_mbar_init;
 
-constexpr int kWarpsPerBlock = 4;
-constexpr int kMaxPerLane = 8;      // n_samples <= 256
+constexpr int kMaxPerLane = 8;      // samples per lane
+constexpr int kSkew = 8;            // floats between the rows of the rays of a group (bank skew)
 
-__device__ __forceinline__ float warp_excl_scan_mul(float v, int lane) {
+// Layout of the work: a warp integrates G rays at a time, LPR = 32 / G lanes per ray, each lane a
+// contiguous block of samples; transmittance is a product scan over the ray's lanes (forward), the
+// adjoint a reverse sum scan (backward).  The rows / depths of the G consecutive rays arrive through
+// the bulk-copy engine (one copy per tensor and group) into a 2-deep per-warp ring, so the next group
+// is in flight while this one is integrated.  G = 4 (n <= 64) or 2 (n <= 128) need 16-byte multiples
+// (n * n_out % 4 == 0, n % 4 == 0); otherwise G = 1 and the warp copies one ray at a time itself.
+template <int LPR>
+__device__ __forceinline__ float seg_excl_scan_mul(float v, int sl) {
   float inc = v;
 #pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    const float o = __shfl_up_sync(0xffffffffu, inc, s);
-    if (lane >= s) inc *= o;
+  for (int s = 1; s < LPR; s <<= 1) {
+    const float o = __shfl_up_sync(0xffffffffu, inc, s, LPR);
+    if (sl >= s) inc *= o;
   }
-  const float ex = __shfl_up_sync(0xffffffffu, inc, 1);
-  return lane == 0 ? 1.f : ex;
+  const float ex = __shfl_up_sync(0xffffffffu, inc, 1, LPR);
+  return sl == 0 ? 1.f : ex;
 }
-__device__ __forceinline__ float warp_sum(float v) {
+// inclusive product over the ray's lanes; ex = product over lanes < sl, tot = product over all of them
+template <int LPR>
+__device__ __forceinline__ void seg_scan_mul(float v, int sl, float& ex, float& tot) {
+  float inc = v;
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  for (int s = 1; s < LPR; s <<= 1) {
+    const float o = __shfl_up_sync(0xffffffffu, inc, s, LPR);
+    if (sl >= s) inc *= o;
+  }
+  ex = __shfl_up_sync(0xffffffffu, inc, 1, LPR);
+  if (sl == 0) ex = 1.f;
+  tot = __shfl_sync(0xffffffffu, inc, LPR - 1, LPR);
+}
+// inclusive suffix sum; ex = sum over lanes > sl, tot = sum over all of them
+template <int LPR>
+__device__ __forceinline__ void seg_suffix_sum(float v, int sl, float& ex, float& tot) {
+  float inc = v;
+#pragma unroll
+  for (int s = 1; s < LPR; s <<= 1) {
+    const float o = __shfl_down_sync(0xffffffffu, inc, s, LPR);
+    if (sl + s < LPR) inc += o;
+  }
+  ex = __shfl_down_sync(0xffffffffu, inc, 1, LPR);
+  if (sl == LPR - 1) ex = 0.f;
+  tot = __shfl_sync(0xffffffffu, inc, 0, LPR);
+}
+template <int LPR>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int s = LPR / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s, LPR);
   return v;
 }
-// exclusive suffix sum: result(lane) = sum of v over lanes > lane
-__device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
+// exclusive suffix sum inside the ray's lanes: result(sl) = sum of v over lanes > sl
+template <int LPR>
+__device__ __forceinline__ float seg_excl_suffix_sum(float v, int sl) {
   float inc = v;
 #pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    const float o = __shfl_down_sync(0xffffffffu, inc, s);
-    if (lane + s < 32) inc += o;
+  for (int s = 1; s < LPR; s <<= 1) {
+    const float o = __shfl_down_sync(0xffffffffu, inc, s, LPR);
+    if (sl + s < LPR) inc += o;
   }
-  const float ex = __shfl_down_sync(0xffffffffu, inc, 1);
-  return lane == 31 ? 0.f : ex;
+  const float ex = __shfl_down_sync(0xffffffffu, inc, 1, LPR);
+  return sl == LPR - 1 ? 0.f : ex;
 }
 
 // coalesced copy of `n` floats global -> shared for one warp (16-byte vectors when aligned)
@@ -70,63 +109,108 @@ struct FwdP {
   float* weights; float* trans; float* rgb; float* rgb_raw; float* depth; float* sem;
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_fwd_kernel(const FwdP p) {
+template <int G>
+__global__ void composite_fwd_kernel(const FwdP p) {
   extern __shared__ __align__(16) float sm[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int row_f = (p.n * p.n_out + 3) & ~3;
-  float* rows = sm + (size_t)wib * (row_f + 2 * p.n);     // [n][n_out]
-  float* zs = rows + row_f;                               // [n]
-  float* ws = zs + p.n;                                   // [n]  (weights, then reused for T)
-  const int per = (p.n + 31) / 32;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib, nw = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t r = warp0; r < p.n_rays; r += nw) {
-    warp_load(rows, p.out + r * p.n * p.n_out, p.n * p.n_out, lane);
-    warp_load(zs, p.z + r * p.n, p.n, lane);
+  constexpr bool PIPE = G > 1;
+  constexpr int LPR = 32 / G;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  // Lane sl of a ray owns samples sl, sl + LPR, sl + 2 LPR, ...: consecutive lanes read consecutive rows
+  // (stride n_out floats), and the rays of a group are skewed by kSkew floats, so the shared-memory
+  // reads of a warp fall into distinct banks (a blocked assignment was 8-way conflicted).
+  const int row_f = ((p.n * p.n_out + 3) & ~3) + (PIPE ? kSkew : 0);
+  const int buf_f = G * (row_f + p.n);                     // one ring slot: rows [G][n][n_out] (+skew) + depths [G][n]
+  float* base = sm + (size_t)wib * ((PIPE ? 2 : 1) * buf_f + G * p.n + 4);
+  float* wstage = base + (PIPE ? 2 : 1) * buf_f;           // [G][n] weights staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wstage + G * p.n);
+  const int per = (p.n + LPR - 1) / LPR;
+  const int64_t warp0 = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
+  const int64_t n_groups = (p.n_rays + G - 1) / G;
+  auto prefetch = [&](int64_t g, int slot) {
+    const int64_t r0 = g * G;
+    const uint32_t cnt = (uint32_t)min((int64_t)G, p.n_rays - r0);
+    const uint32_t row_bytes = (uint32_t)(p.n * p.n_out) * 4u, z_bytes = cnt * (uint32_t)p.n * 4u;
+    mbar_expect_tx(&bars[slot], cnt * row_bytes + z_bytes);
+    for (uint32_t q = 0; q < cnt; ++q)
+      bulk_g2s(base + slot * buf_f + q * row_f, p.out + (r0 + q) * p.n * p.n_out, row_bytes, &bars[slot]);
+    bulk_g2s(base + slot * buf_f + G * row_f, p.z + r0 * p.n, z_bytes, &bars[slot]);
+  };
+  if (PIPE) {
+    if (lane == 0) {
+      mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+      fence_mbar_init();
+      if (warp0 < n_groups) prefetch(warp0, 0);
+    }
     __syncwarp();
-    // lane owns samples [i0, i1)
-    const int i0 = min(lane * per, p.n), i1 = min(i0 + per, p.n);
-    float alpha[kMaxPerLane], tloc[kMaxPerLane];
-    float prod = 1.f;
+  }
+  int t = 0;
+  for (int64_t g = warp0; g < n_groups; g += nw, ++t) {
+    float* slot = base + (PIPE ? (t & 1) : 0) * buf_f;
+    const int64_t r0 = g * G;
+    const int cnt = (int)min((int64_t)G, p.n_rays - r0);
+    const int64_t r = r0 + sub;
+    const bool active = sub < cnt;
+    float* rows = slot + sub * row_f;                      // [n][n_out]
+    float* zs = slot + G * row_f + sub * p.n;              // [n]  (depths, then reused for T)
+    float* ws = wstage + sub * p.n;
+    if (PIPE) {
+      if (lane == 0 && g + nw < n_groups) prefetch(g + nw, (t + 1) & 1);
+      mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u, 50);
+    } else {
+      warp_load(rows, p.out + r * p.n * p.n_out, p.n * p.n_out, lane);
+      warp_load(zs, p.z + r * p.n, p.n, lane);
+      __syncwarp();
+    }
+    // lane owns samples sl + LPR * k
+    float alpha[kMaxPerLane], keep[kMaxPerLane];
 #pragma unroll
     for (int k = 0; k < kMaxPerLane; ++k) {
-      const int i = i0 + k;
-      if (k < per && i < i1) {
+      const int i = sl + LPR * k;
+      alpha[k] = 0.f; keep[k] = 1.f;
+      if (k < per && i < p.n) {
         const float delta = (i + 1 < p.n) ? zs[i + 1] - zs[i] : 1e10f;                 // spnerf.py:116-118
         float s = rows[i * p.n_out + 3];
-        if (p.noise) s += p.noise[r * p.n + i] * p.noise_std;                          // :121-122
+        if (p.noise && active) s += p.noise[r * p.n + i] * p.noise_std;                // :121-122
         alpha[k] = 1.f - expf(-delta * fmaxf(s, 0.f));                                 // :123
-        tloc[k] = prod;
-        prod *= (1.f - alpha[k] + 1e-10f);                                             // :126
+        keep[k] = 1.f - alpha[k] + 1e-10f;                                             // :126
       }
     }
-    const float before = warp_excl_scan_mul(prod, lane);                               // :127 (exclusive cumprod)
     float acc_d = 0.f, acc_c[3] = {0.f, 0.f, 0.f}, acc_s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float carry = 1.f;                                      // product over the samples of earlier rounds
 #pragma unroll
     for (int k = 0; k < kMaxPerLane; ++k) {
-      const int i = i0 + k;
-      if (k < per && i < i1) {
-        const float T = before * tloc[k];
-        const float w = alpha[k] * T;                                                  // :128
-        const float* o = rows + i * p.n_out;
-        const float sv = o[4];
-        acc_d = fmaf(w, zs[i], acc_d);                                                 // :131
+      const int i = sl + LPR * k;
+      if (k < per) {                                        // warp-uniform
+        float ex, tot;
+        seg_scan_mul<LPR>(keep[k], sl, ex, tot);            // :127 (exclusive cumprod), one round of LPR samples
+        if (i < p.n) {
+          const float T = carry * ex;
+          const float w = alpha[k] * T;                                                // :128
+          const float* o = rows + i * p.n_out;
+          const float sv = o[4];
+          acc_d = fmaf(w, zs[i], acc_d);                                               // :131
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc_c[c] = fmaf(w * o[c], sv + (1.f - sv) * o[5 + c], acc_c[c]);   // :132-133
-        for (int c = 0; c < p.n_sem; ++c) acc_s[c] += o[p.col_sem + c];
-        ws[i] = w;
-        zs[i] = T;   // z no longer needed by this lane's block; neighbours read zs[i+1] only before this point
+          for (int c = 0; c < 3; ++c) acc_c[c] = fmaf(w * o[c], sv + (1.f - sv) * o[5 + c], acc_c[c]);   // :132-133
+          for (int c = 0; c < p.n_sem; ++c) acc_s[c] += o[p.col_sem + c];
+          ws[i] = w;
+          zs[i] = T;   // every depth difference was formed in the first loop (the scans order the loops)
+        }
+        carry *= tot;
       }
     }
-    // (the read of zs[i1] by this lane happened in the first loop, before any lane overwrote it:
-    //  the scan's shuffles order the two loops across the warp)
+    // The slot was written through the generic proxy (T over the depths) and is refilled by the copy
+    // engine two iterations later: order those writes for the async proxy here, BEFORE this
+    // iteration's global stores are issued (the fence's membar would otherwise wait for them).
+    if (PIPE) fence_proxy_async_smem();
     __syncwarp();
-    warp_store(p.weights + r * p.n, ws, p.n, lane);
-    warp_store(p.trans + r * p.n, zs, p.n, lane);
-    acc_d = warp_sum(acc_d);
+    warp_store(p.weights + r0 * p.n, wstage, cnt * p.n, lane);
+    warp_store(p.trans + r0 * p.n, slot + G * row_f, cnt * p.n, lane);
+    acc_d = seg_sum<LPR>(acc_d);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) acc_c[c] = warp_sum(acc_c[c]);
-    for (int c = 0; c < p.n_sem; ++c) acc_s[c] = warp_sum(acc_s[c]);
-    if (lane == 0) {
+    for (int c = 0; c < 3; ++c) acc_c[c] = seg_sum<LPR>(acc_c[c]);
+    for (int c = 0; c < p.n_sem; ++c) acc_s[c] = seg_sum<LPR>(acc_s[c]);
+    if (sl == 0 && active) {
       p.depth[r] = acc_d;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -148,103 +232,154 @@ struct BwdP {
   float* g_out; float* g_sky_ray; unsigned int* absmax_bits;
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_bwd_kernel(const BwdP p) {
+template <int G>
+__global__ void composite_bwd_kernel(const BwdP p) {
   extern __shared__ __align__(16) float sm[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int row_f = (p.n * p.n_out + 3) & ~3;
-  float* rows = sm + (size_t)wib * (2 * row_f + 3 * p.n);   // network rows, overwritten by their gradients
-  float* ext = rows + row_f;                                // external gradient rows (optional)
-  float* zs = ext + row_f;
-  float* ws = zs + p.n;
-  float* ts = ws + p.n;
-  const int per = (p.n + 31) / 32;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib, nw = (int64_t)gridDim.x * kWarpsPerBlock;
-  float amax = 0.f;
-  for (int64_t r = warp0; r < p.n_rays; r += nw) {
-    warp_load(rows, p.out + r * p.n * p.n_out, p.n * p.n_out, lane);
-    if (p.g_out_ext) warp_load(ext, p.g_out_ext + r * p.n * p.n_out, p.n * p.n_out, lane);
-    warp_load(zs, p.z + r * p.n, p.n, lane);
-    warp_load(ws, p.weights + r * p.n, p.n, lane);
-    warp_load(ts, p.trans + r * p.n, p.n, lane);
+  constexpr bool PIPE = G > 1;
+  constexpr int LPR = 32 / G;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int row_f = ((p.n * p.n_out + 3) & ~3) + (PIPE ? kSkew : 0);   // skewed per ray, see the forward kernel
+  const int ext_f = p.g_out_ext ? row_f : 0;
+  const int buf_f = G * (row_f + ext_f + 3 * p.n);          // one ring slot: rows | external gradient rows | z | w | T
+  float* base = sm + (size_t)wib * ((PIPE ? 2 : 1) * buf_f + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (PIPE ? 2 : 1) * buf_f);
+  const int per = (p.n + LPR - 1) / LPR;
+  const int64_t warp0 = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
+  const int64_t n_groups = (p.n_rays + G - 1) / G;
+  auto prefetch = [&](int64_t g, int slot) {
+    const int64_t r0 = g * G;
+    const uint32_t cnt = (uint32_t)min((int64_t)G, p.n_rays - r0);
+    const uint32_t row_bytes = (uint32_t)(p.n * p.n_out) * 4u, z_bytes = cnt * (uint32_t)p.n * 4u;
+    float* b = base + slot * buf_f;
+    mbar_expect_tx(&bars[slot], cnt * row_bytes * (p.g_out_ext ? 2u : 1u) + 3u * z_bytes);
+    for (uint32_t q = 0; q < cnt; ++q) {
+      bulk_g2s(b + q * row_f, p.out + (r0 + q) * p.n * p.n_out, row_bytes, &bars[slot]);
+      if (p.g_out_ext) bulk_g2s(b + (G + q) * row_f, p.g_out_ext + (r0 + q) * p.n * p.n_out, row_bytes, &bars[slot]);
+    }
+    float* zb = b + G * (row_f + ext_f);
+    bulk_g2s(zb, p.z + r0 * p.n, z_bytes, &bars[slot]);
+    bulk_g2s(zb + G * p.n, p.weights + r0 * p.n, z_bytes, &bars[slot]);
+    bulk_g2s(zb + 2 * G * p.n, p.trans + r0 * p.n, z_bytes, &bars[slot]);
+  };
+  if (PIPE) {
+    if (lane == 0) {
+      mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+      fence_mbar_init();
+      if (warp0 < n_groups) prefetch(warp0, 0);
+    }
     __syncwarp();
+  }
+  float amax = 0.f;
+  int t = 0;
+  for (int64_t g = warp0; g < n_groups; g += nw, ++t) {
+    float* slot = base + (PIPE ? (t & 1) : 0) * buf_f;
+    const int64_t r0 = g * G;
+    const int cnt = (int)min((int64_t)G, p.n_rays - r0);
+    const int64_t r = r0 + sub;
+    const bool active = sub < cnt;
+    float* rows = slot + sub * row_f;                       // network rows, overwritten by their gradients
+    float* ext = slot + G * row_f + sub * row_f;            // external gradient rows (optional)
+    float* zs = slot + G * (row_f + ext_f) + sub * p.n;
+    float* ws = zs + G * p.n;
+    float* ts = ws + G * p.n;
+    if (PIPE) {
+      if (lane == 0 && g + nw < n_groups) prefetch(g + nw, (t + 1) & 1);
+      mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u, 51);
+    } else {
+      warp_load(rows, p.out + r * p.n * p.n_out, p.n * p.n_out, lane);
+      if (p.g_out_ext) warp_load(ext, p.g_out_ext + r * p.n * p.n_out, p.n * p.n_out, lane);
+      warp_load(zs, p.z + r * p.n, p.n, lane);
+      warp_load(ws, p.weights + r * p.n, p.n, lane);
+      warp_load(ts, p.trans + r * p.n, p.n, lane);
+      __syncwarp();
+    }
     float gh[3] = {0.f, 0.f, 0.f};
-    if (p.g_rgb) {
+    if (p.g_rgb && active) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float raw = p.rgb_raw[r * 3 + c];
         gh[c] = (raw >= 0.f && raw <= 1.f) ? p.g_rgb[r * 3 + c] : 0.f;                 // clamp adjoint
       }
     }
-    const float gd = p.g_depth ? p.g_depth[r] : 0.f;
-    const int i0 = min(lane * per, p.n), i1 = min(i0 + per, p.n);
-    float G[kMaxPerLane], S_loc = 0.f;
+    const float gd = (p.g_depth && active) ? p.g_depth[r] : 0.f;
+    // lane owns samples sl + LPR * k
+    float Gd[kMaxPerLane], Sv[kMaxPerLane];
 #pragma unroll
     for (int k = 0; k < kMaxPerLane; ++k) {
-      const int i = i0 + k;
-      G[k] = 0.f;
-      if (k < per && i < i1) {
+      const int i = sl + LPR * k;
+      Gd[k] = 0.f; Sv[k] = 0.f;
+      if (k < per && i < p.n) {
         const float* o = rows + i * p.n_out;
         const float sv = o[4];
-        float g = gd * zs[i];
+        float gg = gd * zs[i];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g = fmaf(o[c] * (sv + (1.f - sv) * o[5 + c]), gh[c], g);
-        if (p.g_w) g += p.g_w[r * p.n + i];
-        G[k] = g;                                                                       // dL/dw_i
-        S_loc += g * ws[i] + (p.g_t ? p.g_t[r * p.n + i] * ts[i] : 0.f);
+        for (int c = 0; c < 3; ++c) gg = fmaf(o[c] * (sv + (1.f - sv) * o[5 + c]), gh[c], gg);
+        if (p.g_w && active) gg += p.g_w[r * p.n + i];
+        Gd[k] = gg;                                                                     // dL/dw_i
+        Sv[k] = gg * ws[i] + ((p.g_t && active) ? p.g_t[r * p.n + i] * ts[i] : 0.f);
       }
     }
-    float R = warp_excl_suffix_sum(S_loc, lane);     // sum of S over later lanes' blocks
     float gsky[3] = {0.f, 0.f, 0.f};
-    // walk this lane's block backwards so R is the exclusive suffix sum at each sample
+    float carry = 0.f;                                       // sum of S over the samples of later rounds
+    // rounds backwards: R = sum of S over later samples (exclusive suffix sum along the ray)
 #pragma unroll
     for (int k = kMaxPerLane - 1; k >= 0; --k) {
-      const int i = i0 + k;
-      if (k < per && i < i1) {
-        float* o = rows + i * p.n_out;
-        const float w = ws[i], T = ts[i];
-        const float delta = (i + 1 < p.n) ? zs[i + 1] - zs[i] : 1e10f;
-        float s = o[3];
-        if (p.noise) s += p.noise[r * p.n + i] * p.noise_std;
-        const float e = expf(-delta * fmaxf(s, 0.f));          // 1 - alpha
-        const float dalpha = G[k] * T - R / (e + 1e-10f);
-        const float dsigma = (s > 0.f) ? dalpha * delta * e : 0.f;
-        R += G[k] * w + (p.g_t ? p.g_t[r * p.n + i] * T : 0.f);
-        const float sv = o[4];
-        float go[8];
-        float dsv = 0.f;
+      const int i = sl + LPR * k;
+      if (k < per) {                                         // warp-uniform
+        float ex, tot;
+        seg_suffix_sum<LPR>(Sv[k], sl, ex, tot);
+        if (i < p.n) {
+          const float R = carry + ex;
+          float* o = rows + i * p.n_out;
+          const float w = ws[i], T = ts[i];
+          const float delta = (i + 1 < p.n) ? zs[i + 1] - zs[i] : 1e10f;
+          float s = o[3];
+          if (p.noise && active) s += p.noise[r * p.n + i] * p.noise_std;
+          const float e = expf(-delta * fmaxf(s, 0.f));          // 1 - alpha
+          const float dalpha = Gd[k] * T - R / (e + 1e-10f);
+          const float dsigma = (s > 0.f) ? dalpha * delta * e : 0.f;
+          const float sv = o[4];
+          float go[8];
+          float dsv = 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float irr = sv + (1.f - sv) * o[5 + c];
-          go[c] = w * irr * gh[c];                              // d albedo
-          const float dirr = w * o[c] * gh[c];
-          dsv = fmaf(dirr, 1.f - o[5 + c], dsv);
-          go[5 + c] = dirr * (1.f - sv);                        // d sky
-        }
-        go[3] = dsigma;
-        go[4] = dsv;
-        const float* e_row = ext + i * p.n_out;
+          for (int c = 0; c < 3; ++c) {
+            const float irr = sv + (1.f - sv) * o[5 + c];
+            go[c] = w * irr * gh[c];                              // d albedo
+            const float dirr = w * o[c] * gh[c];
+            dsv = fmaf(dirr, 1.f - o[5 + c], dsv);
+            go[5 + c] = dirr * (1.f - sv);                        // d sky
+          }
+          go[3] = dsigma;
+          go[4] = dsv;
+          const float* e_row = ext + i * p.n_out;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float v = go[c] + (p.g_out_ext ? e_row[c] : 0.f);
-          o[c] = v;
-          amax = fmaxf(amax, fabsf(v));
-        }
+          for (int c = 0; c < 8; ++c) {
+            const float v = go[c] + (p.g_out_ext ? e_row[c] : 0.f);
+            o[c] = v;
+            if (active) amax = fmaxf(amax, fabsf(v));
+          }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) gsky[c] += o[5 + c];
-        for (int c = 8; c < p.n_out; ++c) {
-          float v = p.g_out_ext ? e_row[c] : 0.f;
-          if (c >= p.col_sem && c < p.col_sem + p.n_sem && p.g_sem) v += p.g_sem[r * p.n_sem + (c - p.col_sem)] / (float)p.n;
-          o[c] = v;
-          amax = fmaxf(amax, fabsf(v));
+          for (int c = 0; c < 3; ++c) gsky[c] += o[5 + c];
+          for (int c = 8; c < p.n_out; ++c) {
+            float v = p.g_out_ext ? e_row[c] : 0.f;
+            if (c >= p.col_sem && c < p.col_sem + p.n_sem && p.g_sem && active)
+              v += p.g_sem[r * p.n_sem + (c - p.col_sem)] / (float)p.n;
+            o[c] = v;
+            if (active) amax = fmaxf(amax, fabsf(v));
+          }
         }
+        carry += tot;
       }
     }
+    if (PIPE) fence_proxy_async_smem();     // see the forward kernel
     __syncwarp();
-    warp_store(p.g_out + r * p.n * p.n_out, rows, p.n * p.n_out, lane);
+    for (int q = 0; q < cnt; ++q)
+      warp_store(p.g_out + (r0 + q) * p.n * p.n_out, slot + q * row_f, p.n * p.n_out, lane);
     if (p.g_sky_ray) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gsky[c] = warp_sum(gsky[c]);
-      if (lane < 3) p.g_sky_ray[r * 3 + lane] = lane == 0 ? gsky[0] : lane == 1 ? gsky[1] : gsky[2];
+      for (int c = 0; c < 3; ++c) gsky[c] = seg_sum<LPR>(gsky[c]);
+      if (sl < 3 && active) p.g_sky_ray[r * 3 + sl] = sl == 0 ? gsky[0] : sl == 1 ? gsky[1] : gsky[2];
     }
     __syncwarp();
   }
@@ -255,14 +390,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_bwd_kernel(cons
   }
 }
 
-int launch_dims(int64_t n_rays, int* blocks) {
+// grid = the blocks that are resident at once (shared memory bound), each warp strides over ray groups
+template <class K, class P>
+int launch(K kern, const P& p, int64_t n_groups, int wpb, size_t smem, cudaStream_t stream, size_t* configured) {
+  if (smem > 48 * 1024 && smem > *configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e;
+    *configured = smem;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t need = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int64_t cap = (int64_t)sms * 16;
-  *blocks = (int)(need < cap ? need : cap);
-  return 0;
+  const int64_t need = (n_groups + wpb - 1) / wpb;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(64 / wpb, (224 * 1024) / (smem + 1024)));
+  const int64_t cap = (int64_t)sms * per_sm;
+  kern<<<(unsigned)(need < cap ? need : cap), wpb * 32, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// rays per warp step: 4 (n <= 64), 2 (n <= 128) with bulk copies; 1 without
+int pick_group(int n, int n_out, bool aligned) {
+  if (!aligned || (n * n_out) % 4 || n % 4) return 1;
+  if (n <= 8 * kMaxPerLane) return 4;
+  if (n <= 16 * kMaxPerLane) return 2;
+  return 1;
 }
 
 }  // namespace
@@ -280,18 +432,16 @@ extern "C" int spnerf_composite_fwd(const SpnerfCompositeFwd* a, void* stream) {
   p.weights = a->weights; p.trans = a->transparency; p.rgb = a->rgb; p.rgb_raw = a->rgb_raw; p.depth = a->depth;
   p.sem = a->sem_logits;
   const int row_f = (p.n * p.n_out + 3) & ~3;
-  const size_t smem = (size_t)kWarpsPerBlock * (row_f + 2 * p.n) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -(int)e;
-    configured = smem;
-  }
-  int blocks;
-  launch_dims(p.n_rays, &blocks);
-  composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : -(int)e;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int G = pick_group(p.n, p.n_out, al16(p.out) && al16(p.z));
+  const int wpb = 4;
+  const int rf = row_f + (G > 1 ? kSkew : 0);
+  const size_t smem = (size_t)wpb * ((G > 1 ? 2 : 1) * G * (rf + p.n) + G * p.n + 4) * sizeof(float);
+  static size_t cfg[3] = {0, 0, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G == 4) return launch(composite_fwd_kernel<4>, p, (p.n_rays + 3) / 4, wpb, smem, st, &cfg[0]);
+  if (G == 2) return launch(composite_fwd_kernel<2>, p, (p.n_rays + 1) / 2, wpb, smem, st, &cfg[1]);
+  return launch(composite_fwd_kernel<1>, p, p.n_rays, wpb, smem, st, &cfg[2]);
 }
 
 extern "C" int spnerf_composite_bwd(const SpnerfCompositeBwd* a, void* stream) {
@@ -308,16 +458,15 @@ extern "C" int spnerf_composite_bwd(const SpnerfCompositeBwd* a, void* stream) {
   p.n_rays = a->n_rays; p.n = a->n_samples; p.n_out = a->n_out; p.col_sem = a->col_sem; p.n_sem = a->n_sem;
   p.g_out = a->g_out; p.g_sky_ray = a->g_sky_ray; p.absmax_bits = reinterpret_cast<unsigned int*>(a->g_absmax);
   const int row_f = (p.n * p.n_out + 3) & ~3;
-  const size_t smem = (size_t)kWarpsPerBlock * (2 * row_f + 3 * p.n) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -(int)e;
-    configured = smem;
-  }
-  int blocks;
-  launch_dims(p.n_rays, &blocks);
-  composite_bwd_kernel<<<blocks, kWarpsPerBlock * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : -(int)e;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int G = pick_group(p.n, p.n_out, al16(p.out) && al16(p.z) && al16(p.weights) && al16(p.trans) &&
+                                             (!p.g_out_ext || al16(p.g_out_ext)));
+  const int slot_f = (row_f + (G > 1 ? kSkew : 0)) * (p.g_out_ext ? 2 : 1) + 3 * p.n;
+  const int wpb = G > 1 ? 2 : 4;      // more resident blocks of 2 warps (shared memory bound)
+  const size_t smem = (size_t)wpb * ((G > 1 ? 2 : 1) * G * slot_f + 4) * sizeof(float);
+  static size_t cfg[3] = {0, 0, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G == 4) return launch(composite_bwd_kernel<4>, p, (p.n_rays + 3) / 4, wpb, smem, st, &cfg[0]);
+  if (G == 2) return launch(composite_bwd_kernel<2>, p, (p.n_rays + 1) / 2, wpb, smem, st, &cfg[1]);
+  return launch(composite_bwd_kernel<1>, p, p.n_rays, wpb, smem, st, &cfg[2]);
 }
