@@ -235,8 +235,8 @@ def run_ours(a):
                                "--depth --sem --num_sem_classes 3 --dense_ss, fc 8x512, 64 samples, n_importance 0",
                    "rays_per_gpu": RAYS_PER_GPU, "global_rays": world * RAYS_PER_GPU, "n_samples": N_SAMPLES,
                    "parallelism": f"ray-sharded dp{world}, one NCCL all-reduce of the flat fp32 gradient per step",
-                   "l2": "each step streams ~23 GB of saved activations / gradient tiles (>> 126 MB L2); no flush needed",
-                   "step": "weight repack, sampling, fused MLP fwd, compositing, losses, adjoints, dgrad, wgrad"
+                   "l2": "each step streams ~30 GB of saved activations / gradient tiles through HBM (>> 126 MB L2); no flush needed",
+                   "step": "weight repack, sampling, fused MLP fwd (CTA pairs), compositing, losses, adjoints, dgrad, wgrad"
                            + (", gradient all-reduce" if world > 1 else "")},
         "gpu_launches": launches * a.steps,
         "loss": {"color": loss_vals[0], "depth": loss_vals[1], "semantic": loss_vals[2]},

@@ -40,42 +40,63 @@ __device__ __forceinline__ float dsin(float y, uint32_t sb, int k) {
   return __uint_as_float(__float_as_uint(c) ^ ((sb >> k) << 31));
 }
 
-// G[j] = acc[j] * dact(j) for columns [j0, j0+ncols) of a chunk at TMEM address taddr;
+// One 16-column batch of a saved sine layer for this thread's row: outputs y (fp16) and derivative signs.
+// The epilogue reads them straight from global memory (HBM latency), so every batch is requested one
+// batch ahead and the first one before the wait for the MMA phase.  (16 columns, not 32: two batches
+// in flight next to the accumulator registers must fit the 96-register budget of 640-thread CTAs.)
+struct YBatch { uint4 y[2]; uint32_t sb; };
+__device__ __forceinline__ YBatch ybatch_load(const uint8_t* ysave, const uint8_t* ssave, int jb, int row) {
+  YBatch b;
+  b.y[0] = ldg16(ysave + xsave_off(jb, row));
+  b.y[1] = ldg16(ysave + xsave_off(jb + 8, row));
+  b.sb = __ldg(reinterpret_cast<const uint32_t*>(ssave + sbit_off(jb, row))) >> (jb & 16);
+  return b;
+}
+
+// A window of kYWin batches per thread is kept in flight (Little: ~64 KB per SM must be outstanding
+// to stream a 128 KB activation tile from HBM in a few microseconds; one batch per thread gave 12 GB/s).
+constexpr int kYWin = 4;
+struct YWindow { YBatch b[kYWin]; };
+__device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, const uint8_t* ssave, int j0, int row) {
+#pragma unroll
+  for (int i = 0; i < kYWin; ++i) w.b[i] = ybatch_load(ysave, ssave, j0 + 16 * i, row);
+}
+
+// G[j] = acc[j] * dact(j) for columns [j0, j0 + 16 NB) of a chunk at TMEM address taddr;
 // MODE 0: dact = cos(x) rebuilt from (ysave, ssave)     MODE 1: dact = 30 cos(30 x), same     MODE 2: dact = 1
 // result -> fp16 -> shared slab at column dst_col0 + j (copied to the gradient save area afterwards)
-template <int MODE>
-__device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, int ncols, const uint8_t* ysave, const uint8_t* ssave,
-                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave = nullptr) {
-#pragma unroll 1
-  for (int jb = j0; jb < j0 + ncols; jb += 32) {
-    uint4 yr[4];
-    uint32_t sb = 0;
-    if (MODE != 2) {
+// `win`: batches j0 .. j0 + 16 kYWin, loaded by the caller before it waited for the accumulator
+template <int MODE, int NB>
+__device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_t* ysave, const uint8_t* ssave,
+                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave, YWindow& win, int nb_run = NB) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) yr[c] = ldg16(ysave + xsave_off(jb + c * 8, row));
-      sb = __ldg(reinterpret_cast<const uint32_t*>(ssave + sbit_off(jb, row)));
-    }
-    uint32_t v[32];
-    tmem_ld32(taddr + jb, v);
-    tmem_wait_ld();
+  for (int b = 0; b < NB; ++b) {
+    if (b < nb_run) {
+      const int jb = j0 + 16 * b;
+      const YBatch cur = win.b[b % kYWin];
+      if (MODE != 2 && b + kYWin < NB) win.b[b % kYWin] = ybatch_load(ysave, ssave, jb + 16 * kYWin, row);
+      uint32_t v[16];
+      tmem_ld16(taddr + jb, v);
+      tmem_wait_ld();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float g[8];
-      if (MODE != 2) {
-        float y[8];
-        unpack8(yr[c], y);
+      for (int c = 0; c < 2; ++c) {
+        float g[8];
+        if (MODE != 2) {
+          float y[8];
+          unpack8(cur.y[c], y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float d = dsin(y[e], sb, c * 8 + e);
-          g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? d : 30.f * d);
+          for (int e = 0; e < 8; ++e) {
+            const float d = dsin(y[e], cur.sb, c * 8 + e);
+            g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? d : 30.f * d);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
+        const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+        *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
+        if (gsave) stg16(gsave + xsave_off(jb + c * 8, row), gp);
       }
-      const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
-      *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
-      if (gsave) stg16(gsave + xsave_off(jb + c * 8, row), gp);
     }
   }
 }
@@ -214,13 +235,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       sync.end(true);
       copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[2]));
       // ---- after sun_v_net.4^T: G_s2 ----
+      YWindow win;
+      ywin_load(win, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), cg * 64, row);
       sync.begin();
-      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row);
+      bwd_columns<0, 4>(taddr, cg * 64, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
       sync.end(true);
       copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[1]));
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
+      ywin_load(win, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), cg * 64, row);
       sync.begin();
-      bwd_columns<0>(taddr, cg * 64, 64, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row);
+      bwd_columns<0, 4>(taddr, cg * 64, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
       {
         const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
         gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * 64, 64,
@@ -249,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       }
       // ---- g_f (linear) -> slabs 0..7 ----
       sync.begin();
-      bwd_columns<2>(taddr, cg * 128, wide_cols, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr);
+      bwd_columns<2, 8>(taddr, cg * 128, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr, win, wide_cols / 16);
       sync.end(true);
       copy_slabs_out(act, 4, 4, gs(p.gm.g_f + 4));
       // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
@@ -292,11 +316,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         if (signal) sync.end(true);
       };
       for (int L = 7; L >= 0; --L) {
+        ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
         sync.begin();
         // half of the gradient tile leaves from registers now, half from shared memory during the next MMAs
         uint8_t* gdirect = cg < 2 ? gs(p.gm.G[L]) : nullptr;
-        if (L > 0) bwd_columns<0>(taddr, cg * 128, wide_cols, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect);
-        else       bwd_columns<1>(taddr, cg * 128, wide_cols, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect);
+        if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else       bwd_columns<1, 8>(taddr, cg * 128, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
         copy_slabs_out(act, 4, 4, gs(p.gm.G[L] + 4));

@@ -269,8 +269,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           c3[0] = fmaf(w.x, y, c3[0]); c3[1] = fmaf(w.y, y, c3[1]); c3[2] = fmaf(w.z, y, c3[2]);
         };
         if (!p.beta) {
-          // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs 0..3
-          epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
+          // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
+          // 0..3, the albedo activations are staged in slabs 4..7; both leave during the next MMA phase
+          epi_cols<0, true>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), nullptr, rgb_each);
           epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), nullptr, NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
@@ -295,6 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         sync.end(true);
       }
       copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[0]));
+      if (!p.beta) copy_slabs_out(act, 4, 4, sv(p.sm.rgb_y));
       // ---- sun layer 1 ----
       sync.begin();
       epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[1]), nullptr, NoEach());

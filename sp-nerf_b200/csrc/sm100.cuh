@@ -152,6 +152,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// Register re-balancing between warpgroups (4 consecutive warps): the producer / issuer warps need
+// few registers, the epilogue warps are pressed against the 65536 / 640 = 96 launch limit.
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // One lane of a fully converged warp.  The single-thread instructions (tcgen05.mma / commit, bulk
 // copies) are issued under this predicate while the surrounding loop stays warp-uniform, so their
 // operands live in uniform registers instead of being broadcast lane by lane.

@@ -46,7 +46,7 @@ def fused_step(model, args, batch, lambda_ds=1.0, lambda_ss=1.0, use_all_depth=F
     launches = 0
     t.mark("start")
     eng.ensure_packed(force=repack)            # parameters change every optimiser step
-    launches += 3 if repack else 0
+    launches += 4 if repack else 0          # two weight packers, small-parameter copy, aux-tile packer
     t.mark("pack")
     u = torch.rand(b, n, dtype=torch.float32, device=rays.device)
     z = E.sample_coarse(rays, u, n)
