@@ -241,7 +241,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = 0.f;
         const bool wide = p.n_classes > 4;
-        epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sem_x), sv(p.sm.sem_y), [&](int j, float y) {
+        epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, (p.debug & 32) ? nullptr : sv(p.sm.sem_x),
+                           (p.debug & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
           const float4 w = Wsem2[j * 2];
           lg[0] = fmaf(w.x, y, lg[0]); lg[1] = fmaf(w.y, y, lg[1]); lg[2] = fmaf(w.z, y, lg[2]); lg[3] = fmaf(w.w, y, lg[3]);
           if (wide) {

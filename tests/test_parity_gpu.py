@@ -323,3 +323,46 @@ def test_full_size_training_step_properties():
         assert bool(torch.isfinite(a).all())
         assert float((a - bb).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12     # atomics reorder a few sums
         assert float((c - 8 * a).abs().max()) <= 1e-4 * float((8 * a).abs().max()) + 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# CTA-pair tiling: an odd number of 128-point tiles leaves the second CTA of the last pair a phantom
+# tile; the gradients of a batch must equal the sum of the gradients of its two halves (additivity
+# over rays: every tile, job slice and column-sum path contributes exactly once)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_rays", [10, 98])          # 5 and 49 tiles of 128 points (64 samples per ray)
+def test_odd_tile_count_and_gradient_additivity(n_rays):
+    cfg = O.make_cfg(sem=True, num_sem_classes=3)
+    args = types.SimpleNamespace(**vars(cfg))
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    model = model.to(DEV)
+    batch = synthetic.make_batch(n_rays, seed=33, device=DEV)
+    gen = torch.Generator().manual_seed(5)
+    u = torch.rand(n_rays, cfg.n_samples, generator=gen)
+
+    class Rng:                                           # same jitter for the full batch and its halves
+        def __init__(self, lo, hi): self.lo, self.hi = lo, hi
+        def uniform(self, shape): return u[self.lo:self.hi]
+        def normal(self, shape): return torch.zeros(shape)
+
+    def grads(lo, hi):
+        a = types.SimpleNamespace(**vars(cfg))
+        a._rng = Rng(lo, hi)
+        res = render_rays({"coarse": model}, a, batch["rays"][lo:hi], None, semantics=batch["sems"][lo:hi], mode="test")
+        # sums (not means) so that the halves add up
+        loss = ((res["rgb_coarse"] - batch["rgbs"][lo:hi]) ** 2).sum() + res["depth_coarse"].sum() \
+            + (res["sem_logits_coarse"] ** 2).sum()
+        return res, torch.autograd.grad(loss, list(model.parameters()))
+
+    res, g_all = grads(0, n_rays)
+    half = n_rays // 2 + 1                               # uneven split: both halves ragged
+    _, g_a = grads(0, half)
+    _, g_b = grads(half, n_rays)
+    assert bool(torch.isfinite(res["rgb_coarse"]).all())
+    for (name, _), ga, gb, gt in zip(model.named_parameters(), g_a, g_b, g_all):
+        ref = float(gt.abs().max())
+        assert float((ga + gb - gt).abs().max()) <= 4e-3 * ref + 1e-9, name     # fp16 gradient tiles, different scales
