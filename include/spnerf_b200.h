@@ -66,9 +66,12 @@ int spnerf_selftest_umma(const SpnerfUmmaSelftest* args, void* stream);
  * each), b_img the two halves of the B rows (b_bytes each), idesc says M = 256, d_out is [256][n]. */
 int spnerf_selftest_umma2(const SpnerfUmmaSelftest* args, void* stream);
 /* Profiling aid: when non-NULL, the next spnerf_mlp_fwd / spnerf_mlp_bwd_data launches log clock64()
- * stamps of CTA 0's epilogue phases into dev_buf512 (512 int64, device memory). NULL disables. */
-void spnerf_debug_phase_clocks_fwd(long long* dev_buf512);
-void spnerf_debug_phase_clocks_bwd(long long* dev_buf512);
+ * stamps of CTA 0 into dev_buf2048 (2048 int64, device memory): [0,256) epilogue phase stamps,
+ * [256,262) issuer wait sums, and for the third tile pair per step i < 256: [512+i] producer saw the
+ * ring stage empty, [768+i] issuer passed the epilogue gate, [1024+i] issuer saw the stage full,
+ * [1280+i] commit issued; [1536,1792) epilogue half-way stamps.  NULL disables. */
+void spnerf_debug_phase_clocks_fwd(long long* dev_buf2048);
+void spnerf_debug_phase_clocks_bwd(long long* dev_buf2048);
 
 /* ---------------------------------------------------------------------------------------------
  * Point network (replaces models/spnerf.py:162-369 SPNeRF.__init__/forward as executed through
@@ -115,6 +118,9 @@ typedef struct SpnerfNetSizes {
 
 /* host only; no device work */
 int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* sizes_host);
+/* Debug aid (host only): the MMA step list of the forward (backward = 0) or backward-data (1) kernel as
+ * 8 int32 per step [n, tmem_col, a_slab, ksteps, first, last, issuer lane, early]; returns the step count. */
+int spnerf_debug_step_table(const SpnerfNetConfig* cfg, int backward, int32_t* out, int max_steps);
 
 /* Packing the fp32 parameters into tensor-core operands, in two steps:
  *  spnerf_net_prepare  once per (configuration, parameter pointers, buffers): uploads the pack
