@@ -390,6 +390,269 @@ __global__ void composite_bwd_kernel(const BwdP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Specialised kernels for the shapes the renderer actually runs (n = 8 * 32 / G samples, i.e. 64 at
+// G = 4 and 128 at G = 2, and the network's four row widths): the same work split and ring as the
+// generic kernels above, with every loop bound, row width and column index a compile-time constant,
+// so the per-sample shared-memory reads use immediate offsets and all per-lane state stays in
+// registers.  The generic kernels spent ~200 instructions per sample (runtime-indexed accumulators in
+// local memory, address arithmetic) and were issue/latency bound at 12 % occupancy.
+// ------------------------------------------------------------------------------------------------
+template <int G, int NO, int NS>
+__global__ void __launch_bounds__(128) composite_fwd_fast(const FwdP p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int LPR = 32 / G, N = LPR * 8, ROW = N * NO + kSkew, BUF = G * (ROW + N), CS = NO - NS;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  float* base = sm + (size_t)wib * (2 * BUF + G * N + 4);
+  float* wstage = base + 2 * BUF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wstage + G * N);
+  const int64_t warp0 = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
+  const int64_t n_groups = (p.n_rays + G - 1) / G;
+  auto prefetch = [&](int64_t g, int slot) {
+    const int64_t r0 = g * G;
+    const uint32_t cnt = (uint32_t)min((int64_t)G, p.n_rays - r0);
+    constexpr uint32_t row_bytes = (uint32_t)(N * NO) * 4u;
+    mbar_expect_tx(&bars[slot], cnt * (row_bytes + N * 4u));
+    for (uint32_t q = 0; q < cnt; ++q)
+      bulk_g2s(base + slot * BUF + q * ROW, p.out + (r0 + q) * (N * NO), row_bytes, &bars[slot]);
+    bulk_g2s(base + slot * BUF + G * ROW, p.z + r0 * N, cnt * N * 4u, &bars[slot]);
+  };
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_mbar_init();
+    if (warp0 < n_groups) prefetch(warp0, 0);
+  }
+  __syncwarp();
+  int t = 0;
+  for (int64_t g = warp0; g < n_groups; g += nw, ++t) {
+    float* slot = base + (t & 1) * BUF;
+    const int64_t r0 = g * G;
+    const int cnt = (int)min((int64_t)G, p.n_rays - r0);
+    const int64_t r = r0 + sub;
+    const bool active = sub < cnt;
+    const float* o = slot + sub * ROW + sl * NO;            // row of sample sl; sample sl + LPR k is LPR k NO floats on
+    float* zs = slot + G * ROW + sub * N + sl;              // depths, overwritten by T
+    float* ws = wstage + sub * N + sl;
+    if (lane == 0 && g + nw < n_groups) prefetch(g + nw, (t + 1) & 1);
+    mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u, 50);
+    float alpha[8], keep[8], zv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      zv[k] = zs[LPR * k];
+      float delta = zs[LPR * k + 1] - zv[k];                // the word after the ray's last depth is never used:
+      if (k == 7 && sl == LPR - 1) delta = 1e10f;           // spnerf.py:116-118
+      float s = o[LPR * k * NO + 3];
+      if (p.noise && active) s += p.noise[r * N + sl + LPR * k] * p.noise_std;          // :121-122
+      alpha[k] = 1.f - __expf(-delta * fmaxf(s, 0.f));                                   // :123
+      keep[k] = 1.f - alpha[k] + 1e-10f;                                                 // :126
+    }
+    float acc_d = 0.f, acc_c[3] = {0.f, 0.f, 0.f}, acc_s[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc_s[c] = 0.f;
+    float carry = 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float ex, tot;
+      seg_scan_mul<LPR>(keep[k], sl, ex, tot);              // :127 (exclusive cumprod), one round of LPR samples
+      const float T = carry * ex;
+      const float w = alpha[k] * T;                                                      // :128
+      const float* ok = o + LPR * k * NO;
+      const float sv = ok[4];
+      acc_d = fmaf(w, zv[k], acc_d);                                                     // :131
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc_c[c] = fmaf(w * ok[c], sv + (1.f - sv) * ok[5 + c], acc_c[c]);   // :132-133
+#pragma unroll
+      for (int c = 0; c < NS; ++c) acc_s[c] += ok[CS + c];
+      ws[LPR * k] = w;
+      zs[LPR * k] = T;      // every depth difference was formed in the first loop (the scans order the loops)
+      carry *= tot;
+    }
+    fence_proxy_async_smem();     // see the generic kernel
+    __syncwarp();
+    if (cnt == G) {
+      const float4* w4 = reinterpret_cast<const float4*>(wstage);
+      const float4* t4 = reinterpret_cast<const float4*>(slot + G * ROW);
+      float4* gw = reinterpret_cast<float4*>(p.weights + r0 * N);
+      float4* gt = reinterpret_cast<float4*>(p.trans + r0 * N);
+#pragma unroll
+      for (int i = 0; i < G * N / 128; ++i) {
+        __stcs(gw + lane + 32 * i, w4[lane + 32 * i]);
+        __stcs(gt + lane + 32 * i, t4[lane + 32 * i]);
+      }
+    } else {
+      warp_store(p.weights + r0 * N, wstage, cnt * N, lane);
+      warp_store(p.trans + r0 * N, slot + G * ROW, cnt * N, lane);
+    }
+    acc_d = seg_sum<LPR>(acc_d);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc_c[c] = seg_sum<LPR>(acc_c[c]);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc_s[c] = seg_sum<LPR>(acc_s[c]);
+    if (sl == 0 && active) {
+      p.depth[r] = acc_d;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (p.rgb_raw) p.rgb_raw[r * 3 + c] = acc_c[c];
+        p.rgb[r * 3 + c] = fminf(fmaxf(acc_c[c], 0.f), 1.f);                             // :134
+      }
+#pragma unroll
+      for (int c = 0; c < NS; ++c) p.sem[r * NS + c] = acc_s[c] / (float)N;              // :156 (plain mean)
+    }
+    __syncwarp();
+  }
+}
+
+template <int G, int NO, int NS, bool EXT>
+__global__ void __launch_bounds__(64) composite_bwd_fast(const BwdP p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int LPR = 32 / G, N = LPR * 8, ROW = N * NO + kSkew, EXTF = EXT ? ROW : 0, CS = NO - NS;
+  constexpr int BUF = G * (ROW + EXTF + 3 * N);             // rows | external gradient rows | z | w | T
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  float* base = sm + (size_t)wib * (2 * BUF + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * BUF);
+  const int64_t warp0 = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
+  const int64_t n_groups = (p.n_rays + G - 1) / G;
+  auto prefetch = [&](int64_t g, int slot) {
+    const int64_t r0 = g * G;
+    const uint32_t cnt = (uint32_t)min((int64_t)G, p.n_rays - r0);
+    constexpr uint32_t row_bytes = (uint32_t)(N * NO) * 4u;
+    const uint32_t z_bytes = cnt * N * 4u;
+    float* b = base + slot * BUF;
+    mbar_expect_tx(&bars[slot], cnt * row_bytes * (EXT ? 2u : 1u) + 3u * z_bytes);
+    for (uint32_t q = 0; q < cnt; ++q) {
+      bulk_g2s(b + q * ROW, p.out + (r0 + q) * (N * NO), row_bytes, &bars[slot]);
+      if (EXT) bulk_g2s(b + (G + q) * ROW, p.g_out_ext + (r0 + q) * (N * NO), row_bytes, &bars[slot]);
+    }
+    float* zb = b + G * (ROW + EXTF);
+    bulk_g2s(zb, p.z + r0 * N, z_bytes, &bars[slot]);
+    bulk_g2s(zb + G * N, p.weights + r0 * N, z_bytes, &bars[slot]);
+    bulk_g2s(zb + 2 * G * N, p.trans + r0 * N, z_bytes, &bars[slot]);
+  };
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_mbar_init();
+    if (warp0 < n_groups) prefetch(warp0, 0);
+  }
+  __syncwarp();
+  float amax = 0.f;
+  int t = 0;
+  for (int64_t g = warp0; g < n_groups; g += nw, ++t) {
+    float m = 0.f;                                          // max |gradient| of this step (dropped for padding rays)
+    float* slot = base + (t & 1) * BUF;
+    const int64_t r0 = g * G;
+    const int cnt = (int)min((int64_t)G, p.n_rays - r0);
+    const int64_t r = r0 + sub;
+    const bool active = sub < cnt;
+    float* o = slot + sub * ROW + sl * NO;                  // network row of sample sl, overwritten by its gradient
+    const float* e_row = slot + G * ROW + sub * ROW + sl * NO;
+    const float* zs = slot + G * (ROW + EXTF) + sub * N + sl;
+    const float* ws = zs + G * N;
+    const float* ts = ws + G * N;
+    if (lane == 0 && g + nw < n_groups) prefetch(g + nw, (t + 1) & 1);
+    float gh[3] = {0.f, 0.f, 0.f};
+    if (p.g_rgb && active) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float raw = p.rgb_raw[r * 3 + c];
+        gh[c] = (raw >= 0.f && raw <= 1.f) ? p.g_rgb[r * 3 + c] : 0.f;                   // clamp adjoint
+      }
+    }
+    const float gd = (p.g_depth && active) ? p.g_depth[r] : 0.f;
+    float gsem[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) gsem[c] = (p.g_sem && active) ? p.g_sem[r * NS + c] / (float)N : 0.f;
+    mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u, 51);
+    float Gd[8], Sv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float* ok = o + LPR * k * NO;
+      const float sv = ok[4];
+      float gg = gd * zs[LPR * k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gg = fmaf(ok[c] * (sv + (1.f - sv) * ok[5 + c]), gh[c], gg);
+      if (p.g_w && active) gg += p.g_w[r * N + sl + LPR * k];
+      Gd[k] = gg;                                                                        // dL/dw_i
+      Sv[k] = gg * ws[LPR * k] + ((p.g_t && active) ? p.g_t[r * N + sl + LPR * k] * ts[LPR * k] : 0.f);
+    }
+    float gsky[3] = {0.f, 0.f, 0.f};
+    float carry = 0.f;                                       // sum of S over the samples of later rounds
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      float ex, tot;
+      seg_suffix_sum<LPR>(Sv[k], sl, ex, tot);
+      const float R = carry + ex;
+      float* ok = o + LPR * k * NO;
+      const float w = ws[LPR * k], T = ts[LPR * k];
+      float delta = zs[LPR * k + 1] - zs[LPR * k];
+      if (k == 7 && sl == LPR - 1) delta = 1e10f;
+      float s = ok[3];
+      if (p.noise && active) s += p.noise[r * N + sl + LPR * k] * p.noise_std;
+      const float e = __expf(-delta * fmaxf(s, 0.f));           // 1 - alpha
+      const float dalpha = Gd[k] * T - __fdividef(R, e + 1e-10f);
+      const float dsigma = (s > 0.f) ? dalpha * delta * e : 0.f;
+      const float sv = ok[4];
+      float go[8];
+      float dsv = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float sky = ok[5 + c];
+        const float irr = sv + (1.f - sv) * sky;
+        go[c] = w * irr * gh[c];                                // d albedo
+        const float dirr = w * ok[c] * gh[c];
+        dsv = fmaf(dirr, 1.f - sky, dsv);
+        go[5 + c] = dirr * (1.f - sv);                          // d sky
+      }
+      go[3] = dsigma;
+      go[4] = dsv;
+      const float* ek = e_row + LPR * k * NO;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float v = go[c] + (EXT ? ek[c] : 0.f);
+        ok[c] = v;
+        m = fmaxf(m, fabsf(v));
+        if (c >= 5) gsky[c - 5] += v;
+      }
+#pragma unroll
+      for (int c = 8; c < NO; ++c) {
+        float v = EXT ? ek[c] : 0.f;
+        if (c >= CS) v += gsem[c - CS < 0 ? 0 : c - CS];
+        ok[c] = v;
+        m = fmaxf(m, fabsf(v));
+      }
+      carry += tot;
+    }
+    if (active) amax = fmaxf(amax, m);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (cnt == G) {
+      // the G gradient rows are ROW floats apart in shared memory, contiguous in global memory
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        const float4* s4 = reinterpret_cast<const float4*>(slot + q * ROW);
+        float4* d4 = reinterpret_cast<float4*>(p.g_out + (r0 + q) * (N * NO));
+#pragma unroll
+        for (int i = 0; i < (N * NO / 4 + 31) / 32; ++i)
+          if (lane + 32 * i < N * NO / 4) __stcs(d4 + lane + 32 * i, s4[lane + 32 * i]);
+      }
+    } else {
+      for (int q = 0; q < cnt; ++q) warp_store(p.g_out + (r0 + q) * (N * NO), slot + q * ROW, N * NO, lane);
+    }
+    if (p.g_sky_ray) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gsky[c] = seg_sum<LPR>(gsky[c]);
+      if (sl < 3 && active) p.g_sky_ray[r * 3 + sl] = sl == 0 ? gsky[0] : sl == 1 ? gsky[1] : gsky[2];
+    }
+    __syncwarp();
+  }
+  if (p.absmax_bits) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+    if (lane == 0 && amax > 0.f) atomicMax(p.absmax_bits, __float_as_uint(amax));   // positive floats order as uints
+  }
+}
+
 // grid = the blocks that are resident at once (shared memory bound), each warp strides over ray groups
 template <class K, class P>
 int launch(K kern, const P& p, int64_t n_groups, int wpb, size_t smem, cudaStream_t stream, size_t* configured) {
@@ -439,6 +702,16 @@ extern "C" int spnerf_composite_fwd(const SpnerfCompositeFwd* a, void* stream) {
   const size_t smem = (size_t)wpb * ((G > 1 ? 2 : 1) * G * (rf + p.n) + G * p.n + 4) * sizeof(float);
   static size_t cfg[3] = {0, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G > 1 && p.n == 8 * (32 / G) && al16(p.weights) && al16(p.trans) && (p.n_sem == 0 || p.col_sem == p.n_out - p.n_sem)) {
+    static size_t fcfg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t ng = (p.n_rays + G - 1) / G;
+#define SPNERF_FWD_FAST(g_, no_, ns_, slot_)                                                        \
+    if (G == g_ && p.n_out == no_ && p.n_sem == ns_)                                                \
+      return launch(composite_fwd_fast<g_, no_, ns_>, p, ng, wpb, smem, st, &fcfg[slot_]);
+    SPNERF_FWD_FAST(4, 11, 3, 0) SPNERF_FWD_FAST(4, 8, 0, 1) SPNERF_FWD_FAST(4, 9, 0, 2) SPNERF_FWD_FAST(4, 12, 3, 3)
+    SPNERF_FWD_FAST(2, 11, 3, 4) SPNERF_FWD_FAST(2, 8, 0, 5) SPNERF_FWD_FAST(2, 9, 0, 6) SPNERF_FWD_FAST(2, 12, 3, 7)
+#undef SPNERF_FWD_FAST
+  }
   if (G == 4) return launch(composite_fwd_kernel<4>, p, (p.n_rays + 3) / 4, wpb, smem, st, &cfg[0]);
   if (G == 2) return launch(composite_fwd_kernel<2>, p, (p.n_rays + 1) / 2, wpb, smem, st, &cfg[1]);
   return launch(composite_fwd_kernel<1>, p, p.n_rays, wpb, smem, st, &cfg[2]);
@@ -466,6 +739,18 @@ extern "C" int spnerf_composite_bwd(const SpnerfCompositeBwd* a, void* stream) {
   const size_t smem = (size_t)wpb * ((G > 1 ? 2 : 1) * G * slot_f + 4) * sizeof(float);
   static size_t cfg[3] = {0, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G > 1 && p.n == 8 * (32 / G) && al16(p.g_out) && (p.n_sem == 0 || p.col_sem == p.n_out - p.n_sem)) {
+    static size_t fcfg[16] = {0};
+    const int64_t ng = (p.n_rays + G - 1) / G;
+#define SPNERF_BWD_FAST(g_, no_, ns_, slot_)                                                        \
+    if (G == g_ && p.n_out == no_ && p.n_sem == ns_) {                                              \
+      if (p.g_out_ext) return launch(composite_bwd_fast<g_, no_, ns_, true>, p, ng, wpb, smem, st, &fcfg[2 * slot_]);      \
+      return launch(composite_bwd_fast<g_, no_, ns_, false>, p, ng, wpb, smem, st, &fcfg[2 * slot_ + 1]);                  \
+    }
+    SPNERF_BWD_FAST(4, 11, 3, 0) SPNERF_BWD_FAST(4, 8, 0, 1) SPNERF_BWD_FAST(4, 9, 0, 2) SPNERF_BWD_FAST(4, 12, 3, 3)
+    SPNERF_BWD_FAST(2, 11, 3, 4) SPNERF_BWD_FAST(2, 8, 0, 5) SPNERF_BWD_FAST(2, 9, 0, 6) SPNERF_BWD_FAST(2, 12, 3, 7)
+#undef SPNERF_BWD_FAST
+  }
   if (G == 4) return launch(composite_bwd_kernel<4>, p, (p.n_rays + 3) / 4, wpb, smem, st, &cfg[0]);
   if (G == 2) return launch(composite_bwd_kernel<2>, p, (p.n_rays + 1) / 2, wpb, smem, st, &cfg[1]);
   return launch(composite_bwd_kernel<1>, p, p.n_rays, wpb, smem, st, &cfg[2]);
