@@ -316,6 +316,89 @@ def run_ours(a):
                        "d2h_bytes_per_step": 4, "ms_per_step": dt / n_e2e * 1e3,
                        "api": "render_rays + SNerfLoss + DepthLoss + SemanticLoss + loss.backward()"}
 
+    # ---- the other BASELINE configurations, through the public API (extra objects; the headline stays C2) ----
+    if not a.skip_extra:
+        from spnerf_b200 import inference
+        other = {}
+        # C3: --guidedsample --mapping training step, 16384 rays per GPU (64-sample pass + 128-sample pass)
+        from oracle import spnerf_oracle as O3     # configuration container only
+        args3 = types.SimpleNamespace(**vars(O3.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES,
+                                                         mapping=True, guidedsample=True, chunk=16384)))
+        model3 = build_model(args3, dev)
+        b3 = {k: v.to(dev) for k, v in synthetic.make_batch(16384, seed=300 + rank).items()}
+        loss_fn, dl, sl = metrics.SNerfLoss(0.0), metrics.DepthLoss(1.0, usealldepth=False), metrics.SemanticLoss(1.0)
+
+        def c3_step():
+            res = render_rays({"coarse": model3}, args3, b3["rays"], None, semantics=b3["sems"], mode="train",
+                              valid_depth=b3["valid_depth"], target_depths=b3["depths"], target_std=b3["depth_std"])
+            loss = loss_fn(res, b3["rgbs"])[0] + dl(res, b3["depths"][:, 0], b3["depths"][:, 1],
+                                                    target_valid_depth=b3["valid_depth"],
+                                                    target_std=b3["depth_std"])[0] + sl(res, b3["sems"])[0]
+            for p_ in model3.parameters():
+                p_.grad = None
+            loss.backward()
+            if world > 1:
+                gl = [p_.grad for p_ in model3.parameters()]
+                flat = torch._utils._flatten_dense_tensors(gl)
+                parallel.allreduce_mean_(flat)
+            return loss
+        for _ in range(2):
+            c3_step()
+        barrier()
+        e0.record()
+        n3 = 3
+        for _ in range(n3):
+            c3_step()
+        e1.record()
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1) / n3], device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        flop3 = 16384 * (64 * 5381120 + 128 * 16011264)          # pass 1 forward only + pass 2 fwd+bwd
+        other["c3_train_guided_mapping"] = {
+            "workload": "BASELINE config 3: training step with --guidedsample --mapping (+ --depth --sem), 16384 rays "
+                        "per GPU, render_rays + losses + backward through the public API, inputs on the device",
+            "rays_per_s": world * 16384 / (float(ms3) / 1e3), "ms_per_step": float(ms3), "steps": n3,
+            "mlp_tflops_lower_bound": flop3 / (float(ms3) * 1e-3) / 1e12,
+            "frac_of_sustained_tensor_peak_lower_bound": flop3 / (float(ms3) * 1e-3) / 1e12 / pk["tc_sustained"]}
+        del model3, b3
+        torch.cuda.empty_cache()
+        # C4: full-image inference (2048 x 2048 rays), rows split across the ranks, per-ray outputs gathered on rank 0
+        side = 2048
+        n_img = side * side
+        lo, hi = parallel.shard_bounds(n_img, rank, world)
+        img_rays = synthetic.make_batch(hi - lo, seed=400 + rank)
+        rays4 = img_rays["rays"].to(dev)
+        sems4 = img_rays["sems"].to(dev)
+        args.chunk = 262144
+
+        def c4_render(n_local):
+            local_ = inference.render_image({"coarse": model}, args, rays4[:n_local], None, semantics=sems4[:n_local])
+            out_ = {}
+            if world > 1:
+                for k_ in sorted(local_):
+                    out_[k_] = parallel.gather_rays(local_[k_], n_local * world, dst=0)
+            return local_, out_
+        c4_render(262144 // world)                   # warm-up on one chunk per job
+        barrier()
+        e0.record()
+        c4_render(hi - lo)
+        e1.record()
+        barrier()
+        ms4 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        flop4 = n_img * N_SAMPLES * FLOP_FWD
+        other["c4_full_image_inference"] = {
+            "workload": f"BASELINE config 4: {side}x{side} rays x 64 samples forward, rows sharded over {world} GPU(s), "
+                        "chunks of 262144 rays, per-ray rgb/depth/logits/class + composited albedo/sun/sky gathered on rank 0",
+            "rays_per_s": n_img / (float(ms4) / 1e3), "seconds_per_image": float(ms4) / 1e3, "scaling": "strong",
+            "mlp_tflops_lower_bound": flop4 / (float(ms4) * 1e-3) / 1e12 / world,
+            "frac_of_sustained_tensor_peak_lower_bound": flop4 / (float(ms4) * 1e-3) / 1e12 / world / pk["tc_sustained"],
+            "d2h_bytes_per_ray_if_exported": 64}
+        line["other_configs"] = other
+        del rays4, sems4
+
     if rank == 0 and world == 1:
         # ---- the reference's CPU path on this box's host cores (bounded sample) ----
         try:
@@ -337,6 +420,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-extra", action="store_true", help="only the headline (C2) workload: no C3 / C4 objects")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -233,12 +233,20 @@ typedef struct SpnerfCompositeFwd {
   int32_t col_sem, n_sem;    /* first logit column / number of classes (0: no semantic head)      */
   float noise_std;
   int32_t _pad;
-  float* weights;            /* (n_rays, n_samples)  alpha_i * T_i                                */
-  float* transparency;       /* (n_rays, n_samples)  T_i                                          */
+  float* weights;            /* (n_rays, n_samples)  alpha_i * T_i, or NULL (image export: not needed) */
+  float* transparency;       /* (n_rays, n_samples)  T_i, or NULL                                 */
   float* rgb;                /* (n_rays, 3) clamped to [0,1]                                      */
   float* rgb_raw;            /* (n_rays, 3) before the clamp, or NULL (needed by the backward)    */
   float* depth;              /* (n_rays)                                                          */
   float* sem_logits;         /* (n_rays, n_sem): plain mean over samples (spnerf.py:156)          */
+  /* Per-ray composited auxiliaries for image export (replaces the (B,N,k) tensors main.py:75-76 ships to
+   * the host and the sums eval.py:75-101 forms there), both optional:
+   *   ray_aux (n_rays, 8) = [sum_i w_i albedo_i (3), sum_i w_i sun_i, sum_i w_i sky_i (3), sum_i w_i beta_i]
+   *   sem_argmax (n_rays) = argmax over classes of sem_logits, first maximum (eval.py:63, main.py:228) */
+  float* ray_aux;
+  int32_t* sem_argmax;
+  int32_t col_beta;          /* beta column of `out`, or -1                                        */
+  int32_t _pad2;
 } SpnerfCompositeFwd;
 int spnerf_composite_fwd(const SpnerfCompositeFwd* args, void* stream);
 

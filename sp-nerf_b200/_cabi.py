@@ -139,7 +139,7 @@ class CompositeFwd(ctypes.Structure):
     _fields_ = [("out", VP), ("z", VP), ("noise", VP), ("n_rays", I64), ("n_samples", I32), ("n_out", I32),
                 ("col_sem", I32), ("n_sem", I32), ("noise_std", F32), ("_pad", I32),
                 ("weights", VP), ("transparency", VP), ("rgb", VP), ("rgb_raw", VP), ("depth", VP),
-                ("sem_logits", VP)]
+                ("sem_logits", VP), ("ray_aux", VP), ("sem_argmax", VP), ("col_beta", I32), ("_pad2", I32)]
 
 
 class CompositeBwd(ctypes.Structure):

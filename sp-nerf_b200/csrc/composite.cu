@@ -107,7 +107,19 @@ struct FwdP {
   const float* out; const float* z; const float* noise; float noise_std;
   int64_t n_rays; int n; int n_out; int col_sem; int n_sem;
   float* weights; float* trans; float* rgb; float* rgb_raw; float* depth; float* sem;
+  float* aux; int* sem_argmax; int col_beta;      // per-ray sums for image export (eval.py:75-101), optional
 };
+
+// first maximum, as torch.argmax (eval.py:63)
+template <int NS>
+__device__ __forceinline__ int argmax_first(const float (&v)[NS > 0 ? NS : 1], int n) {
+  int best = 0;
+  float bv = v[0];
+#pragma unroll
+  for (int c = 1; c < NS; ++c)
+    if (c < n && v[c] > bv) { bv = v[c]; best = c; }
+  return best;
+}
 
 template <int G>
 __global__ void composite_fwd_kernel(const FwdP p) {
@@ -177,6 +189,7 @@ __global__ void composite_fwd_kernel(const FwdP p) {
       }
     }
     float acc_d = 0.f, acc_c[3] = {0.f, 0.f, 0.f}, acc_s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc_a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // albedo(3), sun, sky(3), beta
     float carry = 1.f;                                      // product over the samples of earlier rounds
 #pragma unroll
     for (int k = 0; k < kMaxPerLane; ++k) {
@@ -193,6 +206,12 @@ __global__ void composite_fwd_kernel(const FwdP p) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) acc_c[c] = fmaf(w * o[c], sv + (1.f - sv) * o[5 + c], acc_c[c]);   // :132-133
           for (int c = 0; c < p.n_sem; ++c) acc_s[c] += o[p.col_sem + c];
+          if (p.aux) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { acc_a[c] = fmaf(w, o[c], acc_a[c]); acc_a[4 + c] = fmaf(w, o[5 + c], acc_a[4 + c]); }
+            acc_a[3] = fmaf(w, sv, acc_a[3]);
+            if (p.col_beta >= 0) acc_a[7] = fmaf(w, o[p.col_beta], acc_a[7]);
+          }
           ws[i] = w;
           zs[i] = T;   // every depth difference was formed in the first loop (the scans order the loops)
         }
@@ -204,12 +223,21 @@ __global__ void composite_fwd_kernel(const FwdP p) {
     // iteration's global stores are issued (the fence's membar would otherwise wait for them).
     if (PIPE) fence_proxy_async_smem();
     __syncwarp();
-    warp_store(p.weights + r0 * p.n, wstage, cnt * p.n, lane);
-    warp_store(p.trans + r0 * p.n, slot + G * row_f, cnt * p.n, lane);
+    if (p.weights) warp_store(p.weights + r0 * p.n, wstage, cnt * p.n, lane);
+    if (p.trans) warp_store(p.trans + r0 * p.n, slot + G * row_f, cnt * p.n, lane);
     acc_d = seg_sum<LPR>(acc_d);
 #pragma unroll
     for (int c = 0; c < 3; ++c) acc_c[c] = seg_sum<LPR>(acc_c[c]);
     for (int c = 0; c < p.n_sem; ++c) acc_s[c] = seg_sum<LPR>(acc_s[c]);
+    if (p.aux) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc_a[c] = seg_sum<LPR>(acc_a[c]);
+      if (sl == 0 && active) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p.aux[r * 8 + c] = acc_a[c];
+      }
+    }
+    if (p.sem_argmax && sl == 0 && active) p.sem_argmax[r] = argmax_first<8>(acc_s, p.n_sem);
     if (sl == 0 && active) {
       p.depth[r] = acc_d;
 #pragma unroll
@@ -398,7 +426,7 @@ __global__ void composite_bwd_kernel(const BwdP p) {
 // registers.  The generic kernels spent ~200 instructions per sample (runtime-indexed accumulators in
 // local memory, address arithmetic) and were issue/latency bound at 12 % occupancy.
 // ------------------------------------------------------------------------------------------------
-template <int G, int NO, int NS>
+template <int G, int NO, int NS, bool AUX>
 __global__ void __launch_bounds__(128) composite_fwd_fast(const FwdP p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int LPR = 32 / G, N = LPR * 8, ROW = N * NO + kSkew, BUF = G * (ROW + N), CS = NO - NS;
@@ -448,6 +476,8 @@ __global__ void __launch_bounds__(128) composite_fwd_fast(const FwdP p) {
       keep[k] = 1.f - alpha[k] + 1e-10f;                                                 // :126
     }
     float acc_d = 0.f, acc_c[3] = {0.f, 0.f, 0.f}, acc_s[NS > 0 ? NS : 1];
+    float acc_a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // albedo(3), sun, sky(3), beta
+    acc_s[0] = 0.f;
 #pragma unroll
     for (int c = 0; c < NS; ++c) acc_s[c] = 0.f;
     float carry = 1.f;
@@ -464,25 +494,42 @@ __global__ void __launch_bounds__(128) composite_fwd_fast(const FwdP p) {
       for (int c = 0; c < 3; ++c) acc_c[c] = fmaf(w * ok[c], sv + (1.f - sv) * ok[5 + c], acc_c[c]);   // :132-133
 #pragma unroll
       for (int c = 0; c < NS; ++c) acc_s[c] += ok[CS + c];
+      if (AUX) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { acc_a[c] = fmaf(w, ok[c], acc_a[c]); acc_a[4 + c] = fmaf(w, ok[5 + c], acc_a[4 + c]); }
+        acc_a[3] = fmaf(w, sv, acc_a[3]);
+        if (NO - NS == 9) acc_a[7] = fmaf(w, ok[8], acc_a[7]);      // beta column (models/spnerf.py:148-152)
+      }
       ws[LPR * k] = w;
       zs[LPR * k] = T;      // every depth difference was formed in the first loop (the scans order the loops)
       carry *= tot;
     }
     fence_proxy_async_smem();     // see the generic kernel
     __syncwarp();
-    if (cnt == G) {
-      const float4* w4 = reinterpret_cast<const float4*>(wstage);
-      const float4* t4 = reinterpret_cast<const float4*>(slot + G * ROW);
-      float4* gw = reinterpret_cast<float4*>(p.weights + r0 * N);
-      float4* gt = reinterpret_cast<float4*>(p.trans + r0 * N);
+    if (p.weights) {        // both or neither (host check)
+      if (cnt == G) {
+        const float4* w4 = reinterpret_cast<const float4*>(wstage);
+        const float4* t4 = reinterpret_cast<const float4*>(slot + G * ROW);
+        float4* gw = reinterpret_cast<float4*>(p.weights + r0 * N);
+        float4* gt = reinterpret_cast<float4*>(p.trans + r0 * N);
 #pragma unroll
-      for (int i = 0; i < G * N / 128; ++i) {
-        __stcs(gw + lane + 32 * i, w4[lane + 32 * i]);
-        __stcs(gt + lane + 32 * i, t4[lane + 32 * i]);
+        for (int i = 0; i < G * N / 128; ++i) {
+          __stcs(gw + lane + 32 * i, w4[lane + 32 * i]);
+          __stcs(gt + lane + 32 * i, t4[lane + 32 * i]);
+        }
+      } else {
+        warp_store(p.weights + r0 * N, wstage, cnt * N, lane);
+        warp_store(p.trans + r0 * N, slot + G * ROW, cnt * N, lane);
       }
-    } else {
-      warp_store(p.weights + r0 * N, wstage, cnt * N, lane);
-      warp_store(p.trans + r0 * N, slot + G * ROW, cnt * N, lane);
+    }
+    if (AUX) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc_a[c] = seg_sum<LPR>(acc_a[c]);
+      if (p.aux && sl == 0 && active) {
+        float4* a4 = reinterpret_cast<float4*>(p.aux + r * 8);
+        a4[0] = make_float4(acc_a[0], acc_a[1], acc_a[2], acc_a[3]);
+        a4[1] = make_float4(acc_a[4], acc_a[5], acc_a[6], acc_a[7]);
+      }
     }
     acc_d = seg_sum<LPR>(acc_d);
 #pragma unroll
@@ -498,6 +545,7 @@ __global__ void __launch_bounds__(128) composite_fwd_fast(const FwdP p) {
       }
 #pragma unroll
       for (int c = 0; c < NS; ++c) p.sem[r * NS + c] = acc_s[c] / (float)N;              // :156 (plain mean)
+      if (AUX && NS > 0 && p.sem_argmax) p.sem_argmax[r] = argmax_first<NS>(acc_s, NS);
     }
     __syncwarp();
   }
@@ -683,10 +731,13 @@ int pick_group(int n, int n_out, bool aligned) {
 }  // namespace
 
 extern "C" int spnerf_composite_fwd(const SpnerfCompositeFwd* a, void* stream) {
-  if (!a || !a->out || !a->z || !a->weights || !a->transparency || !a->rgb || !a->depth) return SPNERF_ERR_BAD_ARG;
+  if (!a || !a->out || !a->z || !a->rgb || !a->depth) return SPNERF_ERR_BAD_ARG;
+  if ((a->weights == nullptr) != (a->transparency == nullptr)) return SPNERF_ERR_BAD_ARG;
   if (a->n_samples < 1 || a->n_samples > 32 * kMaxPerLane || a->n_out < 8 || a->n_sem < 0 || a->n_sem > 8)
     return SPNERF_ERR_UNSUPPORTED;
   if (a->n_sem > 0 && (!a->sem_logits || a->col_sem + a->n_sem > a->n_out)) return SPNERF_ERR_BAD_ARG;
+  if (a->sem_argmax && a->n_sem == 0) return SPNERF_ERR_BAD_ARG;
+  if (a->ray_aux && (a->col_beta >= a->n_out || (a->col_beta >= 0 && a->col_beta != 8))) return SPNERF_ERR_BAD_ARG;
   if (a->n_rays <= 0) return a->n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   FwdP p;
   p.out = a->out; p.z = a->z; p.noise = (a->noise && a->noise_std != 0.f) ? a->noise : nullptr;
@@ -694,6 +745,7 @@ extern "C" int spnerf_composite_fwd(const SpnerfCompositeFwd* a, void* stream) {
   p.col_sem = a->col_sem; p.n_sem = a->n_sem;
   p.weights = a->weights; p.trans = a->transparency; p.rgb = a->rgb; p.rgb_raw = a->rgb_raw; p.depth = a->depth;
   p.sem = a->sem_logits;
+  p.aux = a->ray_aux; p.sem_argmax = a->sem_argmax; p.col_beta = a->ray_aux ? a->col_beta : -1;
   const int row_f = (p.n * p.n_out + 3) & ~3;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int G = pick_group(p.n, p.n_out, al16(p.out) && al16(p.z));
@@ -702,12 +754,17 @@ extern "C" int spnerf_composite_fwd(const SpnerfCompositeFwd* a, void* stream) {
   const size_t smem = (size_t)wpb * ((G > 1 ? 2 : 1) * G * (rf + p.n) + G * p.n + 4) * sizeof(float);
   static size_t cfg[3] = {0, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (G > 1 && p.n == 8 * (32 / G) && al16(p.weights) && al16(p.trans) && (p.n_sem == 0 || p.col_sem == p.n_out - p.n_sem)) {
-    static size_t fcfg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool beta_ok = !p.aux || ((p.col_beta == 8) == (p.n_out - p.n_sem == 9));
+  if (G > 1 && p.n == 8 * (32 / G) && al16(p.weights) && al16(p.trans) && (!p.aux || al16(p.aux)) && beta_ok &&
+      (p.n_sem == 0 || p.col_sem == p.n_out - p.n_sem)) {
+    static size_t fcfg[16] = {0};
     const int64_t ng = (p.n_rays + G - 1) / G;
+    const bool aux = p.aux || p.sem_argmax;
 #define SPNERF_FWD_FAST(g_, no_, ns_, slot_)                                                        \
-    if (G == g_ && p.n_out == no_ && p.n_sem == ns_)                                                \
-      return launch(composite_fwd_fast<g_, no_, ns_>, p, ng, wpb, smem, st, &fcfg[slot_]);
+    if (G == g_ && p.n_out == no_ && p.n_sem == ns_) {                                              \
+      if (aux) return launch(composite_fwd_fast<g_, no_, ns_, true>, p, ng, wpb, smem, st, &fcfg[2 * slot_]);      \
+      return launch(composite_fwd_fast<g_, no_, ns_, false>, p, ng, wpb, smem, st, &fcfg[2 * slot_ + 1]);          \
+    }
     SPNERF_FWD_FAST(4, 11, 3, 0) SPNERF_FWD_FAST(4, 8, 0, 1) SPNERF_FWD_FAST(4, 9, 0, 2) SPNERF_FWD_FAST(4, 12, 3, 3)
     SPNERF_FWD_FAST(2, 11, 3, 4) SPNERF_FWD_FAST(2, 8, 0, 5) SPNERF_FWD_FAST(2, 9, 0, 6) SPNERF_FWD_FAST(2, 12, 3, 7)
 #undef SPNERF_FWD_FAST

@@ -79,21 +79,29 @@ def sample_guided(rays, z, weights, depth, u_pred, valid_depth=None, target_dept
     return (z_unsort, z_sorted, inds) if want_indices else (z_unsort, z_sorted)
 
 
-def composite_fwd(out, z, n_out, col_sem, n_sem, noise=None, noise_std=0.0, want_raw=True):
-    """models/spnerf.py:109-157."""
+def composite_fwd(out, z, n_out, col_sem, n_sem, noise=None, noise_std=0.0, want_raw=True, want_samples=True,
+                  want_aux=False, col_beta=-1):
+    """models/spnerf.py:109-157.  want_samples=False skips the (B,N) weights / transparency outputs and
+    want_aux=True adds the per-ray sums of eval.py:75-101 and the class argmax (image export)."""
     b, n = z.shape
     dev = z.device
     f32 = dict(dtype=torch.float32, device=dev)
-    weights, trans = torch.empty(b, n, **f32), torch.empty(b, n, **f32)
+    weights = torch.empty(b, n, **f32) if want_samples else None
+    trans = torch.empty(b, n, **f32) if want_samples else None
     rgb, depth = torch.empty(b, 3, **f32), torch.empty(b, **f32)
     rgb_raw = torch.empty(b, 3, **f32) if want_raw else None
     sem = torch.empty(b, n_sem, **f32) if n_sem > 0 else None
+    aux = torch.empty(b, 8, **f32) if want_aux else None
+    amax = torch.empty(b, dtype=torch.int32, device=dev) if (want_aux and n_sem > 0) else None
     a = _cabi.CompositeFwd()
     a.out, a.z, a.noise = _p(out), _p(z), _p(noise)
     a.n_rays, a.n_samples, a.n_out, a.col_sem, a.n_sem, a.noise_std = b, n, n_out, max(col_sem, 0), n_sem, noise_std
     a.weights, a.transparency, a.rgb, a.rgb_raw, a.depth, a.sem_logits = \
         _p(weights), _p(trans), _p(rgb), _p(rgb_raw), _p(depth), _p(sem)
+    a.ray_aux, a.sem_argmax, a.col_beta = _p(aux), _p(amax), col_beta
     _cabi.check(_cabi.lib().spnerf_composite_fwd(ctypes.byref(a), _stream()), "spnerf_composite_fwd")
+    if want_aux:
+        return weights, trans, rgb, rgb_raw, depth, sem, aux, amax
     return weights, trans, rgb, rgb_raw, depth, sem
 
 

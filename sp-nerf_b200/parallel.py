@@ -11,6 +11,13 @@ import torch
 import torch.distributed as dist
 
 
+def rank_world():
+    """(rank, world size) of this process; (0, 1) without a process group."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def shard_bounds(n_items, rank, world):
     """Contiguous, balanced block of `n_items` for `rank`."""
     base, extra = divmod(n_items, world)

@@ -31,8 +31,12 @@ def _worker(rank, world, port, q):
         parallel.allreduce_mean_(flat)
         gathered = parallel.gather_rays(mine["rays"][:, :3].clone(), 101, dst=0)
         ok = bool(torch.allclose(flat, torch.full((1000,), (1 + world) / 2)))
+        ok = ok and parallel.rank_world() == (rank, world)
+        lo, hi = parallel.shard_bounds(101, rank, world)
+        cls = parallel.gather_rays(torch.arange(lo, hi, dtype=torch.int32), 101, dst=0)     # int32 per-ray output
         if rank == 0:
             ok = ok and torch.equal(gathered, batch["rays"][:, :3])
+            ok = ok and cls.dtype == torch.int32 and torch.equal(cls, torch.arange(101, dtype=torch.int32))
         else:
             ok = ok and gathered is None
         q.put((rank, ok, mine["rays"].shape[0]))

@@ -366,3 +366,68 @@ def test_odd_tile_count_and_gradient_additivity(n_rays):
     for (name, _), ga, gb, gt in zip(model.named_parameters(), g_a, g_b, g_all):
         ref = float(gt.abs().max())
         assert float((ga + gb - gt).abs().max()) <= 4e-3 * ref + 1e-9, name     # fp16 gradient tiles, different scales
+
+
+@pytest.mark.parametrize("b,n,c,beta", [(257, 64, 3, 0), (33, 128, 3, 0), (9, 64, 0, 0), (7, 50, 3, 0), (130, 64, 3, 1),
+                                        (12, 64, 0, 1)])
+def test_compositing_ray_aux_for_image_export(b, n, c, beta):
+    """per-ray sums of eval.py:75-101 and the class argmax (eval.py:63) from the compositing
+    kernel, specialised (n = 64 / 128) and generic shapes, with and without the (B,N) outputs."""
+    n_out = 8 + beta + c
+    out = _fake_out(b, n, n_out, 3 * b + n).to(DEV)
+    batch = synthetic.make_batch(b, seed=b)
+    z = O.stratified_z(batch["rays"], n, torch.rand(b, n, generator=torch.Generator().manual_seed(2))).to(DEV)
+    w, t, rgb, _, depth, sem = E.composite_fwd(out, z, n_out, 8 + beta, c, want_raw=False)
+    w2, t2, rgb2, _, depth2, sem2, aux, cls = E.composite_fwd(out, z, n_out, 8 + beta, c, want_raw=False,
+                                                              want_samples=False, want_aux=True,
+                                                              col_beta=8 if beta else -1)
+    assert w2 is None and t2 is None
+    assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2)
+    o3 = out.view(b, n, n_out)
+    want = torch.cat([(w[..., None] * o3[..., 0:3]).sum(1), (w[..., None] * o3[..., 4:5]).sum(1),
+                      (w[..., None] * o3[..., 5:8]).sum(1),
+                      (w[..., None] * o3[..., 8:9]).sum(1) if beta else torch.zeros(b, 1, device=DEV)], 1)
+    assert torch.allclose(aux, want, rtol=1e-5, atol=2e-6)
+    if c:
+        assert torch.equal(sem, sem2)
+        assert cls.dtype == torch.int32 and torch.equal(cls.long(), sem.argmax(-1))
+    else:
+        assert cls is None
+
+
+@pytest.mark.parametrize("case", ["c1_test_sem", "guided_test_nosem"])
+def test_render_image_matches_render_rays(case):
+    """Full-image inference driver (BASELINE config 4 path) against render_rays in test mode on the golden
+    inputs with the recorded random draws: same rgb / depth / logits, and its per-ray sums equal what
+    eval.py:75-101 computes from render_rays' per-sample outputs."""
+    from spnerf_b200 import inference as image_inference
+    g, meta = load_case(case)
+    model, t_mod, args = build_model(meta, DEV)
+    ins = {k[3:]: torch.from_numpy(g[k]).to(DEV) for k in g.files if k.startswith("in_")}
+    models = {"coarse": model}
+    sems = ins["sems"] if args.sem else None
+    args._rng = Draws(g, DEV)
+    with torch.no_grad():
+        ref = render_rays(models, args, ins["rays"], None, semantics=sems, mode="test")
+    args._rng = Draws(g, DEV)
+    img = image_inference.render_image(models, args, ins["rays"], None, semantics=sems, chunk=ins["rays"].shape[0])
+    assert torch.allclose(img["rgb"], ref["rgb_coarse"], atol=1e-6)
+    assert torch.allclose(img["depth"], ref["depth_coarse"], atol=1e-6)
+    w = ref["weights_coarse"][..., None]
+    for key in ("albedo", "sun", "sky"):
+        assert torch.allclose(img[key], (w * ref[key + "_coarse"]).sum(-2), rtol=1e-5, atol=2e-6), key
+    if args.sem:
+        assert torch.allclose(img["sem_logits"], ref["sem_logits_coarse"], atol=1e-6)
+        assert torch.equal(img["sem_class"].long(), ref["sem_logits_coarse"].argmax(-1))
+    # and against the golden outputs of the reference itself, at the stated tolerances
+    assert float((img["rgb"] - torch.from_numpy(g["out_rgb_coarse"]).to(DEV)).abs().max()) <= TOL["rgb"]
+    assert float((img["depth"] - torch.from_numpy(g["out_depth_coarse"]).to(DEV)).abs().max()) <= TOL["depth"]
+    # chunked and sharded (world size 1) renders cover every ray once and are finite
+    args._rng = None
+    torch.manual_seed(7)
+    a = image_inference.render_image(models, args, ins["rays"], None, semantics=sems, chunk=300)
+    torch.manual_seed(7)
+    bsh = image_inference.render_image_sharded(models, args, ins["rays"], None, semantics=sems, chunk=300)
+    for k in a:
+        assert a[k].shape[0] == ins["rays"].shape[0] and torch.equal(a[k], bsh[k]), k
+        assert bool(torch.isfinite(a[k].float()).all()), k
