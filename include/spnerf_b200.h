@@ -68,8 +68,8 @@ int spnerf_selftest_umma2(const SpnerfUmmaSelftest* args, void* stream);
 /* Profiling aid: when non-NULL, the next spnerf_mlp_fwd / spnerf_mlp_bwd_data launches log clock64()
  * stamps of CTA 0 into dev_buf2048 (2048 int64, device memory): [0,256) epilogue phase stamps,
  * [256,262) issuer wait sums, and for the third tile pair per step i < 256: [512+i] producer saw the
- * ring stage empty, [768+i] issuer passed the epilogue gate, [1024+i] issuer saw the stage full,
- * [1280+i] commit issued; [1536,1792) epilogue half-way stamps.  NULL disables. */
+ * ring stage empty, [768+i] issuer started waiting for the stage, [1024+i] issuer saw the stage full,
+ * [1280+i] commit issued.  NULL disables. */
 void spnerf_debug_phase_clocks_fwd(long long* dev_buf2048);
 void spnerf_debug_phase_clocks_bwd(long long* dev_buf2048);
 
@@ -119,7 +119,7 @@ typedef struct SpnerfNetSizes {
 /* host only; no device work */
 int spnerf_net_sizes(const SpnerfNetConfig* cfg, SpnerfNetSizes* sizes_host);
 /* Debug aid (host only): the MMA step list of the forward (backward = 0) or backward-data (1) kernel as
- * 8 int32 per step [n, tmem_col, a_slab, ksteps, first, last, issuer lane, early]; returns the step count. */
+ * 8 int32 per step [n, tmem_col, a_slab, ksteps, first, last, issuer lane, 0]; returns the step count. */
 int spnerf_debug_step_table(const SpnerfNetConfig* cfg, int backward, int32_t* out, int max_steps);
 
 /* Packing the fp32 parameters into tensor-core operands, in two steps:
@@ -326,6 +326,15 @@ typedef struct SpnerfGuided {
   int32_t* searchsorted_out;  /* (n_rays,n) indices of rendering.py:38, or NULL (parity tests)       */
 } SpnerfGuided;
 int spnerf_sample_guided(const SpnerfGuided* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser step over the flat fp32 parameter buffer (replaces torch.optim.Adam(parameters, lr=args.lr,
+ * weight_decay=0) of main.py:96-97; torch's update order; bias corrections from `step` >= 1 and the
+ * 1 - beta factors are formed in double like torch's).  All four
+ * buffers hold n floats and are 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int spnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     int64_t step, double lr, double beta1, double beta2, double eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,6 +195,8 @@ def _declare_rest(L):
     L.spnerf_sample_coarse.argtypes = [VP, VP, VP, I64, I32, VP, VP]
     L.spnerf_sky_bwd.restype = ctypes.c_int
     L.spnerf_sky_bwd.argtypes = [VP, ctypes.POINTER(NetConfig), VP, VP, VP, VP, I64, VP, VP, VP, VP, VP]
+    L.spnerf_adam_step.restype = I32
+    L.spnerf_adam_step.argtypes = [VP, VP, VP, VP, I64, I64] + [ctypes.c_double] * 4 + [VP]
     L.spnerf_struct_sizes.restype = None
     L.spnerf_struct_sizes.argtypes = [ctypes.POINTER(I32)]
 

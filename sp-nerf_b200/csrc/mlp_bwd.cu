@@ -157,12 +157,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
   }
   const float inv_scale = 1.f / scale;
 
-  if (warp == kProducerWarp) {
+  if (warp == 0) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
-  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
-  } else if (warp < 16) {
+  } else if (warp == 1 || warp == 2) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
+    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
+  } else if (warp >= kEpiWarp0) {
     const int cg = (warp - kEpiWarp0) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -171,8 +171,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
     const float4* Wsem2 = reinterpret_cast<const float4*>(smem + kOffSem2);
     const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
-    const int half_nb = (p.debug & 2) ? 2 : 4;        // 16-column batches per thread and column half
-    EpiSync sync(sh, p.prof, p.tab);
+    const int wide_cols = (p.debug & 2) ? 32 : 128;
+    EpiSync sync(sh, p.prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
 
@@ -190,7 +190,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       auto gs = [&](int slab) -> uint8_t* { return tg ? tg + (size_t)slab * kSlabBytes : nullptr; };
 
       // ---- head-level gradients of this row (fp32, unscaled) ----
-      sync.new_tile();
       sync.stamp();
       float g_u[3] = {0.f, 0.f, 0.f}, g_v = 0.f, g_sp = 0.f, g_bp = 0.f, g_lg[8];
 #pragma unroll
@@ -274,8 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       }
       // ---- g_f (linear) -> slabs 0..7 ----
       sync.begin();
-      bwd_columns<2, 4>(taddr, cg * 64, nullptr, nullptr, act, 0, row, gs(p.gm.g_f), win, half_nb);
-      bwd_columns<2, 4>(taddr, kHalf + cg * 64, nullptr, nullptr, act, 0, row, nullptr, win, half_nb);
+      bwd_columns<2, 8>(taddr, cg * 128, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr, win, wide_cols / 16);
       sync.end(true);
       copy_slabs_out(act, 4, 4, gs(p.gm.g_f + 4));
       // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
@@ -318,23 +316,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         if (signal) sync.end(true);
       };
       for (int L = 7; L >= 0; --L) {
-        // column halves in order (see mlp_fwd.cu): columns 0..255 -> slabs 0..3, half(), columns 256..511;
-        // half of the gradient tile leaves from registers (spread over both column halves), the rest from
-        // shared memory during the next MMAs
-        ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 64, row);
+        ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
         sync.begin();
-        const bool early = sync.next_early();
-        uint8_t* gdirect = cg < 2 ? gs(p.gm.G[L]) : nullptr;      // slabs 0,1 / 4,5 leave from registers
-        if (L > 0) bwd_columns<0, 4>(taddr, cg * 64, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, half_nb);
-        else       bwd_columns<1, 4>(taddr, cg * 64, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, half_nb);
-        ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), kHalf + cg * 64, row);
-        if (early) sync.half();
-        if (L > 0) bwd_columns<0, 4>(taddr, kHalf + cg * 64, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, half_nb);
-        else       bwd_columns<1, 4>(taddr, kHalf + cg * 64, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, half_nb);
+        // half of the gradient tile leaves from registers now, half from shared memory during the next MMAs
+        uint8_t* gdirect = cg < 2 ? gs(p.gm.G[L]) : nullptr;
+        if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else       bwd_columns<1, 8>(taddr, cg * 128, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
-        copy_slabs_out(act, 2, 2, gs(p.gm.G[L] + 2));
-        copy_slabs_out(act, 6, 2, gs(p.gm.G[L] + 6));
+        copy_slabs_out(act, 4, 4, gs(p.gm.G[L] + 4));
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }

@@ -91,12 +91,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
-  if (warp == kProducerWarp) {
+  if (warp == 0) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
-  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
-  } else if (warp < 16) {
+  } else if (warp == 1 || warp == 2) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
+    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
+  } else if (warp >= kEpiWarp0) {
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
     const int row = (warp & 3) * 32 + lane;    // TMEM lane quarter = warp % 4
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -107,7 +107,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
     float* scratch = reinterpret_cast<float*>(smem + kSlabInpHi * kSlabBytes);
-    EpiSync sync(sh, p.prof, p.tab);
+    EpiSync sync(sh, p.prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
 
@@ -122,7 +122,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       float* orow = p.out + pt * p.n_out;
 
       // ---- encoded input [PE(xyz) | label embedding] as fp16 hi + residual, and the aux operand ----
-      sync.new_tile();
       sync.stamp();
       sync.drain_stores();
       {
@@ -212,25 +211,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       }
       sync.end(true);
 
-      // ---- trunk: layer 0 is sin(30 (W0 x + b0)) (spnerf.py:202, Siren w0=30), layers 1..7 sin(W h + b) ----
-      // Column halves in order: accumulator columns 0..255 -> activation slabs 0..3 first, then the MMA
-      // issuer may already start the next layer's first K half on them (half()), then columns 256..511.
-      // Half of the tile leaves from registers during the epilogue (spread over both column halves), the
-      // other half from shared memory during the next MMA phase: global stores are the scarce resource
-      // (~13 B/cycle/SM chip-wide).
-      const int hc = (p.debug & 2) ? 32 : 64;
-      for (int i = 0; i < 8; ++i) {
+      // ---- trunk layer 0: sin(30 (W0 x + b0))  (spnerf.py:202, Siren w0=30) ----
+      sync.begin();
+      // half of the tile leaves from registers during the epilogue, the other half from shared memory
+      // during the next MMA phase: global stores are the scarce resource (~13 B/cycle/SM chip-wide)
+      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]), cg < 2 ? sv(p.sm.y[0]) : nullptr,
+                        NoEach());
+      sync.end(true);
+      copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
+      // ---- trunk layers 1..7 ----
+      for (int i = 1; i < 8; ++i) {
         sync.begin();
-        const bool early = sync.next_early();
-        uint8_t* ydirect = cg < 2 ? sv(p.sm.y[i]) : nullptr;      // slabs 0,1 / 4,5 leave from registers
-        if (i == 0) epi_cols<1, true>(taddr, cg * 64, hc, act, 0, row, sv(p.sm.x[0]), ydirect, NoEach());
-        else        epi_cols<0, true>(taddr, cg * 64, hc, act, 0, row, sv(p.sm.x[i]), ydirect, NoEach());
-        if (early) sync.half();
-        if (i == 0) epi_cols<1, true>(taddr, kHalf + cg * 64, hc, act, 0, row, sv(p.sm.x[0]), ydirect, NoEach());
-        else        epi_cols<0, true>(taddr, kHalf + cg * 64, hc, act, 0, row, sv(p.sm.x[i]), ydirect, NoEach());
+        epi_cols<0, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
+                          cg < 2 ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
-        copy_slabs_out(act, 2, 2, sv(p.sm.y[i] + 2));
-        copy_slabs_out(act, 6, 2, sv(p.sm.y[i] + 6));
+        copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
       }
       // ---- heads on h: semantic hidden (accumulator columns 0..255) and sigma (256, 257) ----
       sync.begin();
@@ -262,8 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
       sync.begin();
-      epi_cols<2, true>(taddr, cg * 64, hc, act, 0, row, nullptr, sv(p.sm.f), NoEach());
-      epi_cols<2, true>(taddr, kHalf + cg * 64, hc, act, 0, row, nullptr, nullptr, NoEach());
+      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr, cg < 2 ? sv(p.sm.f) : nullptr, NoEach());
       sync.end(true);
       copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
 

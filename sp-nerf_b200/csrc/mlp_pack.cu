@@ -162,43 +162,22 @@ struct Builder {
   // Closes a phase.  Its chunks (independent accumulator column ranges) are dealt to the two issuer
   // lanes, balancing step counts, and the ring order interleaves the lanes so that both issuers
   // always have an item in flight.  The order of the steps inside a chunk is preserved.
-  // pipelined: the phase follows a two-half 512-column epilogue (activation slabs 0..3 / accumulator
-  // columns < 256 are released half an epilogue early): the first chunk's steps over slabs 0..3 are
-  // marked early and lead the ring order, so the issuers start them while the epilogue is still busy
-  // with the second column half.  In such a phase the lanes simply alternate in ring order (a lane per
-  // chunk would leave one issuer with all the late work, and a single issuer cannot keep the tensor
-  // pipe fed); two issuers then accumulate into the same columns, which is safe because the pipe
-  // executes MMAs in arrival order and (a) the item after the overwriting first item of the early
-  // group waits for a hand-off barrier (early = 3), (b) any other item follows its chunk's first item
-  // on the same lane or >= 4 ring positions later, i.e. after that item has retired.
-  std::vector<int> phase_first;
-  void end_phase(bool pipelined = false) {
+  void end_phase() {
     const size_t e = steps.size();
-    phase_first.push_back((int)phase_begin);
     chunk_begin.push_back(e);
     std::vector<MmaStep> lane_steps[2];
-    size_t n_early = 0;
     for (size_t c = 0; c + 1 < chunk_begin.size(); ++c) {
       const int lane = lane_steps[0].size() <= lane_steps[1].size() ? 0 : 1;
       for (size_t i = chunk_begin[c]; i < chunk_begin[c + 1]; ++i) {
         MmaStep st = steps[i];
         st.lane = (uint8_t)lane;
-        st.early = (pipelined && c == 0 && st.a_slab < 4 && st.tmem_col + st.n <= 256) ? 1 : 0;
-        n_early += st.early;
         lane_steps[lane].push_back(st);
       }
     }
     size_t o = phase_begin, a = 0, b = 0;
-    while (a < lane_steps[0].size() && lane_steps[0][a].early) steps[o++] = lane_steps[0][a++];
     while (a < lane_steps[0].size() || b < lane_steps[1].size()) {
       if (a < lane_steps[0].size()) steps[o++] = lane_steps[0][a++];
       if (b < lane_steps[1].size()) steps[o++] = lane_steps[1][b++];
-    }
-    if (n_early >= 2 && steps[phase_begin].first) {
-      for (size_t i = phase_begin; i < e; ++i) steps[i].lane = (uint8_t)((i - phase_begin) & 1);
-      steps[phase_begin + 1].early = 3;
-    } else {
-      for (size_t i = phase_begin; i < e; ++i) steps[i].early = 0;
     }
     steps[e - 1].last = 1;
     chunk_begin.clear();
@@ -231,7 +210,7 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
       b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs, false, false,
               aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], kFeat));
     }
-    b.end_phase(true);
+    b.end_phase();
   }
   // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212)
   if (c.sem) b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat), false, false,
@@ -249,7 +228,7 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
       b.items.push_back(lo);
     }
   }
-  b.end_phase(true);            // follows the two-half epilogue of trunk layer 7
+  b.end_phase();
   for (int g = 0; g < 2; ++g)   // feats_from_xyz (:215)
     b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, act8(kFeat), false, false,
             aux_bias(P[SPNERF_P_FEATS_B], kFeat));
@@ -292,7 +271,7 @@ int validate(const SpnerfNetConfig* c) {
 }  // namespace
 
 void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
-                    std::vector<PackItem>* items, uint32_t* off16, std::vector<int>* phases = nullptr);   // below
+                    std::vector<PackItem>* items, uint32_t* off16);   // mlp_pack_bwd section below
 
 // cached per configuration; entries are never freed or moved (callers keep the pointer for a launch)
 #include <map>
@@ -309,29 +288,25 @@ const net::StepTable* net::step_table(const SpnerfNetConfig& cfg, int backward) 
   if (it != cache.end()) return it->second.get();
   const float* P[SPNERF_NUM_PARAMS] = {};
   std::vector<MmaStep> steps;
-  std::vector<int> phases;
   if (backward) {
     uint32_t off = 0;
-    build_backward(cfg, P, steps, nullptr, &off, &phases);
+    build_backward(cfg, P, steps, nullptr, &off);
   } else {
     Builder f;
     build_forward(cfg, P, f);
     steps = f.steps;
-    phases = f.phase_first;
   }
-  if ((int)steps.size() > kMaxSteps || (int)phases.size() > kMaxPhases) return nullptr;
+  if ((int)steps.size() > kMaxSteps) return nullptr;
   std::unique_ptr<StepTable> t(new StepTable());
   std::memset(t.get(), 0, sizeof(StepTable));
   t->n = (int)steps.size();
-  t->n_phases = (int)phases.size();
-  for (size_t i = 0; i < phases.size(); ++i) t->phase_first[i] = (uint16_t)phases[i];
   std::memcpy(t->s, steps.data(), steps.size() * sizeof(MmaStep));
   const StepTable* r = t.get();
   cache[key] = std::move(t);
   return r;
 }
 
-// debug: the step list as 8 int32 per step [n, tmem_col, a_slab, ksteps, first, last, lane, early]; returns
+// debug: the step list as 8 int32 per step [n, tmem_col, a_slab, ksteps, first, last, lane, 0]; returns
 // the number of steps (or a negative error)
 extern "C" int spnerf_debug_step_table(const SpnerfNetConfig* cfg, int backward, int32_t* out, int max_steps) {
   if (!cfg || validate(cfg) != 0) return SPNERF_ERR_UNSUPPORTED;
@@ -340,7 +315,7 @@ extern "C" int spnerf_debug_step_table(const SpnerfNetConfig* cfg, int backward,
   for (int i = 0; i < t->n && i < max_steps && out; ++i) {
     const MmaStep& s = t->s[i];
     int32_t* o = out + 8 * i;
-    o[0] = s.n; o[1] = s.tmem_col; o[2] = s.a_slab; o[3] = s.ksteps; o[4] = s.first; o[5] = s.last; o[6] = s.lane; o[7] = s.early;
+    o[0] = s.n; o[1] = s.tmem_col; o[2] = s.a_slab; o[3] = s.ksteps; o[4] = s.first; o[5] = s.last; o[6] = s.lane; o[7] = 0;
   }
   return t->n;
 }
@@ -550,7 +525,7 @@ extern "C" int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, co
 // operands, transposed weights the B operands: g_in[n] = sum_k G[k] * W[k][n].
 // ------------------------------------------------------------------------------------------------
 void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector<MmaStep>& steps,
-                    std::vector<PackItem>* items, uint32_t* off16, std::vector<int>* phases) {
+                    std::vector<PackItem>* items, uint32_t* off16) {
   Builder b;
   const NetDims d = make_dims(c);
   const int base = c.mapping ? 60 : 3;
@@ -602,8 +577,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     }
     for (int g = 0; g < 2; ++g)
       b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, g * kHalf, kHalf, g * kHalf, ks(0, 8), true);
-    // released by the two-half epilogue that wrote G_L, except behind the embedding mini phase
-    b.end_phase(!(skip && c.sem));
+    b.end_phase();
   }
   if (c.sem) {
     b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, base, 16, 0, ks(0, 8), true);
@@ -611,7 +585,6 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   }
   steps = b.steps;
   if (items) *items = b.items;
-  if (phases) *phases = b.phase_first;
   *off16 = b.off16;
 }
 

@@ -5,16 +5,16 @@
 // points (its activations are the A rows 128*rank.. of an M = 256 MMA) and streams only half of
 // every weight tile (B rows (n/2)*rank..), so a weight byte fetched from L2 feeds 256 points.
 // 640 threads per CTA, one CTA per SM:
-//   warps 0-15    epilogue: warp w reads TMEM lanes 32*(w%4).., i.e. point row 32*(w%4)+lane, and
-//                 column group w/4 of the phase's accumulator
-//   warp 16       weight producer (one lane): 1-D bulk copies of this CTA's half of the pre-packed
+//   warp 0        weight producer (one lane): 1-D bulk copies of this CTA's half of the pre-packed
 //                 fp16 B tiles into a 4-stage ring
-//   warps 17, 18  rank 0: the two MMA issuers (tcgen05.mma M=256, N<=256, K=16, fp16 -> fp32 in TMEM).
+//   warps 1, 2    rank 0: the two MMA issuers (tcgen05.mma M=256, N<=256, K=16, fp16 -> fp32 in TMEM).
 //                 Every phase is split into accumulator chunks owned by one issuer each (MmaStep::lane),
 //                 interleaved in ring order: one thread cannot issue 4 MMAs + a commit + a barrier
 //                 wait in the 512 cycles the tensor pipe needs for them (measured ~710).
-//                 rank 1, warp 17: relay, forwards "my ring stage landed" to the issuers
-//   warp 19       idle
+//                 rank 1, warp 1: relay, forwards "my ring stage landed" to the issuers
+//   warp 3        idle (keeps the epilogue warps aligned to TMEM lane quarters)
+//   warps 4-19    epilogue: warp w reads TMEM lanes 32*(w%4).., i.e. point row 32*(w%4)+lane, and
+//                 column group (w-4)/4 of the phase's accumulator
 #pragma once
 #include "sm100.cuh"
 #include "net_plan.h"
@@ -25,10 +25,7 @@ using namespace net;
 
 constexpr int kThreads = 640;
 constexpr int kEpiThreads = 512;
-constexpr int kEpiWarp0 = 0;       // epilogue warps 0..15
-// The control warps take the HIGHEST warp ids: the sub-partition arbiter favours high ids, and the
-// issuers must not queue behind 16 busy epilogue warps when an MMA phase overlaps an epilogue.
-constexpr int kProducerWarp = 16, kIssuerWarp0 = 17, kIssuerWarp1 = 18;
+constexpr int kEpiWarp0 = 4;
 constexpr int kColGroups = 4;
 
 struct Smem {
@@ -39,8 +36,6 @@ struct Smem {
   uint64_t* bar_empty;   // [4] weight stage consumed (arrives from the issuer's commit, both CTAs)
   uint64_t* bar_mma;     // MMA phase retired -> epilogue (both CTAs)
   uint64_t* bar_epi;     // rank 0 only: both epilogues done -> MMA
-  uint64_t* bar_half;    // rank 0 only: both epilogues have finished the first column half -> early steps
-  uint64_t* bar_first;   // rank 0 only: issuer 0 has issued the overwriting first item of an early group -> issuer 1
   uint64_t* bar_par;     // parameter region landed (once)
   uint32_t* tmem_slot;
   uint32_t rank;
@@ -53,7 +48,7 @@ __device__ __forceinline__ Smem carve(uint8_t* smem) {
   s.wst = smem + kOffWst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   s.bar_full = bars; s.bar_empty = bars + 4;
-  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14; s.bar_half = bars + 15; s.bar_first = bars + 8;
+  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   s.rank = cluster_ctarank();
   return s;
@@ -69,14 +64,13 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
       // issuer CTA: its own copy (arrive.expect_tx) + the peer's relay; peer CTA: its own copy only
       mbar_init(&s.bar_full[i], (s.rank == 0 && !(debug & 8)) ? 2 : 1); mbar_init(&s.bar_empty[i], 1);
     }
-    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1); mbar_init(s.bar_first, 1);
-    mbar_init(s.bar_half, 2 * (kEpiThreads / 32));     // every epilogue warp of both CTAs arrives on its own
+    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1);
     fence_mbar_init();
     mbar_expect_tx(s.bar_par, kSmallWFloats * 4);
     bulk_g2s(smem + kOffRgb2, smallw, 3072 * 4, s.bar_par);              // rgb2 | sem2
     bulk_g2s(smem + kOffSun6, smallw + 3072, 512 * 4, s.bar_par);        // sun6 | beta2
   }
-  if (warp == kIssuerWarp0) { tmem_alloc2(s.tmem_slot, 512); tmem_relinquish2(); }
+  if (warp == 1) { tmem_alloc2(s.tmem_slot, 512); tmem_relinquish2(); }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -86,7 +80,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   tc_fence_before();
   cluster_sync_all();      // the peer may still be signalling this CTA's barriers / reading its operands
-  if ((threadIdx.x >> 5) == kIssuerWarp0) tmem_dealloc2(tmem_base, 512);
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc2(tmem_base, 512);
 }
 
 // number of tile pairs this cluster processes
@@ -95,9 +89,7 @@ __device__ __forceinline__ int64_t my_pairs(int64_t n_pairs) {
   return c < n_pairs ? (n_pairs - c + nc - 1) / nc : 0;
 }
 
-// Producer warp of both CTAs (all lanes run the loop; one elected lane issues the copies).
-// (A copy cannot complete on the PEER's mbarrier: the linear cp.async.bulk form faults on a remote
-// barrier and has no .cta_group::2 variant, so rank 1 reports its half through the relay below.)
+// warp 0 of both CTAs (all lanes run the loop; one elected lane issues the copies)
 __device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob, const StepTable& tab,
                                               int64_t n_iters, int debug, long long* prof = nullptr) {
   uint32_t stage = 0, phase = 0;
@@ -123,8 +115,8 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob
   (void)prof;
 }
 
-// rank 1, first issuer warp: tell the issuer that this CTA's half of each item has landed (second
-// arrival on the issuer's stage barrier)
+// warp 1, rank 1: tell the issuer that this CTA's half of each item has landed (second arrival on
+// the issuer's stage barrier)
 __device__ __forceinline__ void relay_loop(const Smem& s, int n_steps, int64_t n_iters, int debug = 0) {
   uint32_t stage = 0, phase = 0;
   if (debug & 8) return;      // timing experiment: the issuer does not wait for this CTA's operands
@@ -146,36 +138,29 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
   constexpr uint64_t tmpl = make_smem_desc_template(16, 1024, kSwizzle128B);
   constexpr uint64_t tmpl_aux = make_smem_desc_template(128, 256, kSwizzleNone);   // 16-column no-swizzle operand
   const uint32_t act_addr = smem_u32(s.act), wst_addr = smem_u32(s.wst), aux_addr = smem_u32(s.aux);
-  uint32_t stage = 0, phase = 0, epi_par = 0, half_par = 0, first_par = 0;
+  uint32_t stage = 0, phase = 0, epi_par = 0;
   const bool plog = prof && blockIdx.x == 0 && (threadIdx.x & 31) == 0;     // per-step log, iteration 2, both lanes
   long long w_epi = 0, w_full = 0, t_all = prof ? clock64() : 0;
   for (int64_t it = 0; it < n_iters; ++it) {
     int i = 0;
     while (i < n_steps) {
-      // One phase.  Early items (leading the ring order) may go as soon as both epilogues have finished
-      // their first column half; everything else waits for the whole epilogue.
-      bool last, epi_waited = false, half_waited = false;
+      long long t0 = prof ? clock64() : 0;
+      mbar_wait_cluster(s.bar_epi, epi_par, 20); epi_par ^= 1;
+      if (prof) w_epi += clock64() - t0;
+      tc_fence_after();
+      bool last;
       do {
         const uint32_t n = tab.s[i].n, tcol = tab.s[i].tmem_col, a_slab = tab.s[i].a_slab, ksteps = tab.s[i].ksteps;
-        const uint32_t first = tab.s[i].first, lane = tab.s[i].lane, early = tab.s[i].early;
+        const uint32_t first = tab.s[i].first, lane = tab.s[i].lane;
         last = tab.s[i].last;
         ++i;
         if ((int)lane == my_lane) {
-          long long t0 = prof ? clock64() : 0;
-          if (early) {
-            if (!half_waited) { mbar_wait_cluster(s.bar_half, half_par, 24); half_par ^= 1; half_waited = true; tc_fence_after(); }
-            if (early & 2) { mbar_wait(s.bar_first, first_par, 26); first_par ^= 1; }
-          } else if (!epi_waited) {
-            mbar_wait_cluster(s.bar_epi, epi_par, 20); epi_par ^= 1; epi_waited = true;
-            tc_fence_after();
-          }
-          if (prof) { const long long t1 = clock64(); w_epi += t1 - t0; if (plog && it == 2 && i <= 256) prof[768 + i - 1] = t1; }
           t0 = prof ? clock64() : 0;
           mbar_wait_cluster(&s.bar_full[stage], phase, 21);      // both halves of the item have landed
           if (prof) {
             const long long t1 = clock64();
             w_full += t1 - t0;
-            if (plog && it == 2 && i <= 256) prof[1024 + i - 1] = t1;
+            if (plog && it == 2 && i <= 256) { prof[1024 + i - 1] = t1; prof[768 + i - 1] = t0; }
           }
           tc_fence_after();
           const uint32_t b0 = wst_addr + stage * kWStageBytes;
@@ -192,15 +177,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
               }
             }
             umma2_commit(&s.bar_empty[stage]);
-            if (early && first) mbar_arrive(s.bar_first);       // the overwrite is in the pipe: issuer 1 may accumulate
           }
           __syncwarp();
           if (plog && it == 2 && i <= 256) prof[1280 + i - 1] = clock64();       // commit issued
         }
         if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
       } while (!last);
-      // a lane without late items still consumes the epilogue-done phase (parity bookkeeping)
-      if (!epi_waited) { mbar_wait_cluster(s.bar_epi, epi_par, 25); epi_par ^= 1; tc_fence_after(); }
       if (elect_one()) umma2_commit(s.bar_mma);      // this issuer's share of the phase (possibly empty) has retired
       __syncwarp();
     }
@@ -220,33 +202,12 @@ struct EpiSync {
   uint32_t mma_par = 0;
   bool stores_pending = false;
   long long* prof;        // optional phase clock log (block 0 only)
-  int prof_i = 0, half_i = 0;
-  uint32_t epi_remote, half_remote;    // rank 1: the issuer CTA's bar_epi / bar_half
-  const StepTable& tab;
-  int released = 0;       // MMA phases released so far in this tile (= index of the phase the next end(true) releases)
-  __device__ EpiSync(const Smem& s_, long long* prof_, const StepTable& tab_)
+  int prof_i = 0;
+  uint32_t epi_remote;    // rank 1: the issuer CTA's bar_epi
+  __device__ EpiSync(const Smem& s_, long long* prof_)
       : s(s_), issuer(threadIdx.x == kEpiWarp0 * 32),
         prof((blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) ? prof_ : nullptr),
-        epi_remote(mapa_shared(smem_u32(s_.bar_epi), 0)), half_remote(mapa_shared(smem_u32(s_.bar_half), 0)), tab(tab_) {}
-
-  __device__ __forceinline__ void new_tile() { released = 0; }
-  // does the MMA phase that the next end(true) releases start with early items?
-  __device__ __forceinline__ bool next_early() const {
-    return released < tab.n_phases && tab.s[tab.phase_first[released]].early;
-  }
-  // First column half done: activation slabs 0..3 written, accumulator columns < 256 read out.  Every
-  // warp reports on its own (no block barrier: the fast warps go on with the second half).
-  __device__ __forceinline__ void half() {
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncwarp();
-    if (elect_one()) {
-      if (s.rank == 0) mbar_arrive(s.bar_half);
-      else mbar_arrive_remote(half_remote);
-    }
-    __syncwarp();
-    if (prof && half_i < 256) prof[1536 + half_i++] = clock64();
-  }
+        epi_remote(mapa_shared(smem_u32(s_.bar_epi), 0)) {}
 
   __device__ __forceinline__ void stamp() {
     if (prof && prof_i < 256) prof[prof_i++] = clock64();
@@ -302,7 +263,6 @@ struct EpiSync {
       if (s.rank == 0) mbar_arrive(s.bar_epi);
       else mbar_arrive_remote(epi_remote);
     }
-    if (signal) ++released;
     stamp();
   }
   // after end(): queue `nslabs` activation slabs (starting at slab0) for streaming to global memory

@@ -49,18 +49,14 @@ struct __align__(16) MmaStep {
   uint8_t last;       // 1: last item of a phase (in ring order) -> both issuers signal the epilogue
   uint16_t bytes16;   // item size in 16-byte units
   uint8_t lane;       // which of the two MMA issuer warps owns this item (its accumulation chunk)
-  uint8_t early;      // 1: may be issued as soon as the previous epilogue has finished its first column half
-                      //    (reads activation slabs 0..3, writes accumulator columns < 256 only)
+  uint8_t _pad;
 };
 
 // The step list travels to the kernels as a launch parameter (constant bank): the producer and the
 // MMA issuer read one entry per item, and a dependent global load per item would cap the issue rate.
-constexpr int kMaxPhases = 48;
 struct StepTable {
   int n;
-  int n_phases;
-  int _pad[2];
-  uint16_t phase_first[kMaxPhases];   // index of the first step of every MMA phase
+  int _pad[3];
   MmaStep s[kMaxSteps];
 };
 // host: the forward (backward = 0) or backward-data (1) step list of a configuration (mlp_pack.cu)

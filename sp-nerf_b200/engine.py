@@ -157,6 +157,18 @@ def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, 
     return out, g_rgb, g_depth, g_sem
 
 
+def adam_step(flat_params, flat_grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8):
+    """torch.optim.Adam(weight_decay=0) on flat fp32 buffers in one launch (main.py:96-97)."""
+    _require_cuda(flat_params, "parameters")
+    n = flat_params.numel()
+    for t in (flat_grads, exp_avg, exp_avg_sq):
+        if t.numel() != n or t.dtype != torch.float32 or not t.is_contiguous():
+            raise _cabi.SpnerfError("adam_step: buffers must be contiguous fp32 of the parameters' size")
+    _cabi.check(_cabi.lib().spnerf_adam_step(_p(flat_params), _p(flat_grads), _p(exp_avg), _p(exp_avg_sq), n, int(step),
+                                             float(lr), float(betas[0]), float(betas[1]), float(eps), _stream()),
+                "spnerf_adam_step")
+
+
 # ------------------------------------------------------------------------------------------------
 # per-model state
 # ------------------------------------------------------------------------------------------------
@@ -232,6 +244,10 @@ class NetEngine:
                 v[1:] = v[0]
         self._packed_key = key
         self.n_packs += 1
+
+    def mark_dirty(self):
+        """The parameters were changed behind autograd's back (fused optimiser step): repack on next use."""
+        self._packed_key = None
 
     def save_bytes(self, n_points):
         return ((n_points + TILE - 1) // TILE) * self.sizes.save_slabs_per_tile * SLAB_BYTES

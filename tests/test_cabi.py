@@ -80,39 +80,31 @@ def _step_table(cfg, backward):
 @pytest.mark.parametrize("kw", [dict(mapping=0, sem=1), dict(mapping=1, sem=1), dict(mapping=0, sem=0),
                                 dict(mapping=1, sem=1, beta=1)])
 @pytest.mark.parametrize("backward", [0, 1])
-def test_step_table_issue_order_is_safe(kw, backward):
-    """Two MMA issuers may accumulate into the same accumulator columns only in an order the tensor pipe
-    preserves (mlp_pack.cu end_phase): an item that shares columns with a chunk's overwriting first item
-    and is owned by the other issuer must either wait for the hand-off barrier (early = 3, directly
-    behind the first item) or sit >= 4 ring positions later (its ring stage is only refilled after the
-    first item has retired).  Early items read activation slabs 0..3 and write columns < 256 only."""
+def test_step_table_keeps_accumulation_order_deterministic(kw, backward):
+    """The two MMA issuer warps must never accumulate into the same accumulator columns inside a phase: the
+    tensor pipe executes MMAs in arrival order, so sharing columns across issuers makes the fp32 summation
+    order (and with it the result bits) depend on timing.  Every chunk (column range) of a phase belongs to
+    one issuer, its overwriting item comes first, and every phase ends with exactly one `last` item."""
     base = dict(feat=512, layers=8, skip_layer=4, mapping=0, sem=1, num_sem_classes=3, emb_dim=3, beta=0, t_dim=4)
     base.update(kw)
     if not base["sem"]:
         base.update(num_sem_classes=0, emb_dim=0)
     steps = _step_table(_cabi.NetConfig(**base), backward)
     assert steps[-1]["last"] == 1
-    n_early = 0
-    for p, s in enumerate(steps):
+    phase = []
+    for s in steps:
         assert s["lane"] in (0, 1) and s["n"] % 16 == 0 and s["col"] + s["n"] <= 512
-        if s["early"]:
-            n_early += 1
-            assert s["a_slab"] < 4 and s["col"] + s["n"] <= 256
-            if s["early"] == 3:
-                assert steps[p - 1]["first"] and steps[p - 1]["early"] == 1 and steps[p - 1]["lane"] != s["lane"]
-        if s["first"]:
-            synced = False      # the other issuer has waited for this item's hand-off (later items follow in its program order)
-            for q in range(p + 1, min(p + 4, len(steps))):
-                t = steps[q]
-                if steps[q - 1]["last"]:
-                    break
-                overlap = t["col"] < s["col"] + s["n"] and s["col"] < t["col"] + t["n"]
-                if overlap and t["lane"] != s["lane"]:
-                    if q == p + 1 and t["early"] == 3:
-                        synced = True
-                    assert synced, (p, q, s, t)
-    # early items only ever lead a phase
-    for p, s in enumerate(steps):
-        if s["early"] and p > 0 and not steps[p - 1]["early"]:
-            assert steps[p - 1]["last"] == 1
-    assert n_early > 0
+        phase.append(s)
+        if s["last"]:
+            owner, started = {}, set()
+            for t in phase:
+                rng = (t["col"], t["n"])
+                for (c0, n0), lane in owner.items():
+                    if t["col"] < c0 + n0 and c0 < t["col"] + t["n"]:
+                        assert (c0, n0) == rng and lane == t["lane"], (t, c0, n0, lane)
+                owner[rng] = t["lane"]
+                assert bool(t["first"]) == (rng not in started) or not t["first"], t
+                started.add(rng)
+            assert {t["lane"] for t in phase} <= {0, 1}
+            phase = []
+    assert not phase

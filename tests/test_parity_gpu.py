@@ -431,3 +431,52 @@ def test_render_image_matches_render_rays(case):
     for k in a:
         assert a[k].shape[0] == ins["rays"].shape[0] and torch.equal(a[k], bsh[k]), k
         assert bool(torch.isfinite(a[k].float()).all()), k
+
+
+def test_fused_adam_matches_torch_adam():
+    """spnerf_adam_step against torch.optim.Adam(lr, weight_decay=0) (main.py:96-97) over several steps."""
+    g = torch.Generator().manual_seed(11)
+    n = 100003                                            # not a multiple of 4: exercises the tail
+    p0 = torch.randn(n + 1, generator=g)[:n].contiguous()
+    ref = torch.nn.Parameter(p0.clone().to(DEV))
+    opt = torch.optim.Adam([ref], lr=5e-4, weight_decay=0)
+    flat = p0.clone().to(DEV)
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    for step in range(1, 8):
+        grad = (torch.randn(n, generator=g) * (10.0 ** (step % 3 - 1))).to(DEV)
+        ref.grad = grad.clone()
+        opt.step()
+        E.adam_step(flat, grad, m, v, step, 5e-4)
+        # fp32 round-off only: a few ulp of the parameter plus a few ulp of the (<= lr sized) update
+        err = (flat - ref.data).abs()
+        assert bool((err <= 1e-6 * ref.data.abs() + 1e-7).all()), (step, float(err.max()))
+    # moments: torch forms exp_avg with lerp_, the kernel with b1 m + (1 - b1) g -> ulps of the larger operand
+    assert torch.allclose(m, opt.state[ref]["exp_avg"], rtol=1e-5, atol=5e-6)
+    assert torch.allclose(v, opt.state[ref]["exp_avg_sq"], rtol=1e-5, atol=1e-6)
+
+
+def test_trainer_reduces_the_loss_on_a_fixed_batch():
+    """Lightning-free trainer: parameters as views of one flat buffer, fused Adam, repack after
+    every step.  Fitting one fixed synthetic batch must drive the total loss down, and the parameters the
+    modules expose must be the ones the optimiser updates."""
+    from spnerf_b200 import trainer
+    cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=64)
+    args = types.SimpleNamespace(**vars(cfg), lr=5e-4, batch_size=1024, max_train_steps=1000, depth=True, ds_lambda=1.0,
+                                 ss_lambda=4e-2, ds_drop=1.0, ss_drop=1.0, GNLL=False, usealldepth=False)
+    torch.manual_seed(0)
+    tr = trainer.Trainer(args, DEV, n_train_rays=4096)
+    model = tr.models["coarse"]
+    assert all(p.data_ptr() >= tr.flat.data_ptr() and
+               p.data_ptr() < tr.flat.data_ptr() + tr.flat.numel() * 4 for p in model.parameters())
+    assert all(p.data_ptr() % 16 == 0 for p in model.parameters())
+    batch = {k: v.to(DEV) for k, v in synthetic.make_batch(1024, seed=5).items()}
+    before = tr.flat.clone()
+    losses = []
+    for _ in range(40):
+        loss, ld = tr.training_step(batch)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses))
+    assert sorted(ld) == ["coarse_color", "coarse_ds", "coarse_ss"]
+    assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses
+    assert float((tr.flat - before).abs().max()) > 0
+    assert tr.opt_steps == 40 and tr.get_current_epoch(tr.train_steps) == 10 and abs(tr.lr - 5e-4 * 0.9 ** 10) < 1e-12
