@@ -39,7 +39,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock / throttle reasons of one GPU while the timed region runs: NVML polled every ~5 ms (the timed
+    region of the default run is ~0.1-0.3 s, shorter than one nvidia-smi invocation), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -47,16 +48,40 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda bit: "Active" if r & bit else "Not Active"     # noqa: E731
+        return [str(self.index), str(float(mhz)), str(self.max_mhz), "",
+                flag(n.nvmlClocksThrottleReasonHwSlowdown), flag(n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                flag(n.nvmlClocksThrottleReasonSwThermalSlowdown), flag(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self._nvml_row())
+                    time.sleep(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
-                pass
+                self.nvml = None
             time.sleep(0.1)
 
     def summary(self):
@@ -68,12 +93,14 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": float(self.rows[0][2]) if self.rows and self.rows[0][2].replace(".", "").isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_args():
-    from oracle import spnerf_oracle as O     # configuration container only
-    return types.SimpleNamespace(**vars(O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)))
+def make_args(**kw):
+    import spnerf_b200  # noqa: F401
+    from spnerf_b200 import config
+    return config.make_args(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES, **kw)
 
 
 def build_model(args, device):
@@ -268,13 +295,16 @@ def run_ours(a):
         ev[2].record()
         torch.cuda.synchronize()
         f_ms, b_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
         f_gbs, b_gbs = BYTES_COMP_FWD * nr / f_ms / 1e6, BYTES_COMP_BWD * nr / b_ms / 1e6
         line["roofline_compositing"] = {
             "bound": "hbm", "achieved": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr / (f_ms + b_ms) / 1e6,
             "peak": pk["hbm"], "unit": "GB/s",
-            "frac": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr / (f_ms + b_ms) / 1e6 / pk["hbm"], "traffic": None,
-            "fwd": {"achieved": f_gbs, "frac": f_gbs / pk["hbm"], "ms": f_ms},
-            "bwd": {"achieved": b_gbs, "frac": b_gbs / pk["hbm"], "ms": b_ms},
+            "frac": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr / (f_ms + b_ms) / 1e6 / pk["hbm"],
+            "traffic": (tj.get("composite_fwd", 0) + tj.get("composite_bwd", 0)) or None,
+            "algorithmic_bytes": (BYTES_COMP_FWD + BYTES_COMP_BWD) * nr,
+            "fwd": {"achieved": f_gbs, "frac": f_gbs / pk["hbm"], "ms": f_ms, "traffic": tj.get("composite_fwd")},
+            "bwd": {"achieved": b_gbs, "frac": b_gbs / pk["hbm"], "ms": b_ms, "traffic": tj.get("composite_bwd")},
             "rays": nr, "peak_source": pk["source"] + ": copy bandwidth (kernels timed alone)"}
         del out, z, w, t_
 
@@ -321,9 +351,7 @@ def run_ours(a):
         from spnerf_b200 import inference
         other = {}
         # C3: --guidedsample --mapping training step, 16384 rays per GPU (64-sample pass + 128-sample pass)
-        from oracle import spnerf_oracle as O3     # configuration container only
-        args3 = types.SimpleNamespace(**vars(O3.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES,
-                                                         mapping=True, guidedsample=True, chunk=16384)))
+        args3 = make_args(mapping=True, guidedsample=True, chunk=16384)
         model3 = build_model(args3, dev)
         b3 = {k: v.to(dev) for k, v in synthetic.make_batch(16384, seed=300 + rank).items()}
         loss_fn, dl, sl = metrics.SNerfLoss(0.0), metrics.DepthLoss(1.0, usealldepth=False), metrics.SemanticLoss(1.0)

@@ -1,6 +1,6 @@
 """Run the golden parity cases on the GPU (one subprocess each) and print compact reports."""
 import json, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 CASES = ["c1_test_sem", "c2_train_depth_sem", "guided_test_nosem", "c3_train_guided_mapping_sc"]

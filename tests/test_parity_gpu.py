@@ -13,7 +13,7 @@ import torch
 
 import spnerf_b200
 from oracle import spnerf_oracle as O
-from parity_common import TOL, Draws, build_model, load_case, run_case
+from parity_common import ROOT, TOL, Draws, build_model, load_case, run_case
 from spnerf_b200 import _cabi, engine as E, slab, synthetic
 from spnerf_b200.models import inference, load_model
 from spnerf_b200.modules import metrics
@@ -480,3 +480,52 @@ def test_trainer_reduces_the_loss_on_a_fixed_batch():
     assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses
     assert float((tr.flat - before).abs().max()) > 0
     assert tr.opt_steps == 40 and tr.get_current_epoch(tr.train_steps) == 10 and abs(tr.lr - 5e-4 * 0.9 ** 10) < 1e-12
+
+
+def test_stock_pytorch_on_the_same_gpu_is_the_baseline_we_beat():
+    """SURVEY 8c secondary oracle: the reference's algorithm (oracle restatement, plain torch ops -> cuBLAS +
+    elementwise kernels) on the same B200, BASELINE config 2 shape, fp32 and fp16 autocast (the reference trains
+    under AMP, main.py:334).  Informational numbers go to gpurun_out/stock_pytorch_gpu.json; the assertion is only
+    that the fused path is faster than both."""
+    import json
+    import os
+    import time
+    import bench
+    from spnerf_b200 import train_step
+    b, n = 8192, 64
+    cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=n)
+    P = {k: v.to(DEV).requires_grad_(True) for k, v in O.random_parameters(cfg, seed=0, sigma_bias=3.0).items()}
+    batch = {k: v.to(DEV) for k, v in synthetic.make_batch(b, seed=269).items()}
+
+    def step():
+        draws = O.Draws([torch.rand(b, n, device=DEV)], [torch.randn(b, n, device=DEV)])
+        res = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
+                       batch["depth_std"], draws)
+        loss = O.colour_loss(res, batch["rgbs"])[0] + O.depth_loss(
+            res, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0] \
+            + O.semantic_loss(res, batch["sems"], 1.0)[0]
+        torch.autograd.grad(loss, list(P.values()))
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    try:
+        t_fp32 = timed(step)
+        with torch.autocast("cuda", dtype=torch.float16):
+            t_amp = timed(step)
+    except RuntimeError as ex:      # the oracle is CPU test infrastructure; a device mismatch is not a product bug
+        pytest.skip(f"oracle does not run on cuda: {ex}")
+    args = bench.make_args()
+    model = bench.build_model(args, torch.device(DEV))
+    t_ours = timed(lambda: train_step.fused_step(model, args, batch, repack=True), reps=5)
+    info = {"rays": b, "samples": n, "stock_pytorch_fp32_ms": t_fp32 * 1e3, "stock_pytorch_fp16_autocast_ms": t_amp * 1e3,
+            "fused_ms": t_ours * 1e3, "speedup_vs_fp32": t_fp32 / t_ours, "speedup_vs_fp16_autocast": t_amp / t_ours}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(info, open(os.path.join(ROOT, "gpurun_out", "stock_pytorch_gpu.json"), "w"), indent=1)
+    assert t_ours < t_amp and t_ours < t_fp32, info

@@ -6,14 +6,14 @@ import torch
 import bench
 import spnerf_b200
 from spnerf_b200 import synthetic, train_step
-from oracle import spnerf_oracle as O
+from spnerf_b200 import engine as E, config
 
 dev = torch.device("cuda:0")
 args = bench.make_args()
 model = bench.build_model(args, dev)
 B, N = 8192, 64
 batch = synthetic.make_batch(B, seed=269, device=dev)
-z = O.stratified_z(batch["rays"], N, torch.rand(B, N, device=dev)).contiguous()
+z = E.sample_coarse(batch["rays"], torch.rand(B, N, device=dev), N)
 eng = model.engine
 ref = None
 for i in range(6):

@@ -6,15 +6,15 @@ import torch
 import spnerf_b200
 from spnerf_b200 import synthetic
 from spnerf_b200.models import load_model
-from oracle import spnerf_oracle as O
-cfg = O.make_cfg(sem=True, num_sem_classes=3)
+from spnerf_b200 import engine as E, config
+cfg = config.make_args(sem=True, num_sem_classes=3)
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = load_model(types.SimpleNamespace(**vars(cfg))).to(dev)
 B, N = 8192, 64
 batch = synthetic.make_batch(B, seed=5, device=dev)
 rays = batch["rays"]
-z = O.stratified_z(rays, N, torch.rand(B, N, device=dev)).contiguous()
+z = E.sample_coarse(rays, torch.rand(B, N, device=dev), N)
 eng = model.engine
 res = {}
 for flags in (0, 1, 2, 3, 4, 5, 6, 7):
