@@ -287,10 +287,14 @@ def colour_loss(res, target, lambda_sc=0.0, use_beta=False):
     return sum(ld.values()), ld
 
 
-def depth_loss(res, target_depth, target_weight, valid_depth, target_std, lambda_ds=1.0, usealldepth=False):
-    """modules/metrics.py:68-159 DepthLoss (MSE variants; GNLL is not exercised by any config)."""
+def depth_loss(res, target_depth, target_weight, valid_depth, target_std, lambda_ds=1.0, usealldepth=False, gnll=False):
+    """modules/metrics.py:68-159 DepthLoss: MSE variants and the GNLL subset variant (:76, :129-130: the
+    predicted STD is passed where GaussianNLLLoss expects a variance; kept).  GNLL with usealldepth calls
+    GaussianNLLLoss without a variance in the reference (:140) and raises there."""
     lam = lambda_ds / 3.                                                                # :71
     if usealldepth:                                                                     # :140, :154-156
+        if gnll:
+            raise TypeError("GaussianNLLLoss.forward() missing 1 required positional argument: 'var'")   # as :140 does
         per = (res["depth_coarse"] - target_depth) ** 2
         val = lam * torch.mean(target_weight * per)
         return val, {"coarse_ds": val}
@@ -307,7 +311,10 @@ def depth_loss(res, target_depth, target_weight, valid_depth, target_std, lambda
             per = torch.zeros((1,), device=target_weight.device, requires_grad=True)
         else:
             scale = float(d_a.shape[0]) / float(valid_depth.shape[0])                   # :125-127
-            per = scale * tw[apply] * (d_a - td[apply]) ** 2                            # :132
+            if gnll:                                                                    # :129-130
+                per = scale * F.gaussian_nll_loss(d_a, td[apply], std[apply])
+            else:
+                per = scale * tw[apply] * (d_a - td[apply]) ** 2                        # :132
     val = lam * torch.mean(per)                                                         # :151-153
     return val, {"coarse_ds": val}
 

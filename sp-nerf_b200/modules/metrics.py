@@ -81,19 +81,45 @@ class SatNerfLoss(torch.nn.Module):
 
 
 class DepthLoss(torch.nn.Module):
-    """metrics.py:68-159 (MSE variants; the GNLL variant is not exercised by any configuration)."""
+    """metrics.py:68-159.  The MSE variants (subset and all-depth) are one fused CUDA pass; the GNLL subset
+    variant (metrics.py:76,129-130: torch's GaussianNLLLoss with the predicted STD passed as the variance, kept)
+    is a handful of (rays, samples) torch ops on the device, like the solar-correction terms."""
 
     def __init__(self, lambda_ds=1.0, GNLL=False, usealldepth=True, margin=0, stdscale=1):
         super().__init__()
-        if GNLL:
-            raise NotImplementedError("GNLL depth loss is outside the rebuilt path (metrics.py:130; flag off everywhere)")
         self.lambda_ds = lambda_ds / 3.
         self._lambda_arg = lambda_ds
         self.GNLL, self.usealldepth, self.margin, self.stdscale = GNLL, usealldepth, margin, stdscale
 
+    def _gnll_subset(self, inputs, targets, target_valid_depth, target_std):
+        """ComputeSubsetDepthLoss with GNLL (metrics.py:82-130) without boolean-index gathers or host syncs:
+        masked sums over all rays give the same mean over the selected ones."""
+        z, depth, w = inputs['z_vals_coarse'].detach(), inputs['depth_coarse'], inputs['weights_coarse']
+        E._require_cuda(depth, "depth_coarse")
+        b = depth.shape[0]
+        if target_valid_depth is None:
+            target_valid_depth = torch.ones(b, device=depth.device)                       # metrics.py:86
+        valid = target_valid_depth.reshape(-1) > 0
+        pred_std = ((z - depth.unsqueeze(-1)).pow(2) * w).sum(-1).clamp_min(0).sqrt()      # :102
+        apply = valid
+        if not self.usealldepth:
+            apply = valid & (((depth - targets).abs() > target_std) | (pred_std > target_std))     # :78-80, :115
+        n_apply = apply.sum()
+        var = torch.where(apply, pred_std, torch.ones_like(pred_std)).clamp_min(1e-6)      # GaussianNLLLoss eps
+        per = 0.5 * (torch.log(var) + (depth - targets) ** 2 / var)
+        mean = torch.where(apply, per, torch.zeros_like(per)).sum() / n_apply.clamp_min(1).to(per.dtype)
+        scale = n_apply.to(per.dtype) / float(b)                                           # :125-127
+        return self.lambda_ds * scale * mean       # zero (with zero gradient) when nothing is selected (:97-100,119-121)
+
     def forward(self, inputs, targets, weights=1., target_valid_depth=None, target_std=None):
         depth = inputs['depth_coarse']
         b = depth.shape[0]
+        if self.GNLL:
+            if self.usealldepth:       # the reference calls GaussianNLLLoss without a variance here (metrics.py:140)
+                raise TypeError("GaussianNLLLoss.forward() missing 1 required positional argument: 'var' "
+                                "(--GNLL needs the subset path, as in the reference)")
+            val = self._gnll_subset(inputs, targets.float(), target_valid_depth, target_std.float())
+            return val, {'coarse_ds': val}
         if not torch.is_tensor(weights):
             weights = torch.full((b,), float(weights), device=depth.device)
         kw = dict(depth=_c(depth), target_depth=_c(targets), target_weight=_c(weights), lambda_ds=self._lambda_arg,

@@ -1,11 +1,12 @@
 """The CPU oracle against the golden vectors produced from the unmodified reference
 (oracle/make_golden.py).  Runs anywhere; pins the checker that the GPU parity tests rely on."""
+import os
 import numpy as np
 import pytest
 import torch
 
 from oracle import spnerf_oracle as O
-from parity_common import build_model, load_case, make_args, state_hash
+from parity_common import GOLDEN, build_model, load_case, make_args, state_hash
 
 CASES = ["c1_test_sem", "c2_train_depth_sem", "c3_train_guided_mapping_sc", "guided_test_nosem", "beta_small"]
 
@@ -95,3 +96,24 @@ def test_sampler_recipe_matches_torch_reductions():
             run += float(v)
             e.append(np.float32(run))
         assert np.array_equal(np.array(e, np.float32), torch.cumsum(torch.from_numpy(x.reshape(1, -1)), -1).numpy()[0])
+
+
+def test_depth_loss_variants_against_the_reference():
+    """tests/golden/depth_loss_variants.npz (oracle/make_golden_losses.py, the reference's DepthLoss): GNLL subset,
+    MSE all-depth, MSE subset - loss values and gradients w.r.t. depth and weights."""
+    import numpy as np
+    g = np.load(os.path.join(GOLDEN, "depth_loss_variants.npz"))
+    t = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    for name, kw in (("gnll_subset", dict(gnll=True, usealldepth=False)), ("mse_all", dict(usealldepth=True)),
+                     ("mse_subset", dict(usealldepth=False))):
+        d = t["depth"].clone().requires_grad_(True)
+        w = t["weights"].clone().requires_grad_(True)
+        res = {"z_vals_coarse": t["z"], "depth_coarse": d, "weights_coarse": w}
+        val, _ = O.depth_loss(res, t["target_depth"], t["target_weight"], t["valid"], t["target_std"], lambda_ds=1.5, **kw)
+        gd, gw = torch.autograd.grad(val, [d, w], allow_unused=True)
+        assert abs(float(val) - float(g[name + "_loss"][0])) <= 1e-6 * max(1.0, abs(float(g[name + "_loss"][0]))), name
+        assert torch.allclose(gd, torch.from_numpy(g[name + "_g_depth"]), rtol=1e-5, atol=1e-8), name
+        if gw is not None:
+            assert torch.allclose(gw, torch.from_numpy(g[name + "_g_weights"]), rtol=1e-5, atol=1e-8), name
+        else:
+            assert not g[name + "_g_weights"].any()

@@ -529,3 +529,36 @@ def test_stock_pytorch_on_the_same_gpu_is_the_baseline_we_beat():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(info, open(os.path.join(ROOT, "gpurun_out", "stock_pytorch_gpu.json"), "w"), indent=1)
     assert t_ours < t_amp and t_ours < t_fp32, info
+
+
+def test_depth_loss_variants_against_reference_golden():
+    """DepthLoss mirror on the device against the reference's own outputs (tests/golden/depth_loss_variants.npz):
+    the fused MSE kernels (subset / all-depth) and the GNLL subset variant, values and gradients."""
+    import os
+    g = np.load(os.path.join(ROOT, "tests", "golden", "depth_loss_variants.npz"))
+    t = {k[3:]: torch.from_numpy(g[k]).to(DEV) for k in g.files if k.startswith("in_")}
+    for name, kw in (("gnll_subset", dict(GNLL=True, usealldepth=False)), ("mse_all", dict(GNLL=False, usealldepth=True)),
+                     ("mse_subset", dict(GNLL=False, usealldepth=False))):
+        d = t["depth"].clone().requires_grad_(True)
+        w = t["weights"].clone().requires_grad_(True)
+        res = {"z_vals_coarse": t["z"], "depth_coarse": d, "weights_coarse": w}
+        loss_fn = metrics.DepthLoss(lambda_ds=1.5, margin=1e-4, stdscale=1.0, **kw)
+        loss, ld = loss_fn(res, t["target_depth"], t["target_weight"], target_valid_depth=t["valid"],
+                           target_std=t["target_std"])
+        assert sorted(ld) == ["coarse_ds"]
+        want = float(g[name + "_loss"][0])
+        assert abs(float(loss) - want) <= 2e-6 * max(1.0, abs(want)), (name, float(loss), want)
+        gd, gw = torch.autograd.grad(loss, [d, w], allow_unused=True)
+        assert torch.allclose(gd.cpu(), torch.from_numpy(g[name + "_g_depth"]), rtol=2e-5, atol=1e-8), name
+        if name == "gnll_subset":          # the MSE kernels treat the selection mask as a constant of the weights too
+            assert torch.allclose(gw.cpu(), torch.from_numpy(g[name + "_g_weights"]), rtol=2e-5, atol=1e-8), name
+    with pytest.raises(TypeError):
+        metrics.DepthLoss(GNLL=True, usealldepth=True)(res, t["target_depth"], t["target_weight"])
+    # nothing selected -> zero loss, finite zero gradient (metrics.py:97-100)
+    d = t["depth"].clone().requires_grad_(True)
+    res = {"z_vals_coarse": t["z"], "depth_coarse": d, "weights_coarse": t["weights"]}
+    loss, _ = metrics.DepthLoss(lambda_ds=1.0, GNLL=True, usealldepth=False)(
+        res, t["target_depth"], t["target_weight"], target_valid_depth=torch.zeros_like(t["valid"]),
+        target_std=t["target_std"])
+    (gd,) = torch.autograd.grad(loss, [d])
+    assert float(loss) == 0.0 and bool(torch.isfinite(gd).all()) and float(gd.abs().max()) == 0.0
