@@ -70,8 +70,10 @@ def test_loss_factories():
     a.beta = True
     assert isinstance(metrics.load_loss(a), metrics.SatNerfLoss)
     assert metrics.DepthLoss(lambda_ds=3.0, usealldepth=False).lambda_ds == 1.0       # metrics.py:71
-    with pytest.raises(NotImplementedError):
-        metrics.DepthLoss(GNLL=True)
+    gn = metrics.DepthLoss(lambda_ds=3.0, GNLL=True, usealldepth=True)                 # constructible, like the reference's
+    assert gn.GNLL and gn.lambda_ds == 1.0
+    with pytest.raises(TypeError):                       # metrics.py:140: GaussianNLLLoss called without a variance
+        gn({"depth_coarse": torch.zeros(4)}, torch.zeros(4))
 
 
 def test_slab_layout_model():
