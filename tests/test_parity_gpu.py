@@ -562,3 +562,88 @@ def test_depth_loss_variants_against_reference_golden():
         target_std=t["target_std"])
     (gd,) = torch.autograd.grad(loss, [d])
     assert float(loss) == 0.0 and bool(torch.isfinite(gd).all()) and float(gd.abs().max()) == 0.0
+
+
+def test_full_size_guided_mapping_step_properties():
+    """BASELINE config 3 at full size (16384 rays, --guidedsample --mapping + depth + sem): size-independent
+    properties of the two-pass renderer and its backward."""
+    from spnerf_b200 import config
+    args = config.make_args(sem=True, num_sem_classes=3, mapping=True, guidedsample=True, chunk=16384)
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    model = model.to(DEV)
+    b, n = 16384, args.n_samples
+    batch = synthetic.make_batch(b, seed=33, device=DEV)
+
+    def step():
+        torch.manual_seed(5)
+        res = render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="train",
+                          valid_depth=batch["valid_depth"], target_depths=batch["depths"],
+                          target_std=batch["depth_std"])
+        loss = metrics.SNerfLoss(0.0)(res, batch["rgbs"])[0] \
+            + metrics.DepthLoss(1.0, usealldepth=False)(res, batch["depths"][:, 0], batch["depths"][:, 1],
+                                                        target_valid_depth=batch["valid_depth"],
+                                                        target_std=batch["depth_std"])[0] \
+            + metrics.SemanticLoss(1.0)(res, batch["sems"])[0]
+        return res, loss, torch.autograd.grad(loss, list(model.parameters()))
+
+    res, loss, g1 = step()
+    z, zu = res["z_vals_coarse"], res["z_vals_unsort_coarse"]
+    assert z.shape == (b, 2 * n) and zu.shape == (b, 2 * n) and res["weights_coarse"].shape == (b, 2 * n)
+    assert bool((z[:, 1:] >= z[:, :-1]).all())                                   # merged depths are sorted
+    assert torch.equal(torch.sort(zu, -1).values, z)                             # ... and are a permutation of [z, z2]
+    near, far = batch["rays"][0, 6], batch["rays"][0, 7]                          # Q5: clamp to the first ray's bounds
+    assert float(zu[:, n:].min()) >= float(near) - 1e-7 and float(zu[:, n:].max()) <= float(far) + 1e-7
+    w = res["weights_coarse"]
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-4
+    assert float(res["rgb_coarse"].min()) >= 0 and float(res["rgb_coarse"].max()) <= 1
+    assert bool(torch.isfinite(loss)) and all(bool(torch.isfinite(g).all()) for g in g1)
+    res2, loss2, g2 = step()
+    assert torch.equal(res2["rgb_coarse"], res["rgb_coarse"]) and float(loss2) == float(loss)      # same draws -> same bits
+    for a, bb in zip(g1, g2):
+        assert float((a - bb).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12
+
+
+def test_full_size_inference_chunk_and_shard_independence():
+    """BASELINE config 4 shape: one 262144-ray chunk of the image render.  A ray's outputs must not depend on how
+    the image is chunked or sharded (same per-ray draws): chunk sizes 262144 / 65536 / 1000 give the same pixels."""
+    from spnerf_b200 import config, inference as image_inference
+    args = config.make_args(sem=True, num_sem_classes=3, chunk=262144)
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    models = {"coarse": model.to(DEV)}
+    b = 262144
+    img = synthetic.make_batch(b, seed=41, shuffled=False, device=DEV)
+
+    class PerRay:                      # draws that depend on the ray index only, whatever the chunking
+        def __init__(self, table):
+            self.table, self.pos = table, 0
+
+        def uniform(self, shape):
+            out = self.table[self.pos:self.pos + shape[0]]
+            self.pos += shape[0]
+            return out
+
+        def normal(self, shape):
+            raise AssertionError("no noise in test mode")
+
+    table = torch.rand(b, args.n_samples, device=DEV)
+    outs = []
+    for chunk in (262144, 65536, 1000):
+        args._rng = PerRay(table)
+        outs.append(image_inference.render_image(models, args, img["rays"], None, semantics=img["sems"], chunk=chunk))
+    ref = outs[0]
+    assert ref["rgb"].shape == (b, 3) and ref["sem_class"].shape == (b,)
+    assert float(ref["rgb"].min()) >= 0 and float(ref["rgb"].max()) <= 1
+    assert bool(torch.isfinite(ref["depth"]).all()) and float(ref["depth"].min()) >= 0
+    assert bool(((ref["sun"] >= 0) & (ref["sun"] <= 1 + 1e-5)).all())            # sum_i w_i sun_i with sum w = 1, sun in [0,1]
+    assert int(ref["sem_class"].min()) >= 0 and int(ref["sem_class"].max()) <= 2
+    for o in outs[1:]:
+        for k in ref:
+            assert torch.equal(o[k], ref[k]), k
