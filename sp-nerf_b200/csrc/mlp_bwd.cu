@@ -208,7 +208,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         if (p.sem)
           for (int c = 0; c < p.n_classes; ++c) g_lg[c] = go[p.col_sem + c];
       }
-      sync.drain_stores();
       // small-gradient slab [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)] (scaled), the B operand
       // of the tiny last-layer weight gradients; bias gradients of those layers are reduced right here
       if (cg == 0 && tile_ok) {
@@ -348,7 +347,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       tc_fence_before();
       epi_bar_sync();
     }
-    sync.finish();
   }
   teardown(tmem_base);
 }

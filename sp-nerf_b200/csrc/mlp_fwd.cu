@@ -123,7 +123,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 
       // ---- encoded input [PE(xyz) | label embedding] as fp16 hi + residual, and the aux operand ----
       sync.stamp();
-      sync.drain_stores();
       {
         float q[3] = {0.f, 0.f, 0.f}, sun[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -315,7 +314,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // no signal: the next tile's input phase releases the MMA warp
       sync.end(false);
     }
-    sync.finish();
   }
   teardown(tmem_base);
 }

@@ -200,7 +200,6 @@ struct EpiSync {
   const Smem& s;
   bool issuer;
   uint32_t mma_par = 0;
-  bool stores_pending = false;
   long long* prof;        // optional phase clock log (block 0 only)
   int prof_i = 0;
   uint32_t epi_remote;    // rank 1: the issuer CTA's bar_epi
@@ -212,44 +211,12 @@ struct EpiSync {
   __device__ __forceinline__ void stamp() {
     if (prof && prof_i < 256) prof[prof_i++] = clock64();
   }
-  // Activation slabs leave through bulk stores issued one slab at a time while the issuer thread
-  // waits for the next MMA phase: the copy engine serves loads and stores in order, and a 128 KB
-  // store in front of the weight ring's loads stalled the tensor pipe for thousands of cycles.
-  struct Pending { uint8_t* dst; const uint8_t* src; int n; };
-  Pending q[2];
-  int nq = 0;
-  __device__ __forceinline__ bool issue_one() {      // issuer thread only
-    if (nq == 0) return false;
-    bulk_s2g(q[0].dst, q[0].src, kSlabBytes);
-    bulk_commit();
-    q[0].dst += kSlabBytes; q[0].src += kSlabBytes;
-    if (--q[0].n == 0) { q[0] = q[1]; --nq; }
-    return true;
-  }
-  __device__ __forceinline__ void drain_stores() {   // all pending stores issued and their slabs read
-    if (stores_pending) {
-      if (issuer) { while (issue_one()) {} bulk_wait_read<0>(); }
-      epi_bar_sync();
-      stores_pending = false;
-    }
-  }
   // Wait for the MMA phase that feeds this epilogue.  One thread polls the mbarrier and the rest
   // block on the named barrier: 512 pollers on one mbarrier starve the producer's and the issuer's
   // own barrier traffic.
   __device__ __forceinline__ void begin() {
-    if (issuer) {
-      bool done = false;
-      while (!done && issue_one()) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < 600) {
-          if (mbar_try_wait(s.bar_mma, mma_par)) { done = true; break; }
-        }
-      }
-      if (!done) mbar_wait(s.bar_mma, mma_par, 30);
-      if (stores_pending) { while (issue_one()) {} bulk_wait_read<0>(); }
-    }
+    if (issuer) mbar_wait(s.bar_mma, mma_par, 30);
     mma_par ^= 1;
-    stores_pending = false;
     epi_bar_sync();
     tc_fence_after();
     stamp();
@@ -265,13 +232,6 @@ struct EpiSync {
     }
     stamp();
   }
-  // after end(): queue `nslabs` activation slabs (starting at slab0) for streaming to global memory
-  __device__ __forceinline__ void store_slabs(uint8_t* dst, int slab0, int nslabs) {
-    if (!dst) return;
-    if (issuer) { q[nq].dst = dst; q[nq].src = s.act + slab0 * kSlabBytes; q[nq].n = nslabs; ++nq; }
-    stores_pending = true;
-  }
-  __device__ __forceinline__ void finish() { if (issuer) { while (issue_one()) {} bulk_wait_all<0>(); } }
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
