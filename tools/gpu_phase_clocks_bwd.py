@@ -28,6 +28,11 @@ L.spnerf_debug_phase_clocks_bwd(None)
 L.spnerf_debug_counters_wgrad(None)
 w = wb.cpu().view(80, 8).tolist()
 print("wgrad pairs: (tiles, total kclk, clk/tile)", [(r[3], r[4] // 1000, r[4] // max(r[3], 1)) for r in w[:74]])
+act = [r for r in w[:74] if r[3]]
+tot = sum(r[4] for r in act)
+print("wgrad issuer totals over %d pairs: wait_full %.1f%%  wait_drained %.1f%%  issue %.1f%%  (of %d Mclk), tiles/pair min %d max %d, clk/pair min %d k max %d k" % (
+    len(act), 100.0 * sum(r[0] for r in act) / tot, 100.0 * sum(r[1] for r in act) / tot, 100.0 * sum(r[2] for r in act) / tot,
+    tot // 1000000, min(r[3] for r in act), max(r[3] for r in act), min(r[4] for r in act) // 1000, max(r[4] for r in act) // 1000))
 t = buf.cpu().tolist()
 st = [x for x in t[:256] if x]
 d = [st[i + 1] - st[i] for i in range(len(st) - 1)]
