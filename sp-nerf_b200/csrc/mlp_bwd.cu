@@ -194,9 +194,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       float g_u[3] = {0.f, 0.f, 0.f}, g_v = 0.f, g_sp = 0.f, g_bp = 0.f, g_lg[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) g_lg[c] = 0.f;
+      {
+        // The tile's rows of g_out / out (n_out floats per point, contiguous over the tile) are staged through
+        // activation slab 7 with coalesced 16-byte loads: a per-thread row read has a 4 n_out byte stride
+        // (44 sectors per warp-level load, 22 loads per thread, all four column groups reading the same rows)
+        // and cost ~15 k cycles per tile with the tensor pipe idle.  Slabs 4..7 are free here: every thread has
+        // passed the barrier of the previous tile's last begin().
+        float* stage_go = reinterpret_cast<float*>(act + 7 * kSlabBytes);
+        float* stage_o = stage_go + kTileM * 16;
+        const int etid = (int)threadIdx.x - kEpiWarp0 * 32;
+        const int64_t p0 = tile * kTileM;
+        const int nrow = tile_ok ? (int)min((int64_t)kTileM, p.n_points - p0) : 0;
+        const int nflt = nrow * p.n_out;
+        const float* src_go = p.g_out + p0 * p.n_out;
+        const float* src_o = p.out + p0 * p.n_out;
+        if (((p0 * p.n_out) & 3) == 0) {                       // 16-byte aligned tile start (always: 128 * n_out floats)
+          for (int i = etid * 4; i < nflt; i += kEpiThreads * 4) {
+            if (i + 4 <= nflt) {
+              *reinterpret_cast<float4*>(stage_go + i) = ldg4(src_go + i);
+              *reinterpret_cast<float4*>(stage_o + i) = ldg4(src_o + i);
+            } else {
+              for (int e = i; e < nflt; ++e) { stage_go[e] = __ldg(src_go + e); stage_o[e] = __ldg(src_o + e); }
+            }
+          }
+        } else {
+          for (int i = etid; i < nflt; i += kEpiThreads) { stage_go[i] = __ldg(src_go + i); stage_o[i] = __ldg(src_o + i); }
+        }
+        epi_bar_sync();
+      }
       if (valid) {
-        const float* go = p.g_out + pt * p.n_out;
-        const float* o = p.out + pt * p.n_out;
+        const float* go = reinterpret_cast<const float*>(act + 7 * kSlabBytes) + row * p.n_out;
+        const float* o = go + kTileM * 16;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {                  // rgb = sigmoid(u)*1.002 - 0.001  (spnerf.py:346-347)
           const float s = (o[c] + 0.001f) / 1.002f;
