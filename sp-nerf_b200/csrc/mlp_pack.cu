@@ -159,6 +159,37 @@ struct Builder {
       off16 += (uint32_t)(n * 32 / 16);
     }
   }
+  // Fuses the K-slab steps of the chunk that was just added into ONE ring item (n <= 16 only: 2 KB per slab,
+  // so all slabs fit a ring stage).  A 16-wide product over K = 512 is 8 items of 32 cycles of tensor work
+  // each, but every item costs the issuer a full wait / issue / commit round trip (~750 cycles alone).
+  // The blob keeps each CTA's half of every slab contiguous: [rank 0: slab 0..S-1][rank 1: slab 0..S-1].
+  void merge_last_chunk() {
+    const size_t c0 = chunk_begin.back(), ns = steps.size() - c0;
+    if (ns < 2) return;
+    const MmaStep f = steps[c0];
+    const size_t i0 = items.size() - ns;
+    const uint32_t half16 = (uint32_t)(f.n / 2) * 128 / 16;          // one CTA's half of one slab, 16-byte units
+    std::vector<PackItem> halves;
+    for (size_t k = 0; k < ns; ++k) {
+      for (int r = 0; r < 2; ++r) {
+        PackItem h = items[i0 + k];
+        h.n = f.n / 2;
+        if (h.transpose) h.col0 += r * (f.n / 2); else h.row0 += r * (f.n / 2);
+        h.dst_row0 = 0;
+        h.dst_off16 = f.w_off16 + (uint32_t)r * (uint32_t)ns * half16 + (uint32_t)k * half16;
+        halves.push_back(h);
+      }
+    }
+    items.resize(i0);
+    items.insert(items.end(), halves.begin(), halves.end());
+    MmaStep m = f;
+    m.ksteps = 0;
+    uint32_t b16 = 0;
+    for (size_t k = 0; k < ns; ++k) { m.ksteps = (uint8_t)(m.ksteps + steps[c0 + k].ksteps); b16 += steps[c0 + k].bytes16; }
+    m.bytes16 = (uint16_t)b16;
+    steps.resize(c0);
+    steps.push_back(m);
+  }
   // Closes a phase.  Its chunks (independent accumulator column ranges) are dealt to the two issuer
   // lanes, balancing step counts, and the ring order interleaves the lanes so that both issuers
   // always have an item in flight.  The order of the steps inside a chunk is preserved.
@@ -573,6 +604,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     const int cols = kFeat + (skip ? d.in_dim : 0);
     if (skip && c.sem) {
       b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, kFeat + base, 16, 0, ks(0, 8), true);
+      b.merge_last_chunk();
       b.end_phase();
     }
     for (int g = 0; g < 2; ++g)
@@ -581,6 +613,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   }
   if (c.sem) {
     b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, base, 16, 0, ks(0, 8), true);
+    b.merge_last_chunk();
     b.end_phase();
   }
   steps = b.steps;

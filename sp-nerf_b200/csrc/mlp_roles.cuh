@@ -170,10 +170,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
               if (a_slab == kAuxSlab) {
                 umma2_f16(tmem_base + tcol, smem_desc(tmpl_aux, aux_addr), smem_desc(tmpl_aux, b0), idesc, first ? 0u : 1u);
               } else {
-                const uint32_t a0 = act_addr + a_slab * kSlabBytes;
+                // K = 16 steps: 4 per 64-wide slab; a fused item (mlp_pack.cu merge_last_chunk) runs on over the
+                // following A slabs, its B tiles (this CTA's n / 2 rows x 128 bytes per slab) back to back
+                const uint32_t a0 = act_addr + a_slab * kSlabBytes, b_slab = (n >> 1) * 128u;
                 for (uint32_t k = 0; k < ksteps; ++k)
-                  umma2_f16(tmem_base + tcol, smem_desc(tmpl, a0 + k * 32), smem_desc(tmpl, b0 + k * 32), idesc,
-                            (first && k == 0) ? 0u : 1u);
+                  umma2_f16(tmem_base + tcol, smem_desc(tmpl, a0 + (k >> 2) * kSlabBytes + (k & 3) * 32),
+                            smem_desc(tmpl, b0 + (k >> 2) * b_slab + (k & 3) * 32), idesc, (first && k == 0) ? 0u : 1u);
               }
             }
             umma2_commit(&s.bar_empty[stage]);

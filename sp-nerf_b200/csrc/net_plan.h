@@ -44,7 +44,7 @@ struct __align__(16) MmaStep {
   uint16_t n;         // B rows (accumulator columns) of this item
   uint16_t tmem_col;  // first accumulator column
   uint8_t a_slab;     // shared-memory slab holding the A operand, or kAuxSlab
-  uint8_t ksteps;     // K=16 instructions to issue from this slab (1..4)
+  uint8_t ksteps;     // K=16 instructions to issue: 1..4 from this slab, more for an item fused over following slabs
   uint8_t first;      // 1: overwrite the accumulator (first item of a chunk)
   uint8_t last;       // 1: last item of a phase (in ring order) -> both issuers signal the epilogue
   uint16_t bytes16;   // item size in 16-byte units
