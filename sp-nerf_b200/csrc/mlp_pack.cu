@@ -159,36 +159,47 @@ struct Builder {
       off16 += (uint32_t)(n * 32 / 16);
     }
   }
-  // Fuses the K-slab steps of the chunk that was just added into ONE ring item (n <= 16 only: 2 KB per slab,
-  // so all slabs fit a ring stage).  A 16-wide product over K = 512 is 8 items of 32 cycles of tensor work
-  // each, but every item costs the issuer a full wait / issue / commit round trip (~750 cycles alone).
-  // The blob keeps each CTA's half of every slab contiguous: [rank 0: slab 0..S-1][rank 1: slab 0..S-1].
-  void merge_last_chunk() {
-    const size_t c0 = chunk_begin.back(), ns = steps.size() - c0;
-    if (ns < 2) return;
-    const MmaStep f = steps[c0];
-    const size_t i0 = items.size() - ns;
-    const uint32_t half16 = (uint32_t)(f.n / 2) * 128 / 16;          // one CTA's half of one slab, 16-byte units
+  // Fuses runs of `per_item` consecutive K-slab steps of the chunk that was just added into one ring item each
+  // (the fused B tiles of one CTA, per_item * (n / 2) * 128 bytes, must fit a ring stage).  A narrow product is
+  // little tensor work per slab (n = 16: 32 cycles, n = 128: 256 cycles) but every ring item costs the issuer a
+  // full wait / issue / commit round trip (~550-750 cycles).  The blob keeps each CTA's half of the fused slabs
+  // contiguous: [rank 0: slab 0..S-1][rank 1: slab 0..S-1].  An aux step at the end of the chunk stays as it is.
+  void merge_last_chunk(int per_item) {
+    const size_t c0 = chunk_begin.back();
+    size_t ns = steps.size() - c0;
+    const bool has_aux = ns > 0 && steps.back().a_slab == kAuxSlab;
+    const MmaStep aux_step = steps.back();
+    if (has_aux) --ns;
+    if (ns < 2 || per_item < 2) return;
+    const size_t i0 = items.size() - ns;                            // aux steps have no PackItem
+    std::vector<MmaStep> fused;
     std::vector<PackItem> halves;
-    for (size_t k = 0; k < ns; ++k) {
-      for (int r = 0; r < 2; ++r) {
-        PackItem h = items[i0 + k];
-        h.n = f.n / 2;
-        if (h.transpose) h.col0 += r * (f.n / 2); else h.row0 += r * (f.n / 2);
-        h.dst_row0 = 0;
-        h.dst_off16 = f.w_off16 + (uint32_t)r * (uint32_t)ns * half16 + (uint32_t)k * half16;
-        halves.push_back(h);
+    for (size_t g0 = 0; g0 < ns; g0 += (size_t)per_item) {
+      const size_t gn = std::min(ns - g0, (size_t)per_item);
+      MmaStep m = steps[c0 + g0];
+      const uint32_t half16 = (uint32_t)(m.n / 2) * 128 / 16;       // one CTA's half of one slab, 16-byte units
+      uint32_t b16 = 0, ks = 0;
+      for (size_t k = 0; k < gn; ++k) {
+        const MmaStep& st = steps[c0 + g0 + k];
+        b16 += st.bytes16; ks += st.ksteps;
+        for (int r = 0; r < 2; ++r) {
+          PackItem h = items[i0 + g0 + k];
+          h.n = m.n / 2;
+          if (h.transpose) h.col0 += r * (m.n / 2); else h.row0 += r * (m.n / 2);
+          h.dst_row0 = 0;
+          h.dst_off16 = m.w_off16 + (uint32_t)r * (uint32_t)gn * half16 + (uint32_t)k * half16;
+          halves.push_back(h);
+        }
       }
+      m.ksteps = (uint8_t)ks;
+      m.bytes16 = (uint16_t)b16;
+      fused.push_back(m);
     }
     items.resize(i0);
     items.insert(items.end(), halves.begin(), halves.end());
-    MmaStep m = f;
-    m.ksteps = 0;
-    uint32_t b16 = 0;
-    for (size_t k = 0; k < ns; ++k) { m.ksteps = (uint8_t)(m.ksteps + steps[c0 + k].ksteps); b16 += steps[c0 + k].bytes16; }
-    m.bytes16 = (uint16_t)b16;
     steps.resize(c0);
-    steps.push_back(m);
+    steps.insert(steps.end(), fused.begin(), fused.end());
+    if (has_aux) steps.push_back(aux_step);
   }
   // Closes a phase.  Its chunks (independent accumulator column ranges) are dealt to the two issuer
   // lanes, balancing step counts, and the ring order interleaves the lanes so that both issuers
@@ -282,9 +293,11 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     b.end_phase();
   }
   for (int j = 1; j <= 2; ++j) {      // sun layers 1, 2: two 128-wide chunks, one per issuer lane
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < 2; ++g) {
       b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, act8(kHalf), false, false,
               aux_bias(P[SPNERF_P_SUN0_W + 2 * j + 1], kHalf));
+      b.merge_last_chunk(2);          // 128-wide chunks: two K slabs (2 x 8 KB per CTA) per ring item
+    }
     b.end_phase();
   }
 }
@@ -568,8 +581,10 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   };
   // sun_v_net.4 and .2 (256x256): G_s3 -> g_s2 -> g_s1
   for (int j = 2; j >= 1; --j) {      // two 128-wide chunks, one per issuer lane
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < 2; ++g) {
       b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, ks(0, 4), true);
+      b.merge_last_chunk(2);
+    }
     b.end_phase();
   }
   // g_f = G_s1 * W_sun0[:, :512] + G_r1 * W_rgb0 (+ G_b1 * W_beta0[:, :512] in a second phase)
@@ -604,7 +619,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     const int cols = kFeat + (skip ? d.in_dim : 0);
     if (skip && c.sem) {
       b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, kFeat + base, 16, 0, ks(0, 8), true);
-      b.merge_last_chunk();
+      b.merge_last_chunk(8);
       b.end_phase();
     }
     for (int g = 0; g < 2; ++g)
@@ -613,7 +628,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   }
   if (c.sem) {
     b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, base, 16, 0, ks(0, 8), true);
-    b.merge_last_chunk();
+    b.merge_last_chunk(8);
     b.end_phase();
   }
   steps = b.steps;
