@@ -254,21 +254,34 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     }
     b.end_phase();
   }
-  // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212)
-  if (c.sem) b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat), false, false,
-                     aux_bias(P[SPNERF_P_SEM0_B], kHalf));
+  // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212).  The 256-wide hidden layer
+  // runs as two 128-wide chunks, one per issuer (a single 256-wide chunk left one issuer alone with 9 items, which
+  // it cannot issue at the tensor pipe's pace), two K slabs per ring item; the 1-wide sigma head is one fused item.
+  if (c.sem)
+    for (int g = 0; g < 2; ++g) {
+      b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, g * 128, 128, g * 128, act8(kFeat), false, false,
+              aux_bias(P[SPNERF_P_SEM0_B], kHalf));
+      b.merge_last_chunk(2);
+    }
   {
     // sigma: B row 0 = fp16(w), row 1 = residual; the epilogue adds the two accumulator columns
     auto srcs = act8(kFeat);
     const size_t i0 = b.items.size();
     b.chunk(P[SPNERF_P_SIGMA_W], 1, kFeat, 0, 16, kHalf, srcs, false, false, aux_bias(P[SPNERF_P_SIGMA_B], 1));
+    b.merge_last_chunk(8);            // PackItems are now per (slab, CTA half): rank 0's half holds rows 0..7
     const size_t i1 = b.items.size();
+    std::vector<PackItem> kept;
     for (size_t i = i0; i < i1; ++i) {
-      b.items[i].n = 1;
-      PackItem lo = b.items[i];
+      PackItem hi = b.items[i];
+      if (hi.row0 != 0) continue;     // rank 1's rows 8..15: never read (accumulator columns 264..271 are unused)
+      hi.n = 1;
+      PackItem lo = hi;
       lo.mode = 1; lo.dst_row0 = 1;
-      b.items.push_back(lo);
+      kept.push_back(hi);
+      kept.push_back(lo);
     }
+    b.items.resize(i0);
+    b.items.insert(b.items.end(), kept.begin(), kept.end());
   }
   b.end_phase();
   for (int g = 0; g < 2; ++g)   // feats_from_xyz (:215)
