@@ -157,12 +157,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
   }
   const float inv_scale = 1.f / scale;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
-  } else if (warp == 1 || warp == 2) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
-    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
+  } else if (warp < 16) {
     const int cg = (warp - kEpiWarp0) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);

@@ -91,12 +91,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
-  } else if (warp == 1 || warp == 2) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - 1, n_iters, p.debug, p.prof);
-    else if (warp == 1) relay_loop(sh, p.tab.n, n_iters, p.debug);
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
+  } else if (warp < 16) {
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
     const int row = (warp & 3) * 32 + lane;    // TMEM lane quarter = warp % 4
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);

@@ -5,16 +5,19 @@
 // points (its activations are the A rows 128*rank.. of an M = 256 MMA) and streams only half of
 // every weight tile (B rows (n/2)*rank..), so a weight byte fetched from L2 feeds 256 points.
 // 640 threads per CTA, one CTA per SM:
-//   warp 0        weight producer (one lane): 1-D bulk copies of this CTA's half of the pre-packed
+//   warps 0-15    epilogue: warp w reads TMEM lanes 32*(w%4).., i.e. point row 32*(w%4)+lane, and
+//                 column group w/4 of the phase's accumulator
+//   warp 16       weight producer (one lane): 1-D bulk copies of this CTA's half of the pre-packed
 //                 fp16 B tiles into a 4-stage ring
-//   warps 1, 2    rank 0: the two MMA issuers (tcgen05.mma M=256, N<=256, K=16, fp16 -> fp32 in TMEM).
+//   warps 17, 18  rank 0: the two MMA issuers (tcgen05.mma M=256, N<=256, K=16, fp16 -> fp32 in TMEM).
 //                 Every phase is split into accumulator chunks owned by one issuer each (MmaStep::lane),
 //                 interleaved in ring order: one thread cannot issue 4 MMAs + a commit + a barrier
 //                 wait in the 512 cycles the tensor pipe needs for them (measured ~710).
-//                 rank 1, warp 1: relay, forwards "my ring stage landed" to the issuers
-//   warp 3        idle (keeps the epilogue warps aligned to TMEM lane quarters)
-//   warps 4-19    epilogue: warp w reads TMEM lanes 32*(w%4).., i.e. point row 32*(w%4)+lane, and
-//                 column group (w-4)/4 of the phase's accumulator
+//                 rank 1, warp 17: relay, forwards "my ring stage landed" to the issuers
+//   warp 19       idle
+// The control warps sit ABOVE the epilogue warps: with the same code and the control warps at ids 0-2 the
+// kernels were 1-2 % slower (the issuers' few instructions queue behind the epilogue warps of their
+// scheduler when the phases overlap at their edges: copy-out, window loads).
 #pragma once
 #include "sm100.cuh"
 #include "net_plan.h"
@@ -25,7 +28,8 @@ using namespace net;
 
 constexpr int kThreads = 640;
 constexpr int kEpiThreads = 512;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 0;       // epilogue warps 0..15
+constexpr int kProducerWarp = 16, kIssuerWarp0 = 17, kIssuerWarp1 = 18;
 constexpr int kColGroups = 4;
 
 struct Smem {
@@ -70,7 +74,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
     bulk_g2s(smem + kOffRgb2, smallw, 3072 * 4, s.bar_par);              // rgb2 | sem2
     bulk_g2s(smem + kOffSun6, smallw + 3072, 512 * 4, s.bar_par);        // sun6 | beta2
   }
-  if (warp == 1) { tmem_alloc2(s.tmem_slot, 512); tmem_relinquish2(); }
+  if (warp == kIssuerWarp0) { tmem_alloc2(s.tmem_slot, 512); tmem_relinquish2(); }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -80,7 +84,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   tc_fence_before();
   cluster_sync_all();      // the peer may still be signalling this CTA's barriers / reading its operands
-  if ((threadIdx.x >> 5) == 1) tmem_dealloc2(tmem_base, 512);
+  if ((threadIdx.x >> 5) == kIssuerWarp0) tmem_dealloc2(tmem_base, 512);
 }
 
 // number of tile pairs this cluster processes
