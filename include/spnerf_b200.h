@@ -163,8 +163,10 @@ typedef struct SpnerfMlpFwd {
   const float* small;
   float* out;             /* (n_rays*n_samples, n_out) fp32, reference column order            */
   void* saves;            /* activation save area or NULL (inference)                          */
-  int32_t debug_flags;    /* must be 0.  Timing experiments only (results invalid): 1 = skip the
-                             weight copies, 2 = skip the epilogue arithmetic, 4 = skip the MMAs  */
+  int32_t debug_flags;    /* must be 0.  Timing experiments only: 1 = skip the weight copies, 2 = skip
+                             the epilogue arithmetic, 4 = skip the MMAs (results invalid); 128 = copy half
+                             of every saved tile out of shared memory during the next MMA phase instead
+                             of storing all of it from registers (same results, slower)             */
   int32_t _pad;
 } SpnerfMlpFwd;
 int spnerf_mlp_fwd(const SpnerfMlpFwd* args, void* stream);

@@ -214,17 +214,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.begin();
       // half of the tile leaves from registers during the epilogue, the other half from shared memory
       // during the next MMA phase: global stores are the scarce resource (~13 B/cycle/SM chip-wide)
-      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]), cg < 2 ? sv(p.sm.y[0]) : nullptr,
-                        NoEach());
+      // The saved copy of every activation tile leaves from registers during the epilogue.  (Copying half of it out
+      // of shared memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy
+      // competes with the MMAs for shared-memory bandwidth.  debug & 128 selects that variant.)
+      const bool direct_all = !(p.debug & 128);
+      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]),
+                        (cg < 2 || direct_all) ? sv(p.sm.y[0]) : nullptr, NoEach());
       sync.end(true);
-      copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
+      if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
       // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
         sync.begin();
         epi_cols<0, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
-                          cg < 2 ? sv(p.sm.y[i]) : nullptr, NoEach());
+                          (cg < 2 || direct_all) ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
-        copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
+        if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
       }
       // ---- heads on h: semantic hidden (accumulator columns 0..255) and sigma (256, 257) ----
       sync.begin();
@@ -256,9 +260,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
       sync.begin();
-      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr, cg < 2 ? sv(p.sm.f) : nullptr, NoEach());
+      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr,
+                        (cg < 2 || direct_all) ? sv(p.sm.f) : nullptr, NoEach());
       sync.end(true);
-      copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
+      if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
 
       // ---- albedo hidden layer (columns 0..255) + first sun layer or beta hidden layer (256..511) ----
       sync.begin();

@@ -157,6 +157,10 @@ def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, 
     return out, g_rgb, g_depth, g_sem
 
 
+import os as _os
+_ENV_DEBUG = int(_os.environ.get("SPNERF_DEBUG_FLAGS", "0"))     # kernel timing experiments only (include/spnerf_b200.h)
+
+
 def adam_step(flat_params, flat_grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8):
     """torch.optim.Adam(weight_decay=0) on flat fp32 buffers in one launch (main.py:96-97)."""
     _require_cuda(flat_params, "parameters")
@@ -280,7 +284,7 @@ class NetEngine:
         a.labels, a.t_emb, a.sky = _p(labels), _p(t_emb), _p(sky)
         a.n_rays, a.n_samples, a.n_steps = n_rays, n_samples, self.sizes.fwd_steps
         a.blob, a.steps, a.small = _p(self.fwd_blob), _p(self.fwd_steps), _p(self.small)
-        a.out, a.saves, a.debug_flags = _p(out), _p(saves), debug_flags
+        a.out, a.saves, a.debug_flags = _p(out), _p(saves), debug_flags | _ENV_DEBUG
         _cabi.check(_cabi.lib().spnerf_mlp_fwd(ctypes.byref(a), _stream()), "spnerf_mlp_fwd")
         return out, saves
 
@@ -321,7 +325,7 @@ class NetEngine:
         a.blob, a.steps, a.small = _p(self.bwd_blob), _p(self.bwd_steps), _p(self.small)
         a.saves, a.grad_saves, a.g_absmax, a.scale_out = _p(saves), _p(gsaves), _p(absmax), _p(scale)
         a.g_emb = _p(by_name.get("semantic_embedding.weight"))
-        a.g_small_bias, a.g_t_emb, a.debug_flags = _p(small_bias), _p(g_t), debug_flags
+        a.g_small_bias, a.g_t_emb, a.debug_flags = _p(small_bias), _p(g_t), debug_flags | _ENV_DEBUG
         _cabi.check(_cabi.lib().spnerf_mlp_bwd_data(ctypes.byref(a), _stream()), "spnerf_mlp_bwd_data")
         if timer is not None:
             timer.mark("mlp_bwd_data")
