@@ -275,9 +275,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         };
         if (!p.beta) {
           // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
-          // 0..3, the albedo activations are staged in slabs 4..7; both leave during the next MMA phase
-          epi_cols<0, true>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), nullptr, rgb_each);
-          epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), nullptr, NoEach());
+          // 0..3, the albedo activations to slabs 4..7 (only read back by the debug & 128 copy-out variant)
+          epi_cols<0, true>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
+          epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
+                            NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
           // feats stay live for the sun layer of the next phase: nothing may be written to the slabs
@@ -297,16 +298,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       if (p.beta) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), nullptr, NoEach());
+        epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
         sync.end(true);
       }
-      copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[0]));
-      if (!p.beta) copy_slabs_out(act, 4, 4, sv(p.sm.rgb_y));
+      if (!direct_all) {
+        copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[0]));
+        if (!p.beta) copy_slabs_out(act, 4, 4, sv(p.sm.rgb_y));
+      }
       // ---- sun layer 1 ----
       sync.begin();
-      epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[1]), nullptr, NoEach());
+      epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
       sync.end(true);
-      copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[1]));
+      if (!direct_all) copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[1]));
       // ---- sun layer 2 + output unit (256 -> 1, sigmoid) ----
       sync.begin();
       {
