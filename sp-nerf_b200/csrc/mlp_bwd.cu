@@ -345,13 +345,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       for (int L = 7; L >= 0; --L) {
         ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
         sync.begin();
-        // half of the gradient tile leaves from registers now, half from shared memory during the next MMAs
-        uint8_t* gdirect = cg < 2 ? gs(p.gm.G[L]) : nullptr;
+        // three of the four column groups store their part of the gradient tile from registers, the last quarter is
+        // copied out of shared memory during the next MMAs (alternating A/B on one box: 2 groups 4.68 ms, 3 groups
+        // 4.60, all four 4.72; debug & 256 / 512 select 2 / 1 groups)
+        const int ndirect = (p.debug & 256) ? 2 : (p.debug & 512) ? 1 : 3;
+        uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
         if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
         else       bwd_columns<1, 8>(taddr, cg * 128, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
-        copy_slabs_out(act, 4, 4, gs(p.gm.G[L] + 4));
+        copy_slabs_out(act, 2 * ndirect, 8 - 2 * ndirect, gs(p.gm.G[L] + 2 * ndirect));
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }
