@@ -147,6 +147,25 @@ def time_cpu_reference(rays, steps, warmup):
     return rays * steps / dt, dt / steps, cores
 
 
+def time_cpu_reference_forward(rays, steps):
+    """Forward-only rays/s of the reference's CPU path (BASELINE config 1: render_rays in test mode)."""
+    import torch
+    from oracle import spnerf_oracle as O
+    from spnerf_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)
+    P = O.random_parameters(cfg, seed=0, sigma_bias=3.0)
+    batch = synthetic.make_batch(rays, seed=269)
+    b, n = rays, cfg.n_samples
+    with torch.no_grad():
+        O.render(P, cfg, batch["rays"], None, batch["sems"], "test", None, None, None, O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.render(P, cfg, batch["rays"], None, batch["sems"], "test", None, None, None, O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
+        dt = time.perf_counter() - t0
+    return rays * steps / dt
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -454,7 +473,11 @@ def run_ours(a):
         # ---- the reference's CPU path on this box's host cores (bounded sample) ----
         try:
             rps, sec, cores = time_cpu_reference(1024, 3, 1)
-            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+            try:
+                fwd_rps = time_cpu_reference_forward(1024, 3)
+            except Exception:          # pragma: no cover
+                fwd_rps = None
+            line["cpu_baseline"] = {"value": rps, "forward_only_value": fwd_rps, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": "3 steps x 1024 rays x 64 samples (BASELINE config 1 shape), fwd + "
                                               "losses + bwd, torch fp32 oracle restatement of the reference"}
         except Exception as ex:          # pragma: no cover
