@@ -41,7 +41,9 @@ struct FwdParams {
 // ysave: copy of y (fp16) in the row-interleaved layout, which the weight-gradient GEMMs read as a
 //        no-swizzle MN-major operand (mlp_wgrad.cu); used where y does not pass through shared memory
 // `each(j, y)` is called for every output (tiny last layers).
-template <int ACT, bool TO_SMEM, class Each>
+// BITS: compute and save the derivative sign bits (training); the inference instantiation drops the two
+//       instructions per element they cost
+template <int ACT, bool TO_SMEM, bool BITS, class Each>
 __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, int dst_col0, int row, uint8_t* ssave,
                                           uint8_t* ysave, Each each) {
   uint32_t v[32];
@@ -59,7 +61,7 @@ __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, 
       else {
         const float a = (ACT == 1) ? 30.f * x : x;
         y[e] = __sinf(a);
-        sb = __funnelshift_r(sb, __float_as_uint(fmaf(a, 0.318309886f, 12582912.f)), 1);   // bit (c*8+e) <- parity
+        if (BITS) sb = __funnelshift_r(sb, __float_as_uint(fmaf(a, 0.318309886f, 12582912.f)), 1);   // bit (c*8+e) <- parity
       }
       each(j + e, y[e]);
     }
@@ -67,14 +69,19 @@ __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, 
     if (TO_SMEM) *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + j, row)) = yp;
     if (ysave) stg16(ysave + xsave_off(j, row), yp);
   }
-  if (ACT != 2 && ssave) *reinterpret_cast<uint32_t*>(ssave + sbit_off(j0, row)) = sb;
+  if (BITS && ACT != 2) *reinterpret_cast<uint32_t*>(ssave + sbit_off(j0, row)) = sb;
 }
 
 template <int ACT, bool TO_SMEM, class Each>
 __device__ __forceinline__ void epi_cols(uint32_t taddr, int j0, int ncols, uint8_t* act, int dst_col0, int row,
                                          uint8_t* xsave, uint8_t* ysave, Each each) {
+  if (ACT != 2 && xsave) {
 #pragma unroll 1
-  for (int jb = j0; jb < j0 + ncols; jb += 32) epi_batch<ACT, TO_SMEM>(taddr, jb, act, dst_col0, row, xsave, ysave, each);
+    for (int jb = j0; jb < j0 + ncols; jb += 32) epi_batch<ACT, TO_SMEM, true>(taddr, jb, act, dst_col0, row, xsave, ysave, each);
+  } else {
+#pragma unroll 1
+    for (int jb = j0; jb < j0 + ncols; jb += 32) epi_batch<ACT, TO_SMEM, false>(taddr, jb, act, dst_col0, row, nullptr, ysave, each);
+  }
 }
 
 struct NoEach { __device__ __forceinline__ void operator()(int, float) const {} };
