@@ -43,15 +43,19 @@ struct FwdParams {
 // `each(j, y)` is called for every output (tiny last layers).
 // BITS: compute and save the derivative sign bits (training); the inference instantiation drops the two
 //       instructions per element they cost
-template <int ACT, bool TO_SMEM, bool BITS, class Each>
+// W:    accumulator columns per batch, 32 or 16.  The phases that also feed a tiny last layer through `each`
+//       use 16: with 32 accumulator values in registers next to the layer's partial sums the training variant
+//       spilled inside the loop (semantic head epilogue 17.6 k cycles against 5.8 k without the saves)
+template <int ACT, bool TO_SMEM, bool BITS, int W, class Each>
 __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, int dst_col0, int row, uint8_t* ssave,
                                           uint8_t* ysave, Each each) {
-  uint32_t v[32];
-  tmem_ld32(taddr + j0, v);
+  uint32_t v[W];
+  if (W == 32) tmem_ld32(taddr + j0, reinterpret_cast<uint32_t(&)[32]>(v));
+  else tmem_ld16(taddr + j0, reinterpret_cast<uint32_t(&)[16]>(v));
   tmem_wait_ld();
   uint32_t sb = 0;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < W / 8; ++c) {
     const int j = j0 + c * 8;
     float y[8];
 #pragma unroll
@@ -69,18 +73,21 @@ __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, 
     if (TO_SMEM) *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + j, row)) = yp;
     if (ysave) stg16(ysave + xsave_off(j, row), yp);
   }
-  if (BITS && ACT != 2) *reinterpret_cast<uint32_t*>(ssave + sbit_off(j0, row)) = sb;
+  if (BITS && ACT != 2) {
+    if (W == 32) *reinterpret_cast<uint32_t*>(ssave + sbit_off(j0, row)) = sb;
+    else *reinterpret_cast<uint16_t*>(ssave + sbit_off(j0, row) + ((j0 & 16) >> 3)) = (uint16_t)(sb >> 16);   // low half: columns 0..15
+  }
 }
 
-template <int ACT, bool TO_SMEM, class Each>
+template <int ACT, bool TO_SMEM, int W = 32, class Each>
 __device__ __forceinline__ void epi_cols(uint32_t taddr, int j0, int ncols, uint8_t* act, int dst_col0, int row,
                                          uint8_t* xsave, uint8_t* ysave, Each each) {
   if (ACT != 2 && xsave) {
 #pragma unroll 1
-    for (int jb = j0; jb < j0 + ncols; jb += 32) epi_batch<ACT, TO_SMEM, true>(taddr, jb, act, dst_col0, row, xsave, ysave, each);
+    for (int jb = j0; jb < j0 + ncols; jb += W) epi_batch<ACT, TO_SMEM, true, W>(taddr, jb, act, dst_col0, row, xsave, ysave, each);
   } else {
 #pragma unroll 1
-    for (int jb = j0; jb < j0 + ncols; jb += 32) epi_batch<ACT, TO_SMEM, false>(taddr, jb, act, dst_col0, row, nullptr, ysave, each);
+    for (int jb = j0; jb < j0 + ncols; jb += W) epi_batch<ACT, TO_SMEM, false, W>(taddr, jb, act, dst_col0, row, nullptr, ysave, each);
   }
 }
 
@@ -251,7 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = 0.f;
         const bool wide = p.n_classes > 4;
-        epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, (p.debug & 32) ? nullptr : sv(p.sm.sem_x),
+        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, (p.debug & 32) ? nullptr : sv(p.sm.sem_x),
                            (p.debug & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
           const float4 w = Wsem2[j * 2];
           lg[0] = fmaf(w.x, y, lg[0]); lg[1] = fmaf(w.y, y, lg[1]); lg[2] = fmaf(w.z, y, lg[2]); lg[3] = fmaf(w.w, y, lg[3]);
@@ -283,15 +290,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         if (!p.beta) {
           // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
           // 0..3, the albedo activations to slabs 4..7 (only read back by the debug & 128 copy-out variant)
-          epi_cols<0, true>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
+          epi_cols<0, true, 16>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
           epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
                             NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
           // feats stay live for the sun layer of the next phase: nothing may be written to the slabs
           float bsum[1] = {0.f};
-          epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
-          epi_cols<0, false>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
+          epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
+          epi_cols<0, false, 16>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
                              [&](int j, float y) { bsum[0] = fmaf(Wbeta2[j], y, bsum[0]); });
           float r4[4] = {c3[0], c3[1], c3[2], bsum[0]};
           reduce_groups<4>(scratch, r4, cg, row);
@@ -321,7 +328,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.begin();
       {
         float part[1] = {0.f};
-        epi_cols<0, false>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
+        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
                            [&](int j, float y) { part[0] = fmaf(Wsun6[j], y, part[0]); });
         reduce_groups<1>(scratch, part, cg, row);
         if (cg == 0 && valid) orow[4] = sigmoid_ref(part[0] + S[p.so.sun6_b]);   // spnerf.py:352
