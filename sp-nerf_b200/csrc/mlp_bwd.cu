@@ -109,19 +109,20 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
 template <class CoefW, class Each>
 __device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, const uint8_t* ysave, const uint8_t* ssave,
                                             uint8_t* act, int dst_col0, int row, Each each) {
+  // 16-column batches, the next one requested before the current one is used (the saved activations come
+  // straight from HBM and nothing else runs on the SM during these phases)
+  YBatch nxt = ybatch_load(ysave, ssave, j0, row);
 #pragma unroll 1
-  for (int jb = j0; jb < j0 + ncols; jb += 32) {
-    uint4 yr[4];
+  for (int jb = j0; jb < j0 + ncols; jb += 16) {
+    const YBatch cur = nxt;
+    if (jb + 16 < j0 + ncols) nxt = ybatch_load(ysave, ssave, jb + 16, row);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) yr[c] = ldg16(ysave + xsave_off(jb + c * 8, row));
-    const uint32_t sb = __ldg(reinterpret_cast<const uint32_t*>(ssave + sbit_off(jb, row)));
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float y[8], g[8];
-      unpack8(yr[c], y);
+      unpack8(cur.y[c], y);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        g[e] = coefw(jb + c * 8 + e) * dsin(y[e], sb, c * 8 + e);
+        g[e] = coefw(jb + c * 8 + e) * dsin(y[e], cur.sb, c * 8 + e);
         each(jb + c * 8 + e, g[e]);
       }
       *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
