@@ -198,7 +198,9 @@ typedef struct SpnerfMlpBwd {
   float* g_small_bias;      /* 14 floats += : d rgb.2.bias(3), sun.6.bias, sigma.bias, beta.2.bias,
                                logit.2.bias(8); pre-zeroed                                       */
   float* g_t_emb;           /* (n_rays, t_dim) += or NULL; pre-zeroed                            */
-  int32_t debug_flags;
+  int32_t debug_flags;      /* must be 0.  Timing experiments only: 1 / 2 / 4 as in SpnerfMlpFwd (results
+                               invalid); 256 / 512 = two / one (instead of three) of the four column groups
+                               store their gradient tile part from registers (same results)          */
   int32_t _pad;
 } SpnerfMlpBwd;
 int spnerf_mlp_bwd_data(const SpnerfMlpBwd* args, void* stream);
