@@ -647,3 +647,44 @@ def test_full_size_inference_chunk_and_shard_independence():
     for o in outs[1:]:
         for k in ref:
             assert torch.equal(o[k], ref[k]), k
+
+
+@pytest.mark.parametrize("n_classes", [5, 8])
+def test_wide_semantic_head_forward_and_gradients(n_classes):
+    """More than four classes use the second float4 of the tiny last-layer weights (forward sums, backward
+    coefficients) and a wider label embedding: forward rows and parameter gradients against the oracle."""
+    cfg = O.make_cfg(sem=True, num_sem_classes=n_classes, mapping=False, fc_units=512, n_samples=64)
+    args = types.SimpleNamespace(**vars(cfg))
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    model = model.to(DEV)
+    b, n = 96, cfg.n_samples
+    batch = synthetic.make_batch(b, seed=13)
+    gen = torch.Generator().manual_seed(14)
+    batch["sems"] = torch.randint(0, n_classes, (b,), generator=gen)
+    batch["sems"][::11] = -100
+    u, nz = torch.rand(b, n, generator=gen), torch.randn(b, n, generator=gen)
+    want = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
+                    batch["depth_std"], O.Draws([u.clone()], [nz.clone()]))
+    want_loss = O.colour_loss(want, batch["rgbs"])[0] + O.semantic_loss(want, batch["sems"], 1.0)[0]
+    want_grads = torch.autograd.grad(want_loss, list(P.values()), allow_unused=True)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    args._rng = O.Draws([u.to(DEV)], [nz.to(DEV)])
+    got = render_rays({"coarse": model}, args, d["rays"], None, semantics=d["sems"], mode="train",
+                      valid_depth=d["valid_depth"], target_depths=d["depths"], target_std=d["depth_std"])
+    assert got["sem_logits_coarse"].shape == (b, n_classes)
+    assert float((got["sem_logits_coarse"].cpu() - want["sem_logits_coarse"].detach()).abs().max()) <= TOL["sem_logits"]
+    assert float((got["rgb_coarse"].cpu() - want["rgb_coarse"].detach()).abs().max()) <= TOL["rgb"]
+    loss = metrics.SNerfLoss(0.0)(got, d["rgbs"])[0] + metrics.SemanticLoss(1.0)(got, d["sems"])[0]
+    grads = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    assert abs(float(loss) - float(want_loss)) <= 2e-3 * abs(float(want_loss))
+    top = max(float(w.norm()) for w in want_grads if w is not None)
+    for (name, _), a, w in zip(model.named_parameters(), grads, want_grads):
+        if w is None or float(w.norm()) < 1e-3 * top:
+            continue
+        rel = float((a.cpu() - w).norm() / w.norm())
+        assert rel <= 2e-2, (name, rel)
