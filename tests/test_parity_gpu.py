@@ -688,3 +688,48 @@ def test_wide_semantic_head_forward_and_gradients(n_classes):
             continue
         rel = float((a.cpu() - w).norm() / w.norm())
         assert rel <= 2e-2, (name, rel)
+
+
+@pytest.mark.parametrize("n_samples,b", [(40, 77), (96, 33)])
+def test_sample_counts_off_the_fast_paths(n_samples, b):
+    """Sample counts that are not 64 / 128 (generic compositing kernels) and not a multiple of 32 (the rows of a
+    warp span two rays: per-lane label-embedding gradient path), ragged last tile: render + losses + backward
+    against the oracle."""
+    cfg = O.make_cfg(sem=True, num_sem_classes=3, mapping=False, fc_units=512, n_samples=n_samples)
+    args = types.SimpleNamespace(**vars(cfg))
+    torch.manual_seed(0)
+    model = load_model(args)
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    model = model.to(DEV)
+    n = n_samples
+    batch = synthetic.make_batch(b, seed=23)
+    gen = torch.Generator().manual_seed(24)
+    u, nz = torch.rand(b, n, generator=gen), torch.randn(b, n, generator=gen)
+    want = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
+                    batch["depth_std"], O.Draws([u.clone()], [nz.clone()]))
+    want_loss = O.colour_loss(want, batch["rgbs"])[0] + O.depth_loss(
+        want, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0] \
+        + O.semantic_loss(want, batch["sems"], 1.0)[0]
+    want_grads = torch.autograd.grad(want_loss, list(P.values()), allow_unused=True)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    args._rng = O.Draws([u.to(DEV)], [nz.to(DEV)])
+    got = render_rays({"coarse": model}, args, d["rays"], None, semantics=d["sems"], mode="train",
+                      valid_depth=d["valid_depth"], target_depths=d["depths"], target_std=d["depth_std"])
+    assert torch.equal(got["z_vals_coarse"].cpu(), want["z_vals_coarse"])
+    for key in ("rgb", "depth", "weights", "transparency", "sem_logits"):
+        err = float((got[key + "_coarse"].cpu() - want[key + "_coarse"].detach()).abs().max())
+        assert err <= TOL[key], (key, err)
+    loss = metrics.SNerfLoss(0.0)(got, d["rgbs"])[0] + metrics.DepthLoss(1.0, usealldepth=False)(
+        got, d["depths"][:, 0], d["depths"][:, 1], target_valid_depth=d["valid_depth"], target_std=d["depth_std"])[0] \
+        + metrics.SemanticLoss(1.0)(got, d["sems"])[0]
+    grads = torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)
+    assert abs(float(loss) - float(want_loss)) <= 2e-3 * abs(float(want_loss))
+    top = max(float(w.norm()) for w in want_grads if w is not None)
+    for (name, _), a, w in zip(model.named_parameters(), grads, want_grads):
+        if w is None or float(w.norm()) < 1e-3 * top:
+            continue
+        rel = float((a.cpu() - w).norm() / w.norm())
+        assert rel <= 2e-2, (name, rel)
