@@ -296,9 +296,52 @@ typedef struct SpnerfLosses {
   float* g_sem_logits;
   float* losses;               /* 8 floats */
   void* workspace;             /* >= spnerf_losses_workspace_bytes() bytes */
+  /* --GNLL subset variant (metrics.py:76,129-130: GaussianNLLLoss with the predicted STD passed as the variance,
+   * eps 1e-6): needs use_all_depth = 0; the gradient reaches the weights through the predicted STD */
+  int32_t gnll, _pad2;
+  float* g_weights;            /* (n_rays, n_samples), written when gnll != 0 */
 } SpnerfLosses;
 int64_t spnerf_losses_workspace_bytes(void);
 int spnerf_losses(const SpnerfLosses* args, void* stream);
+
+/* Solar-correction terms of Shadow-NeRF (replaces modules/metrics.py:17-24 solar_correction):
+ *   sc_term2 = lambda_sc/3 * mean_r sum_i (transparency_sc - sun_sc)^2
+ *   sc_term3 = lambda_sc/3 * mean_r (1 - sum_i weights_sc * sun_sc)
+ * transparency_sc / weights_sc are constants (the reference detaches them); the gradient goes to sun_sc only.
+ * backward = 0: writes losses[0..1].  backward = 1: writes g_sun = upstream[0] d term2 + upstream[1] d term3
+ * (upstream: 2 floats on the device, NULL = ones). */
+typedef struct SpnerfLossSolar {
+  int64_t n_rays;
+  int32_t n_samples, _pad;
+  const float* transparency_sc; const float* weights_sc;   /* (n_rays, n_samples) */
+  const float* sun_sc; int64_t sun_stride;                 /* element (r,i) at sun_sc[(r*n_samples+i)*sun_stride] */
+  float lambda_sc; int32_t _pad2;
+  const float* upstream;
+  float* g_sun;                                            /* (n_rays, n_samples) */
+  float* losses;                                           /* 2 floats */
+  void* workspace;                                         /* >= spnerf_losses_workspace_bytes() */
+} SpnerfLossSolar;
+int spnerf_loss_solar(const SpnerfLossSolar* args, int backward, void* stream);
+
+/* Uncertainty-aware colour loss of Sat-NeRF (replaces modules/metrics.py:10-14 uncertainty_aware_loss):
+ *   beta_ray = sum_i weights * beta + beta_min;  color = mean((rgb - target)^2 / (2 beta_ray^2));
+ *   logbeta = (3 + mean(log beta_ray)) / 2.
+ * backward = 0: writes losses[0..1] and beta_ray.  backward = 1: reads beta_ray, writes g_rgb, g_weights, g_beta
+ * scaled by upstream[0] (color) and upstream[1] (logbeta). */
+typedef struct SpnerfLossUncertainty {
+  int64_t n_rays;
+  int32_t n_samples, _pad;
+  const float* rgb; const float* rgb_target;               /* (n_rays, 3) */
+  const float* weights;                                    /* (n_rays, n_samples) */
+  const float* beta; int64_t beta_stride;                  /* element (r,i) at beta[(r*n_samples+i)*beta_stride] */
+  float beta_min; int32_t _pad2;
+  const float* upstream;
+  float* beta_ray;                                         /* (n_rays) */
+  float* g_rgb; float* g_weights; float* g_beta;           /* (n_rays,3), (n_rays,n_samples) x 2 */
+  float* losses;                                           /* 2 floats */
+  void* workspace;
+} SpnerfLossUncertainty;
+int spnerf_loss_uncertainty(const SpnerfLossUncertainty* args, int backward, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ray samplers (replace modules/rendering.py:128-144 and :14-116,165-167).  Uniform draws are

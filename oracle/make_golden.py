@@ -97,7 +97,16 @@ CASES = {
     # beta head + transient embedding, small trunk (stored with its weights)
     "beta_small": dict(B=32, mode="train", seed=15, store_weights=True,
                        cfg=dict(sem=True, num_sem_classes=5, fc_units=64, beta=True, mapping=True, sc_lambda=0.05)),
+    # Sat-NeRF branch at the width the library builds: uncertainty head + transient embedding (models/spnerf.py:359-362),
+    # SatNerfLoss with solar correction (metrics.py:10-24,48-65), --mapping, sem C=3
+    "beta_512": dict(B=64, mode="train", seed=16, trained_like=True,
+                     cfg=dict(sem=True, num_sem_classes=3, fc_units=512, beta=True, mapping=True, sc_lambda=0.05,
+                              t_embbeding_tau=4)),
 }
+# parameters whose FULL gradient is stored whatever their size (two trunk-sized matrices; the rest of the
+# large ones are pinned by norm + a random probe)
+FULL_GRADS = ("fc_net.8.weight", "feats_from_xyz.weight")
+FULL_GRAD_CASES = ("c2_train_depth_sem", "beta_512")
 
 
 def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
@@ -205,7 +214,7 @@ def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
         store[f"gradnorm_{n_}"] = np.array([float(gr.norm()), float((gr * probe).sum())], dtype=np.float64)
     # full gradients only for the small tensors (heads' last layers, biases, embedding)
     for n_, gr in zip(names, ref_grads):
-        if gr is not None and gr.numel() <= 1024:
+        if gr is not None and (gr.numel() <= 1024 or (n_ in FULL_GRADS and name in FULL_GRAD_CASES)):
             store[f"grad_{n_}"] = gr.numpy()
     meta = dict(name=name, B=B, mode=mode, cfg={k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(cfg).items()},
                 trained_like=bool(spec.get("trained_like")), state_sha256=state_hash(ref_model.state_dict()),

@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspnerf_sm100a.so")
+LIB_PATH = os.environ.get("SPNERF_LIB") or os.path.join(_HERE, "lib", "libspnerf_sm100a.so")   # SPNERF_LIB: experiment builds (tools/build_variant.sh)
 
 SELFTEST_MAX_KSTEPS = 64
 
@@ -157,7 +157,19 @@ class Losses(ctypes.Structure):
                 ("target_std", VP), ("valid_depth", VP), ("lambda_ds", F32), ("use_all_depth", I32),
                 ("g_depth", VP),
                 ("sem_logits", VP), ("labels", VP), ("lambda_ss", F32), ("_pad", I32), ("g_sem_logits", VP),
-                ("losses", VP), ("workspace", VP)]
+                ("losses", VP), ("workspace", VP), ("gnll", I32), ("_pad2", I32), ("g_weights", VP)]
+
+
+class LossSolar(ctypes.Structure):
+    _fields_ = [("n_rays", I64), ("n_samples", I32), ("_pad", I32), ("transparency_sc", VP), ("weights_sc", VP),
+                ("sun_sc", VP), ("sun_stride", I64), ("lambda_sc", F32), ("_pad2", I32), ("upstream", VP),
+                ("g_sun", VP), ("losses", VP), ("workspace", VP)]
+
+
+class LossUncertainty(ctypes.Structure):
+    _fields_ = [("n_rays", I64), ("n_samples", I32), ("_pad", I32), ("rgb", VP), ("rgb_target", VP), ("weights", VP),
+                ("beta", VP), ("beta_stride", I64), ("beta_min", F32), ("_pad2", I32), ("upstream", VP),
+                ("beta_ray", VP), ("g_rgb", VP), ("g_weights", VP), ("g_beta", VP), ("losses", VP), ("workspace", VP)]
 
 
 class Guided(ctypes.Structure):
@@ -187,6 +199,10 @@ def _declare_rest(L):
         f = getattr(L, name)
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.POINTER(st), VP]
+    for name, st in (("spnerf_loss_solar", LossSolar), ("spnerf_loss_uncertainty", LossUncertainty)):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.POINTER(st), I32, VP]
     L.spnerf_losses_workspace_bytes.restype = I64
     L.spnerf_losses_workspace_bytes.argtypes = []
     L.spnerf_mlp_wgrad_workspace_bytes.restype = I64
@@ -201,7 +217,8 @@ def _declare_rest(L):
     L.spnerf_struct_sizes.argtypes = [ctypes.POINTER(I32)]
 
 
-STRUCTS = (UmmaSelftest, NetConfig, NetSizes, MlpFwd, CompositeFwd, CompositeBwd, Losses, Guided, MlpBwd, MlpWgrad)
+STRUCTS = (UmmaSelftest, NetConfig, NetSizes, MlpFwd, CompositeFwd, CompositeBwd, Losses, Guided, MlpBwd, MlpWgrad,
+           LossSolar, LossUncertainty)
 
 _declare_base = _declare
 

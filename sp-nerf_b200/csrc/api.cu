@@ -30,4 +30,6 @@ extern "C" void spnerf_struct_sizes(int32_t* out) {
   out[i++] = (int32_t)sizeof(SpnerfGuided);
   out[i++] = (int32_t)sizeof(SpnerfMlpBwd);
   out[i++] = (int32_t)sizeof(SpnerfMlpWgrad);
+  out[i++] = (int32_t)sizeof(SpnerfLossSolar);
+  out[i++] = (int32_t)sizeof(SpnerfLossUncertainty);
 }

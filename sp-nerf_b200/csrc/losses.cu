@@ -1,7 +1,8 @@
-// Fused loss reductions + gradients: colour MSE, depth supervision, semantic cross-entropy.
+// Fused loss reductions + gradients: colour MSE, depth supervision, semantic cross-entropy, solar-correction
+// terms, uncertainty-aware colour loss.
 //
-// Replaces modules/metrics.py:27-45 (SNerfLoss colour term), :68-159 (DepthLoss, MSE variants) and
-// :162-183 (SemanticLoss): one warp per ray, block partial sums, the last block to finish adds
+// Replaces modules/metrics.py:10-24 (uncertainty_aware_loss, solar_correction), :27-45 (SNerfLoss colour term),
+// :68-159 (DepthLoss, MSE variants) and :162-183 (SemanticLoss): one warp per ray, block partial sums, the last block to finish adds
 // the partials in block order (deterministic scalars).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -51,21 +52,38 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
     if (a.depth) {
       const float d = a.depth[r], td = a.target_depth[r], tw = a.target_weight[r];
       bool apply;
+      float pstd = 0.f, m1 = 0.f;      // predicted STD and sum_i (z_i - d) w_i (GNLL gradient)
       if (a.use_all_depth) {
         apply = true;                                                                  // metrics.py:140,154-156
       } else {
         const bool valid = a.valid_depth ? a.valid_depth[r] > 0 : true;               // :89
         float v = 0.f;
         for (int i = lane; i < a.n_samples; i += 32) {
-          const float dz = a.z[r * a.n_samples + i] - d;
-          v = fmaf(dz * dz, a.weights[r * a.n_samples + i], v);
+          const float dz = a.z[r * a.n_samples + i] - d, w = a.weights[r * a.n_samples + i];
+          v = fmaf(dz * dz, w, v);
+          m1 = fmaf(dz, w, m1);
         }
-        const float pstd = sqrtf(warp_sum(v));                                         // :102
+        pstd = sqrtf(fmaxf(warp_sum(v), 0.f));                                         // :102
         const float tsd = a.target_std[r];
         apply = valid && (fabsf(d - td) > tsd || pstd > tsd);                          // :78-80,115
       }
-      if (lane == 0) {
-        const float e = d - td;
+      const float e = d - td;
+      if (a.gnll) {
+        // 0.5 (log var + e^2 / var), var = max(pstd, 1e-6) with an identity gradient through the clamp (torch's
+        // GaussianNLLLoss clamps a detached copy); d pstd / d S = 1 / (2 pstd)
+        m1 = warp_sum(m1);
+        const float var = fmaxf(pstd, 1e-6f);
+        const float dvar = apply ? lam_d * inv_b * 0.5f * (1.f / var - e * e / (var * var)) : 0.f;   // d loss / d var
+        const float ds = dvar * 0.5f / pstd;                                            // d loss / d S
+        for (int i = lane; i < a.n_samples; i += 32) {
+          const float dz = a.z[r * a.n_samples + i] - d;
+          a.g_weights[r * a.n_samples + i] = apply ? ds * dz * dz : 0.f;
+        }
+        if (lane == 0) {
+          a.g_depth[r] = apply ? lam_d * inv_b * e / var - 2.f * ds * m1 : 0.f;
+          if (apply) { s_dep += 0.5f * (logf(var) + e * e / var); s_app += 1.f; }
+        }
+      } else if (lane == 0) {
         a.g_depth[r] = apply ? lam_d * 2.f * tw * e * inv_b : 0.f;                     // mean over applied of (n_applied/B) tw e^2
         if (apply) { s_dep += tw * e * e; s_app += 1.f; }
       }
@@ -113,7 +131,155 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Solar-correction terms (metrics.py:17-24) and the uncertainty-aware colour loss (metrics.py:10-14).
+// Forward kernels: one warp per ray, deterministic scalars (block partials summed in block order by the
+// last block).  Backward kernels: the gradients, scaled by the upstream gradients of the two scalars
+// (device pointer; NULL = 1), so the autograd wrapper needs no host synchronisation and no torch arithmetic.
+// `sun` / `beta` are read in place from the network's output rows (element (r, i) at p[(r n + i) stride]).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ bool block_partials(Workspace* ws, const float (&v)[K]) {
+  __shared__ float red[kThreads / 32][4];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < K; ++k) red[wib][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w][threadIdx.x];
+    ws->partial[blockIdx.x][threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+__device__ __forceinline__ float ordered_total(const Workspace* ws, int k) {
+  float t = 0.f;
+  for (unsigned b = 0; b < gridDim.x; ++b) t += ws->partial[b][k];
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads) solar_fwd_kernel(const SpnerfLossSolar a, Workspace* ws) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n = a.n_samples;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + wib, nw = (int64_t)gridDim.x * (kThreads / 32);
+  float s2 = 0.f, s3 = 0.f;
+  for (int64_t r = warp0; r < a.n_rays; r += nw) {
+    float q = 0.f, ws_ = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float s = a.sun_sc[(r * n + i) * a.sun_stride];
+      const float d = a.transparency_sc[r * n + i] - s;
+      q = fmaf(d, d, q);
+      ws_ = fmaf(a.weights_sc[r * n + i], s, ws_);
+    }
+    q = warp_sum(q); ws_ = warp_sum(ws_);
+    if (lane == 0) { s2 += q; s3 += 1.f - ws_; }
+  }
+  const float v[2] = {s2, s3};
+  if (block_partials<2>(ws, v) && threadIdx.x < 2)
+    a.losses[threadIdx.x] = a.lambda_sc / 3.f * ordered_total(ws, threadIdx.x) / (float)a.n_rays;
+}
+
+__global__ void __launch_bounds__(kThreads) solar_bwd_kernel(const SpnerfLossSolar a) {
+  const float up2 = a.upstream ? a.upstream[0] : 1.f, up3 = a.upstream ? a.upstream[1] : 1.f;
+  const float c = a.lambda_sc / 3.f / (float)a.n_rays;
+  const int64_t total = a.n_rays * a.n_samples;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = a.sun_sc[i * a.sun_stride];
+    a.g_sun[i] = c * (up2 * 2.f * (s - a.transparency_sc[i]) - up3 * a.weights_sc[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) uncertainty_fwd_kernel(const SpnerfLossUncertainty a, Workspace* ws) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n = a.n_samples;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + wib, nw = (int64_t)gridDim.x * (kThreads / 32);
+  float s_col = 0.f, s_log = 0.f;
+  for (int64_t r = warp0; r < a.n_rays; r += nw) {
+    float b = 0.f;
+    for (int i = lane; i < n; i += 32) b = fmaf(a.weights[r * n + i], a.beta[(r * n + i) * a.beta_stride], b);
+    b = warp_sum(b) + a.beta_min;
+    if (lane == 0) {
+      a.beta_ray[r] = b;
+      float q = 0.f;
+      for (int c = 0; c < 3; ++c) { const float d = a.rgb[r * 3 + c] - a.rgb_target[r * 3 + c]; q = fmaf(d, d, q); }
+      s_col += q / (2.f * b * b);
+      s_log += logf(b);
+    }
+  }
+  const float v[2] = {s_col, s_log};
+  if (block_partials<2>(ws, v) && threadIdx.x == 0) {
+    a.losses[0] = ordered_total(ws, 0) / (3.f * (float)a.n_rays);
+    a.losses[1] = (3.f + ordered_total(ws, 1) / (float)a.n_rays) * 0.5f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) uncertainty_bwd_kernel(const SpnerfLossUncertainty a) {
+  const float upc = a.upstream ? a.upstream[0] : 1.f, upl = a.upstream ? a.upstream[1] : 1.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n = a.n_samples;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + wib, nw = (int64_t)gridDim.x * (kThreads / 32);
+  const float inv_b = 1.f / (float)a.n_rays;
+  for (int64_t r = warp0; r < a.n_rays; r += nw) {
+    const float b = a.beta_ray[r];
+    float q = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float d = a.rgb[r * 3 + c] - a.rgb_target[r * 3 + c];
+      q = fmaf(d, d, q);
+      if (lane == c) a.g_rgb[r * 3 + c] = upc * d / (b * b) * inv_b / 3.f;
+    }
+    const float gb = -upc * q / (b * b * b) * inv_b / 3.f + upl * 0.5f * inv_b / b;     // d loss / d beta_ray
+    for (int i = lane; i < n; i += 32) {
+      a.g_weights[r * n + i] = gb * a.beta[(r * n + i) * a.beta_stride];
+      a.g_beta[r * n + i] = gb * a.weights[r * n + i];
+    }
+  }
+}
+
 }  // namespace
+
+static unsigned ray_blocks(int64_t n_rays) {
+  const int64_t need = (n_rays + kThreads / 32 - 1) / (kThreads / 32);
+  return (unsigned)(need < kMaxBlocks ? need : kMaxBlocks);
+}
+
+extern "C" int spnerf_loss_solar(const SpnerfLossSolar* a, int backward, void* stream_) {
+  if (!a || a->n_rays <= 0 || a->n_samples < 1 || !a->transparency_sc || !a->weights_sc || !a->sun_sc || a->sun_stride < 1)
+    return SPNERF_ERR_BAD_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!backward) {
+    if (!a->losses || !a->workspace) return SPNERF_ERR_BAD_ARG;
+    Workspace* ws = static_cast<Workspace*>(a->workspace);
+    cudaMemsetAsync(ws, 0, 16, stream);
+    solar_fwd_kernel<<<ray_blocks(a->n_rays), kThreads, 0, stream>>>(*a, ws);
+  } else {
+    if (!a->g_sun) return SPNERF_ERR_BAD_ARG;
+    const int64_t nb = (a->n_rays * a->n_samples + kThreads - 1) / kThreads;
+    solar_bwd_kernel<<<(unsigned)(nb < 148 * 16 ? nb : 148 * 16), kThreads, 0, stream>>>(*a);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+extern "C" int spnerf_loss_uncertainty(const SpnerfLossUncertainty* a, int backward, void* stream_) {
+  if (!a || a->n_rays <= 0 || a->n_samples < 1 || !a->rgb || !a->rgb_target || !a->weights || !a->beta || a->beta_stride < 1 ||
+      !a->beta_ray)
+    return SPNERF_ERR_BAD_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!backward) {
+    if (!a->losses || !a->workspace) return SPNERF_ERR_BAD_ARG;
+    Workspace* ws = static_cast<Workspace*>(a->workspace);
+    cudaMemsetAsync(ws, 0, 16, stream);
+    uncertainty_fwd_kernel<<<ray_blocks(a->n_rays), kThreads, 0, stream>>>(*a, ws);
+  } else {
+    if (!a->g_rgb || !a->g_weights || !a->g_beta) return SPNERF_ERR_BAD_ARG;
+    uncertainty_bwd_kernel<<<ray_blocks(a->n_rays), kThreads, 0, stream>>>(*a);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 
 extern "C" int64_t spnerf_losses_workspace_bytes(void) { return (int64_t)sizeof(Workspace); }
 
@@ -122,6 +288,7 @@ extern "C" int spnerf_losses(const SpnerfLosses* a, void* stream_) {
   if (a->rgb && (!a->rgb_target || !a->g_rgb)) return SPNERF_ERR_BAD_ARG;
   if (a->depth && (!a->target_depth || !a->target_weight || !a->g_depth)) return SPNERF_ERR_BAD_ARG;
   if (a->depth && !a->use_all_depth && (!a->z || !a->weights || !a->target_std)) return SPNERF_ERR_BAD_ARG;
+  if (a->depth && a->gnll && (a->use_all_depth || !a->g_weights)) return SPNERF_ERR_BAD_ARG;
   if (a->sem_logits && (!a->labels || !a->g_sem_logits || a->n_sem < 1 || a->n_sem > 32)) return SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Workspace* ws = static_cast<Workspace*>(a->workspace);

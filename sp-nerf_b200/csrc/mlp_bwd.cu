@@ -24,9 +24,30 @@ struct BwdParams {
   float* g_emb; float* g_small_bias; float* g_t_emb;
   int sem, n_classes, emb_dim, beta, t_dim, n_out, col_beta, col_sem, debug;
   long long* prof;
+  int stagger, stagger_groups;      // start delay of cluster c: stagger * (c % groups) / groups cycles
 };
 
-__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// Streaming 16-byte load of a saved activation chunk.  SPNERF_LDG_MODE (experiment): 0 = ld.global.nc (allocates an L1
+// line per request; with 227 KB of shared memory carved out only ~28 KB of L1 are left to hold the requests in flight),
+// 1 = L1::no_allocate, 2 = .cs (evict-first), 3 = L1::no_allocate + L2::evict_first hint
+#ifndef SPNERF_LDG_MODE
+#define SPNERF_LDG_MODE 0
+#endif
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
+#if SPNERF_LDG_MODE == 0
+  return __ldg(reinterpret_cast<const uint4*>(p));
+#else
+  uint4 v;
+#if SPNERF_LDG_MODE == 1
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#elif SPNERF_LDG_MODE == 2
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
+  return v;
+#endif
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -57,7 +78,10 @@ __device__ __forceinline__ YBatch ybatch_load(const uint8_t* ysave, const uint8_
 // to stream a 128 KB activation tile from HBM in a few microseconds; one batch per thread gave 12 GB/s).
 // Three batches, not four: at the 96-register budget of 640-thread CTAs the fourth one spilled (120 B stores /
 // 272 B loads per thread -> 28 / 36) and the kernel is 1.7 % faster without it; two measure the same as three.
-constexpr int kYWin = 3;
+#ifndef SPNERF_YWIN
+#define SPNERF_YWIN 3
+#endif
+constexpr int kYWin = SPNERF_YWIN;
 struct YWindow { YBatch b[kYWin]; };
 __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, const uint8_t* ssave, int j0, int row) {
 #pragma unroll
@@ -75,11 +99,16 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
   for (int b = 0; b < NB; ++b) {
     if (b < nb_run) {
       const int jb = j0 + 16 * b;
-      const YBatch cur = win.b[b % kYWin];
-      if (MODE != 2 && b + kYWin < NB) win.b[b % kYWin] = ybatch_load(ysave, ssave, jb + 16 * kYWin, row);
+      YBatch cur = win.b[b % kYWin];
+      if (MODE != 2 && MODE != 3 && b + kYWin < NB) win.b[b % kYWin] = ybatch_load(ysave, ssave, jb + 16 * kYWin, row);
       uint32_t v[16];
       tmem_ld16(taddr + jb, v);
       tmem_wait_ld();
+      if (MODE == 3) {     // timing experiment: the epilogue's arithmetic without its global loads
+        cur.y[0] = make_uint4(v[0] & 0x3bff3bffu, v[1] & 0x3bff3bffu, v[2] & 0x3bff3bffu, v[3] & 0x3bff3bffu);
+        cur.y[1] = make_uint4(v[4] & 0x3bff3bffu, v[5] & 0x3bff3bffu, v[6] & 0x3bff3bffu, v[7] & 0x3bff3bffu);
+        cur.sb = v[8];
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float g[8];
@@ -160,12 +189,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
   }
   const float inv_scale = 1.f / scale;
 
+  if (warp >= kProducerWarp) ctl_registers();
   if (warp == kProducerWarp) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
     if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
     else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
   } else if (warp < 16) {
+    epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -178,6 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
     EpiSync sync(sh, p.prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
+    stagger_start(p.stagger, p.stagger_groups);
 
     for (int64_t it = 0; it < n_iters; ++it) {
       // this CTA's tile of the pair; an odd tile count leaves rank 1 a phantom tile: it reads tile 0's
@@ -346,6 +378,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         if (signal) sync.end(true);
       };
       for (int L = 7; L >= 0; --L) {
+#ifdef SPNERF_EXPERIMENTS
+        if (!(p.debug & (1024 | 4096)))
+#endif
         ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
         sync.begin();
         // three of the four column groups store their part of the gradient tile from registers, the last quarter is
@@ -353,10 +388,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         // 4.60, all four 4.72; debug & 256 / 512 select 2 / 1 groups)
         const int ndirect = (p.debug & 256) ? 2 : (p.debug & 512) ? 1 : 3;
         uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
+#ifdef SPNERF_EXPERIMENTS
+        if (p.debug & 2048) gdirect = nullptr;
+        if (p.debug & 1024) bwd_columns<3, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else if (p.debug & 4096) bwd_columns<2, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else
+#endif
         if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
         else       bwd_columns<1, 8>(taddr, cg * 128, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
+#ifdef SPNERF_EXPERIMENTS
+        if (!(p.debug & 2048))
+#endif
         copy_slabs_out(act, 2 * ndirect, 8 - 2 * ndirect, gs(p.gm.G[L] + 2 * ndirect));
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
@@ -422,6 +466,7 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   p.t_dim = a->cfg.t_dim; p.n_out = d.n_out; p.col_beta = d.col_beta; p.col_sem = d.col_sem;
   p.debug = a->debug_flags;
   p.prof = g_prof_bwd;
+  host_stagger(p.stagger, p.stagger_groups);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);

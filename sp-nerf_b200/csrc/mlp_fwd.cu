@@ -30,6 +30,7 @@ struct FwdParams {
   int mapping, sem, n_classes, emb_dim, beta, t_dim, in_dim, n_out, col_beta, col_sem;
   int debug;
   long long* prof;
+  int stagger, stagger_groups;      // start delay of cluster c: stagger * (c % groups) / groups cycles
 };
 
 // 32 accumulator columns [j0, j0+32) of one chunk (column 0 of the chunk at TMEM address `taddr`)
@@ -105,12 +106,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
+  if (warp >= kProducerWarp) ctl_registers();
   if (warp == kProducerWarp) {
     producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
     if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
     else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
   } else if (warp < 16) {
+    epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
     const int row = (warp & 3) * 32 + lane;    // TMEM lane quarter = warp % 4
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -124,6 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     EpiSync sync(sh, p.prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
+    stagger_start(p.stagger, p.stagger_groups);
 
     for (int64_t it = 0; it < n_iters; ++it) {
       // this CTA's tile of the pair; an odd tile count leaves rank 1 a phantom tile (no rows, no stores)
@@ -377,6 +381,7 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.col_beta = d.col_beta; p.col_sem = d.col_sem;
   p.debug = a->debug_flags;
   p.prof = g_prof_fwd;
+  host_stagger(p.stagger, p.stagger_groups);
 
   static bool attr_set = false;
   if (!attr_set) {

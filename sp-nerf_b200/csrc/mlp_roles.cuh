@@ -21,6 +21,8 @@
 #pragma once
 #include "sm100.cuh"
 #include "net_plan.h"
+#include <cstdio>
+#include <cstdlib>
 
 namespace roles {
 using namespace sm100;
@@ -287,6 +289,48 @@ __device__ __forceinline__ void reduce_groups(float* scratch, float (&v)[NV], in
       v[i] = (scratch[(i * kColGroups + 0) * kTileM + row] + scratch[(i * kColGroups + 1) * kTileM + row]) +
              (scratch[(i * kColGroups + 2) * kTileM + row] + scratch[(i * kColGroups + 3) * kTileM + row]);
   }
+}
+
+// Register re-balancing: 640 threads launch at 96 registers each; the control warpgroup (warps 16-19: producer, two
+// issuers / relay, one idle warp) gives most of its share back and the four epilogue warpgroups take it
+// (512 * kEpiRegs + 128 * kCtlRegs <= 640 * 96: the pool is what the CTA was given at launch, not the whole register
+// file -- 112 / 40 passed ptxas and died with a launch failure).  Every warp of a warpgroup executes the instruction.
+#ifndef SPNERF_EPI_REGS
+#define SPNERF_EPI_REGS 104
+#endif
+#ifndef SPNERF_CTL_REGS
+#define SPNERF_CTL_REGS 64
+#endif
+constexpr int kEpiRegs = SPNERF_EPI_REGS, kCtlRegs = SPNERF_CTL_REGS;
+static_assert(kEpiThreads * kEpiRegs + (kThreads - kEpiThreads) * kCtlRegs <= kThreads * 96, "register pool of the launch");
+// (called inside the role branches: the allocator bounds each region by the setmaxnreg that dominates it)
+__device__ __forceinline__ void ctl_registers() {
+#if SPNERF_EPI_REGS > 96
+  reg_dec<kCtlRegs>();
+#endif
+}
+__device__ __forceinline__ void epi_registers() {
+#if SPNERF_EPI_REGS > 96
+  reg_inc<kEpiRegs>();
+#endif
+}
+
+// Phase staggering.  Every cluster runs the same MMA / epilogue sequence on equal tiles, so without a start offset
+// all 74 pairs reach their epilogues (the only phases that touch HBM: activation saves, saved-activation reloads,
+// gradient tiles) at the same moment and the chip alternates between an idle and a saturated memory system.
+// Cluster c therefore starts stagger * (c % groups) / groups cycles late (epilogue warps spin; everything else is
+// driven by their first hand-off).
+__device__ __forceinline__ void stagger_start(int stagger, int groups) {
+  if (stagger <= 0 || groups <= 1) return;
+  const long long d = (long long)stagger * (long long)((blockIdx.x >> 1) % groups) / groups;
+  const long long t0 = clock64();
+  while (clock64() - t0 < d) {}
+}
+inline void host_stagger(int& stagger, int& groups) {
+  stagger = 0; groups = 1;
+#ifdef SPNERF_EXPERIMENTS
+  if (const char* e = getenv("SPNERF_STAGGER")) { int a = 0, b = 1; if (sscanf(e, "%d,%d", &a, &b) >= 1) { stagger = a; groups = b > 0 ? b : 1; } }
+#endif
 }
 
 }  // namespace roles

@@ -129,14 +129,12 @@ _loss_ws = {}
 
 def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, target_depth=None,
            target_weight=None, target_std=None, valid_depth=None, lambda_ds=0.0, use_all_depth=False,
-           sem_logits=None, labels=None, lambda_ss=0.0):
+           sem_logits=None, labels=None, lambda_ss=0.0, gnll=False):
     """Fused loss reductions + gradients (modules/metrics.py:27-45, 68-159, 162-183).
-    Returns (scalars (8,), g_rgb, g_depth, g_sem_logits)."""
+    Returns (scalars (8,), g_rgb, g_depth, g_sem_logits, g_weights); g_weights only for the GNLL depth variant."""
     ref = rgb if rgb is not None else (depth if depth is not None else sem_logits)
     dev = ref.device
     _require_cuda(ref, "loss inputs")
-    if dev not in _loss_ws:
-        _loss_ws[dev] = torch.empty(int(_cabi.lib().spnerf_losses_workspace_bytes()), dtype=torch.uint8, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
     out = torch.empty(8, **f32)
     g_rgb = torch.empty_like(rgb) if rgb is not None else None
@@ -152,9 +150,75 @@ def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, 
         _p(target_depth), _p(target_weight), _p(target_std), _p(valid_depth)
     a.lambda_ds, a.use_all_depth, a.g_depth = lambda_ds, 1 if use_all_depth else 0, _p(g_depth)
     a.sem_logits, a.labels, a.lambda_ss, a.g_sem_logits = _p(sem_logits), _p(labels), lambda_ss, _p(g_sem)
-    a.losses, a.workspace = _p(out), _p(_loss_ws[dev])
+    a.losses, a.workspace = _p(out), _p(_loss_workspace(dev))
+    g_w = torch.empty_like(weights) if (gnll and depth is not None) else None
+    a.gnll, a.g_weights = 1 if gnll else 0, _p(g_w)
     _cabi.check(_cabi.lib().spnerf_losses(ctypes.byref(a), _stream()), "spnerf_losses")
-    return out, g_rgb, g_depth, g_sem
+    return out, g_rgb, g_depth, g_sem, g_w
+
+
+def _loss_workspace(dev):
+    if dev not in _loss_ws:
+        _loss_ws[dev] = torch.empty(int(_cabi.lib().spnerf_losses_workspace_bytes()), dtype=torch.uint8, device=dev)
+    return _loss_ws[dev]
+
+
+def _row_strided(t, n_rays, n_samples):
+    """(pointer tensor, element stride) of a (B,N[,1]) tensor whose element (r,i) sits at base + (r N + i) stride:
+    a column view of the network's output rows is read in place, anything else is made contiguous."""
+    t = t.detach()
+    if t.dim() == 3:
+        t = t[..., 0]
+    if t.dtype == torch.float32 and t.shape == (n_rays, n_samples) and t.stride(1) >= 1 and (
+            n_rays == 1 or t.stride(0) == n_samples * t.stride(1)):
+        return t, t.stride(1)
+    return t.float().contiguous(), 1
+
+
+def loss_solar(trans_sc, weights_sc, sun_sc, lambda_sc, upstream=None, backward=False):
+    """modules/metrics.py:17-24.  Forward: (2,) [sc_term2, sc_term3]; backward: d/d sun_sc (B,N) for the
+    upstream gradients of the two scalars ((2,) device tensor, None = ones)."""
+    b, n = trans_sc.shape
+    _require_cuda(trans_sc, "transparency_sc")
+    dev = trans_sc.device
+    sun, stride = _row_strided(sun_sc, b, n)
+    a = _cabi.LossSolar()
+    a.n_rays, a.n_samples, a.lambda_sc = b, n, float(lambda_sc)
+    a.transparency_sc, a.weights_sc, a.sun_sc, a.sun_stride = _p(trans_sc), _p(weights_sc), _p(sun), stride
+    a.upstream = _p(upstream)
+    if backward:
+        res = torch.empty(b, n, dtype=torch.float32, device=dev)
+        a.g_sun = _p(res)
+    else:
+        res = torch.empty(2, dtype=torch.float32, device=dev)
+        a.losses, a.workspace = _p(res), _p(_loss_workspace(dev))
+    _cabi.check(_cabi.lib().spnerf_loss_solar(ctypes.byref(a), 1 if backward else 0, _stream()), "spnerf_loss_solar")
+    return res
+
+
+def loss_uncertainty(rgb, rgb_target, weights, beta, beta_min=0.05, beta_ray=None, upstream=None, backward=False):
+    """modules/metrics.py:10-14.  Forward: ((2,) [color, logbeta], beta_ray (B,)); backward: (g_rgb, g_weights,
+    g_beta) for the upstream gradients of the two scalars."""
+    b, n = weights.shape
+    _require_cuda(rgb, "rgb")
+    dev = rgb.device
+    bt, stride = _row_strided(beta, b, n)
+    a = _cabi.LossUncertainty()
+    a.n_rays, a.n_samples, a.beta_min = b, n, float(beta_min)
+    a.rgb, a.rgb_target, a.weights, a.beta, a.beta_stride = _p(rgb), _p(rgb_target), _p(weights), _p(bt), stride
+    a.upstream = _p(upstream)
+    f32 = dict(dtype=torch.float32, device=dev)
+    if backward:
+        g_rgb, g_w, g_b = torch.empty(b, 3, **f32), torch.empty(b, n, **f32), torch.empty(b, n, **f32)
+        a.beta_ray, a.g_rgb, a.g_weights, a.g_beta = _p(beta_ray), _p(g_rgb), _p(g_w), _p(g_b)
+        res = (g_rgb, g_w, g_b)
+    else:
+        vals, beta_ray = torch.empty(2, **f32), torch.empty(b, **f32)
+        a.beta_ray, a.losses, a.workspace = _p(beta_ray), _p(vals), _p(_loss_workspace(dev))
+        res = (vals, beta_ray)
+    _cabi.check(_cabi.lib().spnerf_loss_uncertainty(ctypes.byref(a), 1 if backward else 0, _stream()),
+                "spnerf_loss_uncertainty")
+    return res
 
 
 import os as _os

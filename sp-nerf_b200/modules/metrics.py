@@ -1,10 +1,10 @@
 """Loss functions: mirror of modules/metrics.py:10-194 (same classes, constructor / forward
-signatures and loss-dictionary keys) over the fused loss kernel of include/spnerf_b200.h.
+signatures and loss-dictionary keys) over the fused loss kernels of include/spnerf_b200.h.
 
-Colour MSE, depth supervision (subset and all-depth MSE variants) and semantic cross-entropy are
-one CUDA pass each that yields the scalar and its gradient together; the solar-correction and
-uncertainty terms (metrics.py:10-24) are a handful of elementwise ops on (rays, samples) tensors
-and stay in PyTorch for now.
+Every term is evaluated by a CUDA kernel that yields the scalar(s) deterministically; gradients come
+from the same kernels (colour MSE, depth, cross-entropy: value and gradient in one pass; solar
+correction and uncertainty: a gradient pass scaled by the upstream gradients on the device).
+The only PyTorch arithmetic left here is adding the scalars of a loss dictionary.
 """
 import torch
 
@@ -16,7 +16,7 @@ class _Reduce(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, which, x, kwargs):
-        scalars, g_rgb, g_depth, g_sem = E.losses(x.shape[0], **kwargs)
+        scalars, g_rgb, g_depth, g_sem, _ = E.losses(x.shape[0], **kwargs)
         grad = (g_rgb, g_depth, g_sem)[which]
         ctx.save_for_backward(grad)
         return scalars[which].clone()
@@ -31,21 +31,56 @@ def _c(t, dtype=torch.float32):
     return t.detach().to(dtype).contiguous()
 
 
+class _SolarTerms(torch.autograd.Function):
+    """(sc_term2, sc_term3) of metrics.py:17-24 as one (2,) tensor; differentiable w.r.t. the sun visibility of the
+    solar-correction pass only (the reference detaches the transparency and the weights)."""
+
+    @staticmethod
+    def forward(ctx, sun_sc, trans_sc, weights_sc, lambda_sc):
+        trans_sc, weights_sc = _c(trans_sc), _c(weights_sc)
+        ctx.lambda_sc = lambda_sc
+        ctx.save_for_backward(sun_sc, trans_sc, weights_sc)
+        return E.loss_solar(trans_sc, weights_sc, sun_sc, lambda_sc)
+
+    @staticmethod
+    def backward(ctx, g):
+        sun_sc, trans_sc, weights_sc = ctx.saved_tensors
+        g_sun = E.loss_solar(trans_sc, weights_sc, sun_sc, ctx.lambda_sc, upstream=_c(g), backward=True)
+        return g_sun.view(sun_sc.shape), None, None, None
+
+
+class _UncertaintyTerms(torch.autograd.Function):
+    """(color, logbeta) of metrics.py:10-14 as one (2,) tensor; differentiable w.r.t. rgb, weights and beta."""
+
+    @staticmethod
+    def forward(ctx, rgb, weights, beta, gt_rgb, beta_min):
+        rgb_c, w_c, gt = _c(rgb), _c(weights), _c(gt_rgb)
+        vals, beta_ray = E.loss_uncertainty(rgb_c, gt, w_c, beta, beta_min)
+        ctx.beta_min = beta_min
+        ctx.save_for_backward(rgb_c, w_c, beta, gt, beta_ray)
+        return vals
+
+    @staticmethod
+    def backward(ctx, g):
+        rgb_c, w_c, beta, gt, beta_ray = ctx.saved_tensors
+        g_rgb, g_w, g_beta = E.loss_uncertainty(rgb_c, gt, w_c, beta, ctx.beta_min, beta_ray=beta_ray, upstream=_c(g),
+                                                backward=True)
+        return g_rgb, g_w, g_beta.view(beta.shape), None, None
+
+
 def solar_correction(loss_dict, inputs, typ, lambda_sc=0.05):
-    """metrics.py:17-24."""
-    sun_sc = inputs[f'sun_sc_{typ}'].squeeze()
-    term2 = torch.sum(torch.square(inputs[f'transparency_sc_{typ}'].detach() - sun_sc), -1)
-    term3 = 1 - torch.sum(inputs[f'weights_sc_{typ}'].detach() * sun_sc, -1)
-    loss_dict[f'{typ}_sc_term2'] = lambda_sc / 3. * torch.mean(term2)
-    loss_dict[f'{typ}_sc_term3'] = lambda_sc / 3. * torch.mean(term3)
+    """metrics.py:17-24: adds '<typ>_sc_term2' / '<typ>_sc_term3'."""
+    terms = _SolarTerms.apply(inputs[f'sun_sc_{typ}'], inputs[f'transparency_sc_{typ}'], inputs[f'weights_sc_{typ}'],
+                              float(lambda_sc))
+    loss_dict[f'{typ}_sc_term2'], loss_dict[f'{typ}_sc_term3'] = terms[0], terms[1]
     return loss_dict
 
 
 def uncertainty_aware_loss(loss_dict, inputs, gt_rgb, typ, beta_min=0.05):
-    """metrics.py:10-14."""
-    beta = torch.sum(inputs[f'weights_{typ}'].unsqueeze(-1) * inputs['beta_coarse'], -2) + beta_min
-    loss_dict[f'{typ}_color'] = ((inputs[f'rgb_{typ}'] - gt_rgb) ** 2 / (2 * beta ** 2)).mean()
-    loss_dict[f'{typ}_logbeta'] = (3 + torch.log(beta).mean()) / 2
+    """metrics.py:10-14: adds '<typ>_color' / '<typ>_logbeta' (the transient uncertainty is always the coarse one)."""
+    terms = _UncertaintyTerms.apply(inputs[f'rgb_{typ}'], inputs[f'weights_{typ}'], inputs['beta_coarse'], gt_rgb,
+                                    float(beta_min))
+    loss_dict[f'{typ}_color'], loss_dict[f'{typ}_logbeta'] = terms[0], terms[1]
     return loss_dict
 
 
@@ -80,36 +115,31 @@ class SatNerfLoss(torch.nn.Module):
         return loss, loss_dict
 
 
+class _GnllDepth(torch.autograd.Function):
+    """GNLL subset depth loss: value + gradients w.r.t. the depth and the weights (through the predicted STD)."""
+
+    @staticmethod
+    def forward(ctx, depth, weights, kwargs):
+        scalars, _, g_depth, _, g_w = E.losses(depth.shape[0], **kwargs)
+        ctx.save_for_backward(g_depth, g_w)
+        return scalars[1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        g_depth, g_w = ctx.saved_tensors
+        return g * g_depth, g * g_w, None
+
+
 class DepthLoss(torch.nn.Module):
-    """metrics.py:68-159.  The MSE variants (subset and all-depth) are one fused CUDA pass; the GNLL subset
-    variant (metrics.py:76,129-130: torch's GaussianNLLLoss with the predicted STD passed as the variance, kept)
-    is a handful of (rays, samples) torch ops on the device, like the solar-correction terms."""
+    """metrics.py:68-159.  One fused CUDA pass per call: the MSE variants (subset and all-depth) and the GNLL subset
+    variant (metrics.py:76,129-130: torch's GaussianNLLLoss with the predicted STD passed as the variance, kept;
+    nothing selected -> zero loss with zero gradients, :97-100,119-121)."""
 
     def __init__(self, lambda_ds=1.0, GNLL=False, usealldepth=True, margin=0, stdscale=1):
         super().__init__()
         self.lambda_ds = lambda_ds / 3.
         self._lambda_arg = lambda_ds
         self.GNLL, self.usealldepth, self.margin, self.stdscale = GNLL, usealldepth, margin, stdscale
-
-    def _gnll_subset(self, inputs, targets, target_valid_depth, target_std):
-        """ComputeSubsetDepthLoss with GNLL (metrics.py:82-130) without boolean-index gathers or host syncs:
-        masked sums over all rays give the same mean over the selected ones."""
-        z, depth, w = inputs['z_vals_coarse'].detach(), inputs['depth_coarse'], inputs['weights_coarse']
-        E._require_cuda(depth, "depth_coarse")
-        b = depth.shape[0]
-        if target_valid_depth is None:
-            target_valid_depth = torch.ones(b, device=depth.device)                       # metrics.py:86
-        valid = target_valid_depth.reshape(-1) > 0
-        pred_std = ((z - depth.unsqueeze(-1)).pow(2) * w).sum(-1).clamp_min(0).sqrt()      # :102
-        apply = valid
-        if not self.usealldepth:
-            apply = valid & (((depth - targets).abs() > target_std) | (pred_std > target_std))     # :78-80, :115
-        n_apply = apply.sum()
-        var = torch.where(apply, pred_std, torch.ones_like(pred_std)).clamp_min(1e-6)      # GaussianNLLLoss eps
-        per = 0.5 * (torch.log(var) + (depth - targets) ** 2 / var)
-        mean = torch.where(apply, per, torch.zeros_like(per)).sum() / n_apply.clamp_min(1).to(per.dtype)
-        scale = n_apply.to(per.dtype) / float(b)                                           # :125-127
-        return self.lambda_ds * scale * mean       # zero (with zero gradient) when nothing is selected (:97-100,119-121)
 
     def forward(self, inputs, targets, weights=1., target_valid_depth=None, target_std=None):
         depth = inputs['depth_coarse']
@@ -118,7 +148,11 @@ class DepthLoss(torch.nn.Module):
             if self.usealldepth:       # the reference calls GaussianNLLLoss without a variance here (metrics.py:140)
                 raise TypeError("GaussianNLLLoss.forward() missing 1 required positional argument: 'var' "
                                 "(--GNLL needs the subset path, as in the reference)")
-            val = self._gnll_subset(inputs, targets.float(), target_valid_depth, target_std.float())
+            kw = dict(depth=_c(depth), target_depth=_c(targets), target_weight=torch.ones(b, device=depth.device),
+                      lambda_ds=self._lambda_arg, use_all_depth=False, z=_c(inputs['z_vals_coarse']),
+                      weights=_c(inputs['weights_coarse']), target_std=_c(target_std), gnll=True,
+                      valid_depth=None if target_valid_depth is None else _c(target_valid_depth, torch.int64))
+            val = _GnllDepth.apply(depth, inputs['weights_coarse'], kw)
             return val, {'coarse_ds': val}
         if not torch.is_tensor(weights):
             weights = torch.full((b,), float(weights), device=depth.device)
@@ -152,16 +186,3 @@ def load_loss(args):
     if args.model != "sp-nerf":
         raise ValueError(f'model {args.model} is not valid')
     return SatNerfLoss(lambda_sc=args.sc_lambda) if args.beta else SNerfLoss(lambda_sc=args.sc_lambda)
-
-
-def mse(image_pred, image_gt, valid_mask=None, reduction='mean'):
-    """metrics.py:197-204."""
-    value = (image_pred - image_gt) ** 2
-    if valid_mask is not None:
-        value = value[valid_mask]
-    return torch.mean(value) if reduction == 'mean' else value
-
-
-def psnr(image_pred, image_gt, valid_mask=None, reduction='mean'):
-    """metrics.py:206-207."""
-    return -10 * torch.log10(mse(image_pred, image_gt, valid_mask, reduction))

@@ -39,6 +39,14 @@ def allreduce_mean_(flat):
     return flat
 
 
+def broadcast_(flat, src=0):
+    """Every rank takes rank `src`'s copy of the flat parameter buffer (what DDP / Lightning do at construction:
+    without it replicas built from different RNG states would stay different for the whole run)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src=src)
+    return flat
+
+
 def gather_rays(local, n_total, dst=0):
     """Concatenate per-ray outputs of a sharded inference on rank `dst` (others get None)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

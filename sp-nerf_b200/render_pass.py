@@ -10,15 +10,17 @@ from . import engine as E
 
 
 class _Pass(torch.autograd.Function):
-    """inputs: (module, rays, z, xyz, dir_override, labels, t_emb, noise, noise_std, *parameters)
-    outputs: out (P,n_out), weights (B,N), transparency (B,N), rgb (B,3), depth (B), sem_logits (B,C)|empty"""
+    """inputs: (module, rays, z, xyz, dir_override, labels, t_emb, noise, noise_std, grad_mode, *parameters)
+    outputs: out (P,n_out), weights (B,N), transparency (B,N), rgb (B,3), depth (B), sem_logits (B,C)|empty
+    `grad_mode` is torch.is_grad_enabled() at the call site: inside forward() grad mode is always off and
+    needs_input_grad only mirrors the inputs' requires_grad flags, so neither tells a no_grad caller apart."""
 
     @staticmethod
-    def forward(ctx, module, rays, z, xyz, dir_override, labels, t_emb, noise, noise_std, *params):
+    def forward(ctx, module, rays, z, xyz, dir_override, labels, t_emb, noise, noise_std, grad_mode, *params):
         eng = module.engine
         eng.ensure_packed()
         n = z.shape[1]
-        need_grad = any(ctx.needs_input_grad)     # False under no_grad or with frozen parameters
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)     # no activation saves for no_grad / frozen callers
         sky, sky_hidden = eng.sky(rays)
         t_emb_c = None if t_emb is None else t_emb.detach().float().contiguous()
         out, saves = eng.forward(rays, n, z=None if xyz is not None else z, xyz=xyz, dir_override=dir_override,
@@ -26,6 +28,7 @@ class _Pass(torch.autograd.Function):
         weights, trans, rgb, rgb_raw, depth, sem = E.composite_fwd(
             out, z, eng.n_out, eng.col_sem, eng.n_sem, noise=noise, noise_std=noise_std, want_raw=need_grad)
         ctx.module, ctx.n, ctx.noise_std = module, n, noise_std
+        eng.last_saved_bytes = 0 if saves is None else saves.numel()      # observable by tests (no_grad => 0)
         ctx.has_t = t_emb is not None
         ctx.save_for_backward(rays, z, labels, t_emb_c, noise, out, saves, weights, trans, rgb_raw, sky, sky_hidden)
         if sem is None:
@@ -48,12 +51,13 @@ class _Pass(torch.autograd.Function):
             g_out_ext=c(g_out_ext), noise=noise, noise_std=ctx.noise_std)
         _, views, g_temb = eng.backward(g_out, out, rays, n, saves, absmax, labels=labels, t_emb=t_emb,
                                         g_sky_ray=g_sky_ray, sky=sky, sky_hidden=sky_hidden)
-        return (None, None, None, None, None, None, g_temb if ctx.has_t else None, None, None) + tuple(views)
+        return (None, None, None, None, None, None, g_temb if ctx.has_t else None, None, None, None) + tuple(views)
 
 
 def run_pass(module, rays, z, xyz=None, dir_override=None, labels=None, t_emb=None, noise=None, noise_std=0.0):
     params = tuple(module.parameters())
-    return _Pass.apply(module, rays, z, xyz, dir_override, labels, t_emb, noise, float(noise_std), *params)
+    return _Pass.apply(module, rays, z, xyz, dir_override, labels, t_emb, noise, float(noise_std),
+                       torch.is_grad_enabled(), *params)
 
 
 def _f32c(t):
@@ -100,14 +104,15 @@ class _Rows(torch.autograd.Function):
     """SPNeRF.forward on explicit points: one 'ray' per point, no compositing."""
 
     @staticmethod
-    def forward(ctx, module, rays, xyz, labels, t_emb, *params):
+    def forward(ctx, module, rays, xyz, labels, t_emb, grad_mode, *params):
         eng = module.engine
         eng.ensure_packed()
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         sky, sky_hidden = eng.sky(rays)
         t_c = None if t_emb is None else t_emb.detach().float().contiguous()
         out, saves = eng.forward(rays, 1, xyz=xyz, labels=labels, t_emb=t_c, sky=sky, save=need_grad)
         ctx.module, ctx.has_t = module, t_emb is not None
+        eng.last_saved_bytes = 0 if saves is None else saves.numel()
         ctx.save_for_backward(rays, labels, t_c, out, saves, sky, sky_hidden)
         return out
 
@@ -123,7 +128,7 @@ class _Rows(torch.autograd.Function):
         g_sky = g_out[:, 5:8].contiguous()
         _, views, g_t = eng.backward(g_out, out, rays, 1, saves, absmax, labels=labels, t_emb=t_c, g_sky_ray=g_sky,
                                      sky=sky, sky_hidden=sky_hidden)
-        return (None, None, None, None, g_t if ctx.has_t else None) + tuple(views)
+        return (None, None, None, None, g_t if ctx.has_t else None, None) + tuple(views)
 
 
 def point_rows(module, xyz, sun_d, t_emb=None, labels=None):
@@ -135,4 +140,4 @@ def point_rows(module, xyz, sun_d, t_emb=None, labels=None):
     lab = None
     if module.sem and labels is not None:
         lab = labels.detach().reshape(-1).long().contiguous()
-    return _Rows.apply(module, rays, xyz, lab, t_emb, *tuple(module.parameters()))
+    return _Rows.apply(module, rays, xyz, lab, t_emb, torch.is_grad_enabled(), *tuple(module.parameters()))

@@ -59,7 +59,7 @@ def fused_step(model, args, batch, lambda_ds=1.0, lambda_ss=1.0, use_all_depth=F
     weights, trans, rgb, rgb_raw, depth, sem = E.composite_fwd(out, z, eng.n_out, eng.col_sem, eng.n_sem)
     launches += 1
     t.mark("composite_fwd")
-    scalars, g_rgb, g_depth, g_sem = E.losses(
+    scalars, g_rgb, g_depth, g_sem, _ = E.losses(
         b, rgb=rgb, rgb_target=batch["rgbs"], depth=depth, z=z, weights=weights,
         target_depth=batch["depths"][:, 0].contiguous(), target_weight=batch["depths"][:, 1].contiguous(),
         target_std=batch["depth_std"], valid_depth=batch["valid_depth"], lambda_ds=lambda_ds,

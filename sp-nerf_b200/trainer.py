@@ -58,6 +58,9 @@ class Trainer:
         self.models = models
         self.params = get_parameters(models)
         self.flat, self.offsets = flatten_parameters_(self.params)
+        parallel.broadcast_(self.flat)               # replicas start from rank 0's weights, as under DDP
+        if hasattr(models["coarse"], "engine") and self.device.type == "cuda":
+            models["coarse"].engine.mark_dirty()
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.grad = torch.zeros_like(self.flat)

@@ -8,7 +8,7 @@ import torch
 from oracle import spnerf_oracle as O
 from parity_common import GOLDEN, build_model, load_case, make_args, state_hash
 
-CASES = ["c1_test_sem", "c2_train_depth_sem", "c3_train_guided_mapping_sc", "guided_test_nosem", "beta_small"]
+CASES = ["c1_test_sem", "c2_train_depth_sem", "c3_train_guided_mapping_sc", "guided_test_nosem", "beta_small", "beta_512"]
 
 
 def _params(name, g, meta):
@@ -16,9 +16,9 @@ def _params(name, g, meta):
         P = {k[2:]: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in g.files
              if k.startswith("w_") and k != "w_t_table"}
         return P, torch.from_numpy(g["w_t_table"]).clone().requires_grad_(True)
-    model, _, _ = build_model(meta, "cpu")
+    model, t_mod, _ = build_model(meta, "cpu")      # the transient table follows the model in the seeded stream
     assert state_hash(model.state_dict()) == meta["state_sha256"], "seeded init no longer matches the reference's"
-    return dict(model.named_parameters()), None
+    return dict(model.named_parameters()), (t_mod.weight if t_mod is not None else None)
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -39,6 +39,15 @@ def _worker(rank, world, port, q):
             ok = ok and cls.dtype == torch.int32 and torch.equal(cls, torch.arange(101, dtype=torch.int32))
         else:
             ok = ok and gathered is None
+        # replicas built from different RNG states end up with rank 0's weights (DDP-style broadcast at construction)
+        from spnerf_b200 import config
+        from spnerf_b200.trainer import Trainer
+        torch.manual_seed(100 + rank)
+        tr = Trainer(config.make_args(sem=True, num_sem_classes=3, fc_units=512, lr=5e-4), "cpu")
+        copies = [torch.empty_like(tr.flat) for _ in range(world)]
+        dist.all_gather(copies, tr.flat)
+        ok = ok and all(torch.equal(c, copies[0]) for c in copies) and float(tr.flat.abs().sum()) > 0
+        ok = ok and all(p.data_ptr() >= tr.flat.data_ptr() for p in tr.params)      # still views of the flat buffer
         q.put((rank, ok, mine["rays"].shape[0]))
     finally:
         dist.destroy_process_group()

@@ -67,7 +67,7 @@ def test_umma_descriptors(mode, n, k):
 # ------------------------------------------------------------------------------------------------
 # golden vectors from the reference
 # ------------------------------------------------------------------------------------------------
-GOLDEN_CASES = ["c1_test_sem", "c2_train_depth_sem", "guided_test_nosem", "c3_train_guided_mapping_sc"]
+GOLDEN_CASES = ["c1_test_sem", "c2_train_depth_sem", "guided_test_nosem", "c3_train_guided_mapping_sc", "beta_512"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
