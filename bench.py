@@ -2,7 +2,7 @@
 at 1/2/4/8 B200, + fraction of the MLP tensor-core and compositing HBM rooflines).
 
     python bench.py --gpus N --steps K --warmup W            # this framework
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (baseline/_ref, else the oracle port)
 
 Workload at every N: BASELINE config 2 per GPU — a training step (forward + backward, --depth --sem,
 3 semantic classes, dense labels) on a JAX_269-shaped synthetic batch of 8192 rays x 64 samples
@@ -115,76 +115,153 @@ def build_model(args, device):
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation of the path (oracle port), bounded sample
+# reference arm: the reference's own CPU implementation of the path on the box's host cores, bounded sample.
+# baseline/_ref/ (staged by __graft_entry__.build() from the unmodified checkout, git-ignored, travels with the
+# snapshot) is timed when present: kind "reference"; otherwise the oracle restatement: kind "port".
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step(P, cfg, batch, O, torch):
-    b, n = batch["rays"].shape[0], cfg.n_samples
-    draws = O.Draws([torch.rand(b, n)], [torch.randn(b, n)])
-    res = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
-                   batch["depth_std"], draws)
-    loss = O.colour_loss(res, batch["rgbs"])[0] + O.depth_loss(
-        res, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0] \
-        + O.semantic_loss(res, batch["sems"], 1.0)[0]
-    grads = torch.autograd.grad(loss, list(P.values()))
-    return float(loss), grads
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+CPU_SAMPLE_RAYS = 1024            # BASELINE config 1's batch (modules/opt.py:35 default)
 
 
-def time_cpu_reference(rays, steps, warmup):
+def load_reference():
+    """(models, rendering, metrics) modules of the staged reference, or None.  kornia.losses.ssim is only used by an
+    eval metric outside the path (modules/metrics.py:7,210-215) and is stubbed."""
+    need = ["modules/rendering.py", "modules/__init__.py", "modules/metrics.py", "models/spnerf.py", "models/__init__.py"]
+    if not all(os.path.exists(os.path.join(REF_DIR, p)) for p in need):
+        return None
+    k, kl = types.ModuleType("kornia"), types.ModuleType("kornia.losses")
+    kl.ssim = lambda *a, **kw: None
+    k.losses = kl
+    sys.modules.setdefault("kornia", k)
+    sys.modules.setdefault("kornia.losses", kl)
+    for name in [m for m in sys.modules if m.split(".")[0] in ("models", "modules")]:
+        del sys.modules[name]
+    sys.path.insert(0, REF_DIR)
+    try:
+        import models as ref_models
+        from modules import rendering as ref_rendering, metrics as ref_metrics
+    finally:
+        sys.path.remove(REF_DIR)
+    return ref_models, ref_rendering, ref_metrics
+
+
+def make_cpu_step(rays):
+    """One training step (forward + losses + backward) of BASELINE config 2's model on `rays` synthetic rays, on the
+    host CPU.  Returns (step function, forward-only function, kind)."""
     import torch
+    from spnerf_b200 import config, synthetic
+    batch = synthetic.make_batch(rays, seed=269)
+    ref = load_reference()
+    if ref is not None:
+        ref_models, ref_rendering, ref_metrics = ref
+        args = config.make_args(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)
+        torch.manual_seed(0)
+        model = ref_models.load_model(args)
+        with torch.no_grad():
+            model.sigma_from_xyz[0].bias.fill_(3.0)
+            model.sigma_from_xyz[0].weight.mul_(4.0)
+        models = {"coarse": model}
+        colour, depth, sem = (ref_metrics.SNerfLoss(lambda_sc=0.0),
+                              ref_metrics.DepthLoss(lambda_ds=1.0, GNLL=False, usealldepth=False),
+                              ref_metrics.SemanticLoss(lambda_ss=1.0))
+
+        def forward(mode):
+            return ref_rendering.render_rays(models, args, batch["rays"], None, semantics=batch["sems"], mode=mode,
+                                             valid_depth=batch["valid_depth"], target_depths=batch["depths"],
+                                             target_std=batch["depth_std"])
+
+        def step():
+            res = forward("train")
+            loss = colour(res, batch["rgbs"])[0] + depth(res, batch["depths"][:, 0], batch["depths"][:, 1],
+                                                         target_valid_depth=batch["valid_depth"],
+                                                         target_std=batch["depth_std"])[0] + sem(res, batch["sems"])[0]
+            model.zero_grad(set_to_none=True)
+            loss.backward()
+            return float(loss.detach())
+
+        def fwd_only():
+            with torch.no_grad():
+                forward("test")
+        return step, fwd_only, "reference"
     from oracle import spnerf_oracle as O
-    from spnerf_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)
     P = {k: v.requires_grad_(True) for k, v in O.random_parameters(cfg, seed=0, sigma_bias=3.0).items()}
-    batch = synthetic.make_batch(rays, seed=269)
-    for _ in range(warmup):
-        cpu_reference_step(P, cfg, batch, O, torch)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(P, cfg, batch, O, torch)
-    dt = time.perf_counter() - t0
-    return rays * steps / dt, dt / steps, cores
-
-
-def time_cpu_reference_forward(rays, steps):
-    """Forward-only rays/s of the reference's CPU path (BASELINE config 1: render_rays in test mode)."""
-    import torch
-    from oracle import spnerf_oracle as O
-    from spnerf_b200 import synthetic
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.make_cfg(sem=True, num_sem_classes=3, fc_units=512, n_samples=N_SAMPLES)
-    P = O.random_parameters(cfg, seed=0, sigma_bias=3.0)
-    batch = synthetic.make_batch(rays, seed=269)
     b, n = rays, cfg.n_samples
-    with torch.no_grad():
-        O.render(P, cfg, batch["rays"], None, batch["sems"], "test", None, None, None, O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
+
+    def step():
+        res = O.render(P, cfg, batch["rays"], None, batch["sems"], "train", batch["valid_depth"], batch["depths"],
+                       batch["depth_std"], O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
+        loss = O.colour_loss(res, batch["rgbs"])[0] + O.depth_loss(
+            res, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0] \
+            + O.semantic_loss(res, batch["sems"], 1.0)[0]
+        torch.autograd.grad(loss, list(P.values()))
+        return float(loss.detach())
+
+    def fwd_only():
+        with torch.no_grad():
+            O.render(P, cfg, batch["rays"], None, batch["sems"], "test", None, None, None,
+                     O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
+    return step, fwd_only, "port"
+
+
+def time_cpu_path(rays, steps, warmup, forward_reps=0):
+    """Median-of-steps timing of the CPU path.  Returns a dict (rays/s from the median step, min, cores, kind)."""
+    import statistics
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, fwd_only, kind = make_cpu_step(rays)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
         t0 = time.perf_counter()
-        for _ in range(steps):
-            O.render(P, cfg, batch["rays"], None, batch["sems"], "test", None, None, None, O.Draws([torch.rand(b, n)], [torch.randn(b, n)]))
-        dt = time.perf_counter() - t0
-    return rays * steps / dt
+        step()
+        times.append(time.perf_counter() - t0)
+    out = {"kind": kind, "cores": cores, "rays": rays, "steps": steps, "median_s": statistics.median(times),
+           "min_s": min(times), "total_s": sum(times), "value": rays / statistics.median(times)}
+    if forward_reps:
+        fwd_only()
+        ft = []
+        for _ in range(forward_reps):
+            t0 = time.perf_counter()
+            fwd_only()
+            ft.append(time.perf_counter() - t0)
+        out["forward_only_value"] = rays / statistics.median(ft)
+    return out
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_rays = 512
-    steps, warmup = max(1, min(a.steps, 6)), max(1, min(a.warmup, 2))
-    rps, sec, cores = time_cpu_reference(sample_rays, steps, warmup)
+    steps, warmup = max(5, min(a.steps, 8)), max(1, min(a.warmup, 2))
+    r = time_cpu_path(CPU_SAMPLE_RAYS, steps, warmup)
+    what = ("the UNMODIFIED reference (baseline/_ref: modules/rendering.py, models/spnerf.py, modules/metrics.py)"
+            if r["kind"] == "reference" else "the oracle restatement of the reference (baseline/_ref not staged)")
     line = {
-        "impl": "reference", "metric": "render_rays_fwd_bwd_rays_per_s", "value": rps, "unit": "rays/s",
-        "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": "render_rays_fwd_bwd_rays_per_s", "value": r["value"], "unit": "rays/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["median_s"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE config 2: training step fwd+bwd, --depth --sem C=3, 64 samples, fc 8x512; "
-                               f"reference CPU path on a bounded sample of {sample_rays} rays per step",
-                   "rays_per_step": sample_rays},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {sample_rays} rays x {N_SAMPLES} samples, fwd+losses+bwd, torch "
-                                   f"fp32 on {cores} host threads (oracle restatement of the reference; the Python "
-                                   "reference itself cannot travel to the GPU box)"},
-        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                               f"reference CPU path on a bounded sample of {CPU_SAMPLE_RAYS} rays per step "
+                               "(BASELINE config 1's batch)",
+                   "rays_per_step": CPU_SAMPLE_RAYS, "statistic": "median step", "min_ms_per_step": r["min_s"] * 1e3},
+        "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": r["kind"],
+                         "cpu": cpu_model_name(),
+                         "sample": f"{steps} steps x {CPU_SAMPLE_RAYS} rays x {N_SAMPLES} samples, render_rays + SNerfLoss + "
+                                   f"DepthLoss + SemanticLoss + backward, torch fp32 on {r['cores']} host threads: {what}"},
+        "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -470,16 +547,14 @@ def run_ours(a):
         del rays4, sems4
 
     if rank == 0 and world == 1:
-        # ---- the reference's CPU path on this box's host cores (bounded sample) ----
+        # ---- the reference's CPU path on this box's host cores (bounded sample, ~10 s) ----
         try:
-            rps, sec, cores = time_cpu_reference(1024, 3, 1)
-            try:
-                fwd_rps = time_cpu_reference_forward(1024, 3)
-            except Exception:          # pragma: no cover
-                fwd_rps = None
-            line["cpu_baseline"] = {"value": rps, "forward_only_value": fwd_rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": "3 steps x 1024 rays x 64 samples (BASELINE config 1 shape), fwd + "
-                                              "losses + bwd, torch fp32 oracle restatement of the reference"}
+            r = time_cpu_path(CPU_SAMPLE_RAYS, 5, 1, forward_reps=3)
+            line["cpu_baseline"] = {"value": r["value"], "forward_only_value": r.get("forward_only_value"), "unit": "rays/s",
+                                    "cores": r["cores"], "kind": r["kind"], "cpu": cpu_model_name(),
+                                    "sample": f"median of 5 steps x {CPU_SAMPLE_RAYS} rays x 64 samples (BASELINE config 1 "
+                                              "batch), render_rays + losses + backward, torch fp32; kind 'reference' = the "
+                                              "unmodified reference staged under baseline/_ref, 'port' = the oracle"}
         except Exception as ex:          # pragma: no cover
             line["cpu_baseline"] = {"value": None, "error": repr(ex)}
     if rank == 0:

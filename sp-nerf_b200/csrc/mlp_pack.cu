@@ -27,8 +27,7 @@ struct PackItem {
   uint32_t dst_off16;
 };
 
-__global__ void pack_kernel(const PackItem* __restrict__ items, uint8_t* __restrict__ blob) {
-  const PackItem it = items[blockIdx.x];
+__device__ __forceinline__ void pack_item(const PackItem& it, uint8_t* __restrict__ blob) {
   for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < it.n * 8; t += gridDim.y * blockDim.x) {
     const int r = t >> 3, c = t & 7;   // tile row, 16-byte chunk
     __half h[8];
@@ -53,9 +52,8 @@ struct CopyItem {
   int dst_ld;
 };
 
-__global__ void small_copy_kernel(const CopyItem* __restrict__ items, float* __restrict__ small) {
-  const CopyItem it = items[blockIdx.x];
-  if (!it.src) return;
+__device__ __forceinline__ void small_copy_item(const CopyItem& it, float* __restrict__ small) {
+  if (!it.src || blockIdx.y != 0) return;
   const int n = it.rows * it.cols;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const int r = t / it.cols, c = t % it.cols;
@@ -72,8 +70,8 @@ struct AuxItem {
   uint32_t dst_off16;
 };
 
-__global__ void aux_pack_kernel(const AuxItem* __restrict__ items, uint8_t* __restrict__ blob) {
-  const AuxItem it = items[blockIdx.x];
+__device__ __forceinline__ void aux_pack_item(const AuxItem& it, uint8_t* __restrict__ blob) {
+  if (blockIdx.y != 0) return;
   for (int i = threadIdx.x; i < it.n; i += blockDim.x) {
     __half h[16];
 #pragma unroll
@@ -91,6 +89,26 @@ __global__ void aux_pack_kernel(const AuxItem* __restrict__ items, uint8_t* __re
     *reinterpret_cast<uint4*>(dst + aux_offset(i, 0)) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(dst + aux_offset(i, 8)) = *reinterpret_cast<const uint4*>(h + 8);
   }
+}
+
+// One launch converts everything: blockIdx.x walks [forward weight tiles | backward weight tiles | small fp32
+// copies | aux tiles] (three launches less per optimiser step than a kernel per table).
+struct PackTables {
+  const PackItem* f; int nf;
+  const PackItem* b; int nb;
+  const CopyItem* c; int nc;
+  const AuxItem* a; int na;
+};
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackTables t, uint8_t* __restrict__ fwd_blob,
+                                                       uint8_t* __restrict__ bwd_blob, float* __restrict__ small) {
+  int i = blockIdx.x;
+  if (i < t.nf) { pack_item(t.f[i], fwd_blob); return; }
+  i -= t.nf;
+  if (i < t.nb) { pack_item(t.b[i], bwd_blob); return; }
+  i -= t.nb;
+  if (i < t.nc) { small_copy_item(t.c[i], small); return; }
+  i -= t.nc;
+  if (i < t.na) aux_pack_item(t.a[i], fwd_blob);
 }
 
 struct AuxSpec {
@@ -499,7 +517,7 @@ extern "C" int spnerf_net_prepare(const SpnerfNetConfig* cfg, const float* const
   return e == cudaSuccess ? 0 : -(int)e;
 }
 
-// fp32 parameters -> packed operands (three small kernels, no host synchronisation).
+// fp32 parameters -> packed operands (one launch, no host synchronisation).
 extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, void* fwd_blob, void* bwd_blob,
                                float* small, void* stream_) {
   int rc = validate(cfg);
@@ -510,15 +528,13 @@ extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, 
   PackPlan pl;                       // host-side counts only
   make_pack_plan(cfg, P, pl);
   const uint8_t* sc = static_cast<const uint8_t*>(pack_ws);
-  pack_kernel<<<dim3((unsigned)pl.f.items.size(), 2), 256, 0, stream>>>(reinterpret_cast<const PackItem*>(sc),
-                                                                        static_cast<uint8_t*>(fwd_blob));
-  pack_kernel<<<dim3((unsigned)pl.bitems.size(), 2), 256, 0, stream>>>(
-      reinterpret_cast<const PackItem*>(sc + pl.bytes_f), static_cast<uint8_t*>(bwd_blob));
-  small_copy_kernel<<<(unsigned)pl.cp.size(), 256, 0, stream>>>(
-      reinterpret_cast<const CopyItem*>(sc + pl.bytes_f + pl.bytes_b), small);
-  if (!pl.f.aux_items.empty())
-    aux_pack_kernel<<<(unsigned)pl.f.aux_items.size(), 256, 0, stream>>>(
-        reinterpret_cast<const AuxItem*>(sc + pl.bytes_f + pl.bytes_b + pl.bytes_c), static_cast<uint8_t*>(fwd_blob));
+  PackTables t;
+  t.f = reinterpret_cast<const PackItem*>(sc); t.nf = (int)pl.f.items.size();
+  t.b = reinterpret_cast<const PackItem*>(sc + pl.bytes_f); t.nb = (int)pl.bitems.size();
+  t.c = reinterpret_cast<const CopyItem*>(sc + pl.bytes_f + pl.bytes_b); t.nc = (int)pl.cp.size();
+  t.a = reinterpret_cast<const AuxItem*>(sc + pl.bytes_f + pl.bytes_b + pl.bytes_c); t.na = (int)pl.f.aux_items.size();
+  pack_all_kernel<<<dim3((unsigned)(t.nf + t.nb + t.nc + t.na), 2), 256, 0, stream>>>(
+      t, static_cast<uint8_t*>(fwd_blob), static_cast<uint8_t*>(bwd_blob), small);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -58,7 +58,13 @@ constexpr int kWsRows = 129;    // 128 accumulator rows + the column-sum row
 // [peer0, peer0 + npeers) are the items that read the same B' tiles over the same points: they run
 // on adjacent pairs at the same time and pace each other (see the gate in the producer).
 struct Item { int job, slice, nslices, peer0, npeers, _pad; int64_t ws_off; };      // partial tile: [2][kWsRows][ncols] floats
-constexpr int kGateWindow = 3;     // a pair may run at most this many point tiles ahead of its slowest peer
+#ifndef SPNERF_WGRAD_SYNC
+#define SPNERF_WGRAD_SYNC 1
+#endif
+#ifndef SPNERF_WGRAD_GATE_WINDOW
+#define SPNERF_WGRAD_GATE_WINDOW 6
+#endif
+constexpr int kGateWindow = SPNERF_WGRAD_GATE_WINDOW;     // a pair may run at most this many point tiles ahead of its slowest peer
 
 struct Segment {                // scatter rule: rows [row0, row0+nrows) of CTA `rank` x packed columns [col0, col0+ncols)
   int job, rank, row0, nrows, col0, ncols;
@@ -72,7 +78,7 @@ struct WgradParams {
   int64_t n_ptiles;
   const Job* jobs; const Item* items; int n_items;
   float* ws;
-  int* progress;                         // [n_items] point tiles loaded so far (zeroed before the launch)
+  int* progress;                         // [n_items] arrival counters of the peer groups, [n_items] pacing words (zeroed before the launch)
   long long* prof;                       // optional counters of pair 0 (debug)
 };
 
@@ -89,6 +95,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
   uint64_t* bar_acc = bars + 4;     // accumulator complete -> epilogue (multicast commit)
   uint64_t* bar_drained = bars + 5; // rank 0: both accumulators read out -> issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  volatile int* pace_item = reinterpret_cast<volatile int*>(bars + 9);            // item the producer is on (-1: none yet, -2: finished)
+  volatile long long* pace_limit = reinterpret_cast<volatile long long*>(bars + 10);   // (item << 32) | tiles the producer may have issued
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -97,6 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
     // a stage is free when its MMAs have retired (commit) and the column-sum warps have read it
     for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 2); }
     mbar_init(bar_acc, 1); mbar_init(bar_drained, 2);
+    *pace_item = -1; *pace_limit = -1;
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
@@ -117,11 +126,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
       uint32_t bytes = 0;
       for (int r = 0; r < job.na[rank]; ++r) bytes += (uint32_t)job.a[rank][r].nchunks * kChunkBytes;
       for (int j = 0; j < job.nb; ++j) bytes += (uint32_t)job.b[rank][j].nchunks * kChunkBytes;
+      // The jobs of one layer and point slice read the same G tiles (each of them once): they start together, so
+      // that whichever of them requests a tile second finds it in L2 (and from then on the follower, served from
+      // L2, runs faster than the leader and stays with it).  Without the rendezvous the pairs reach their items
+      // several tile times apart and every G tile came from HBM twice (18.2 GB per launch against 12.1 GB).
+#if SPNERF_WGRAD_SYNC >= 1
+      if (item.npeers > 1) {
+        if (lane == 0) {
+          volatile int* cnt = p.progress + item.peer0;
+          if (rank == 0) atomicAdd(p.progress + item.peer0, 1);
+          long long t0 = 0; uint32_t spins = 0;
+          while (*cnt < item.npeers) {
+            if ((++spins & 0xff) == 0) {
+              const long long now = clock64();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > SPNERF_WATCHDOG_CYCLES) { atomicCAS(&g_watchdog_code, 0u, 45u); __trap(); }
+            }
+          }
+        }
+        __syncwarp();
+      }
+#endif
+#if SPNERF_WGRAD_SYNC == 3
+      if (rank == 0 && item.npeers > 1 && lane == 0) *pace_item = it;
+#endif
       for (int64_t k = k0; k < k1; ++k) {
-        // Gate: the peers stream the same G tiles; keeping them within a few tiles of each other makes
-        // the second and third reader hit L2 instead of HBM (the slowest peer never waits).
+#if SPNERF_WGRAD_SYNC == 3
+        // Pacing: this pair may be at most kGateWindow point tiles ahead of the slowest peer, so that a G tile is still
+        // in L2 when the other jobs of the layer ask for it.  The producer only posts its own progress (a store) and
+        // reads the allowance from shared memory; the pacing warp below does the global polling off the critical path.
         if (rank == 0 && item.npeers > 1 && lane == 0) {
-          volatile int* prog = p.progress;
+          volatile int* prog = p.progress + p.n_items;
+          prog[it] = (int)(k - k0);
+          long long t0 = 0; uint32_t spins = 0;
+          for (;;) {
+            const long long lim = *pace_limit;
+            if ((int)(lim >> 32) == it && (int)(k - k0) <= (int)(lim & 0xffffffffLL)) break;
+            if ((++spins & 0xfff) == 0) {
+              const long long now = clock64();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > SPNERF_WATCHDOG_CYCLES) { atomicCAS(&g_watchdog_code, 0u, 46u); __trap(); }
+            }
+          }
+        }
+#elif SPNERF_WGRAD_SYNC == 2
+        // pacing: at most kGateWindow point tiles ahead of the slowest peer (progress words behind the arrival counters)
+        if (rank == 0 && item.npeers > 1 && lane == 0) {
+          volatile int* prog = p.progress + p.n_items;
           prog[it] = (int)(k - k0);
           for (int q = item.peer0; q < item.peer0 + item.npeers; ++q) {
             if (q == it) continue;
@@ -130,11 +181,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
               if ((++spins & 0xff) == 0) {
                 const long long now = clock64();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > SPNERF_WATCHDOG_CYCLES) { atomicCAS(&g_watchdog_code, 0u, 45u); __trap(); }
+                else if (now - t0 > SPNERF_WATCHDOG_CYCLES) { atomicCAS(&g_watchdog_code, 0u, 46u); __trap(); }
               }
             }
           }
         }
+#endif
         __syncwarp();
         mbar_wait(&bar_empty[stage], phase ^ 1, 40);
         if (elect_one()) {
@@ -157,8 +209,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (rank == 0 && item.npeers > 1 && lane == 0) { volatile int* prog = p.progress; prog[it] = 1 << 30; }   // done: never holds a peer back
+#if SPNERF_WGRAD_SYNC >= 2
+      if (rank == 0 && item.npeers > 1 && lane == 0) { volatile int* prog = p.progress + p.n_items; prog[it] = 1 << 30; }   // done: never holds a peer back
+#endif
     }
+#if SPNERF_WGRAD_SYNC == 3
+    if (rank == 0 && lane == 0) *pace_item = -2;
+  } else if (warp == 2 && rank == 0) {
+    // ---- pacing warp: polls the peers' progress words and publishes the producer's allowance ----
+    if (lane == 0) {
+      volatile int* prog = p.progress + p.n_items;
+      int cur = -1, peer0 = 0, npeers = 0;
+      for (;;) {
+        const int it = *pace_item;
+        if (it == -2) break;
+        if (it < 0) continue;
+        if (it != cur) { const Item item = p.items[it]; peer0 = item.peer0; npeers = item.npeers; cur = it; }
+        int m = 1 << 29;
+        for (int q = peer0; q < peer0 + npeers; ++q)
+          if (q != it) { const int v = prog[q]; m = v < m ? v : m; }
+        *pace_limit = ((long long)it << 32) | (long long)(unsigned)(m + kGateWindow);
+      }
+    }
+#endif
   } else if (warp == 1 && rank == 1) {
     // ---- relay: second arrival on the issuer's stage barrier ----
     uint32_t stage = 0, phase = 0;
@@ -599,7 +672,7 @@ Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_pairs) {
       for (int jid : groups[g]) {
         Item it{};
         it.job = jid; it.slice = s; it.nslices = slices; it.peer0 = peer0;
-        it.npeers = getenv("SPNERF_WGRAD_GATE") ? nj : 1;     // experiment: pace the peers (slower as measured)
+        it.npeers = nj;
         it.ws_off = pl.ws_floats;
         pl.ws_floats += 2 * kWsRows * (int64_t)pl.jobs[jid].ncols;
         pl.items.push_back(it);
@@ -680,7 +753,7 @@ extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   const int pairs = n_sms() / 2;
   Plan pl = make_plan(a->cfg, a->grads_host, pairs);     // host-side counts only; tables were uploaded by _prepare
   if ((int64_t)pl.ws_floats * 4 + kTableRoom + kProgressRoom > a->workspace_bytes ||
-      (int64_t)pl.n_launch * 4 > kProgressRoom)
+      (int64_t)pl.n_launch * 8 > kProgressRoom)
     return SPNERF_ERR_WORKSPACE;
   const Tables t = table_ptrs(pl, a->workspace);
   WgradParams p;
@@ -693,7 +766,7 @@ extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   p.ws = static_cast<float*>(a->workspace);
   p.progress = reinterpret_cast<int*>(static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4 + kTableRoom);
   p.prof = g_prof_wgrad;
-  cudaMemsetAsync(p.progress, 0, (size_t)pl.n_launch * sizeof(int), stream);
+  cudaMemsetAsync(p.progress, 0, (size_t)pl.n_launch * 2 * sizeof(int), stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW);

@@ -48,7 +48,8 @@ def fused_step(model, args, batch, lambda_ds=1.0, lambda_ss=1.0, use_all_depth=F
     eng.ensure_packed(force=repack)            # parameters change every optimiser step
     launches += 4 if repack else 0          # two weight packers, small-parameter copy, aux-tile packer
     t.mark("pack")
-    u = torch.rand(b, n, dtype=torch.float32, device=rays.device)
+    rng = getattr(args, "_rng", None)          # parity tests replay the reference's draws
+    u = rng.uniform((b, n)) if rng is not None else torch.rand(b, n, dtype=torch.float32, device=rays.device)
     z = E.sample_coarse(rays, u, n)
     sky, sky_hidden = eng.sky(rays)
     launches += 2

@@ -129,7 +129,9 @@ def test_guided_sampler_bit_exact(name):
     var_sum = torch.from_numpy(var).sum(-1).numpy()           # torch's own reduction order (checked on CPU)
     exact = np.sqrt(var_sum.astype(np.float64)).astype(np.float32)
     clean = (exact == g["mid_std"]) | ~uses_std
-    assert clean.mean() > 0.9
+    excluded = 1.0 - float(clean.mean())
+    print(f"{name}: {int((~clean).sum())} of {clean.size} rays excluded from the bit-exact comparison ({100 * excluded:.2f} %)")
+    assert excluded <= 0.02, excluded      # MKL's sqrt is off by one ulp in ~0.6 % of inputs (measured)
     clean_t = torch.from_numpy(clean)
     got_i, want_i = inds.cpu(), torch.from_numpy(g["mid_inds"]).int()
     got_u, want_u = z_unsort.cpu(), torch.from_numpy(g["out_z_vals_unsort_coarse"])
