@@ -423,12 +423,8 @@ def run_ours(a):
             for p in model.parameters():
                 p.grad = None
             loss.backward()
-            if world > 1:                # one all-reduce of the flattened gradients
-                gl = [p.grad for p in model.parameters()]
-                flat = torch._utils._flatten_dense_tensors(gl)
-                parallel.allreduce_mean_(flat)
-                for g_, f_ in zip(gl, torch._utils._unflatten_dense_tensors(flat, gl)):
-                    g_.copy_(f_)
+            if world > 1:                # the .grad tensors are slices of one flat buffer: one in-place all-reduce
+                parallel.allreduce_grads_(model)
             # device -> host read of the step's result: every step's loss is copied to pinned memory and read on
             # the host one step later (the way a training loop logs), so the queue never drains at a step boundary
             k = state["k"]
@@ -465,6 +461,43 @@ def run_ours(a):
                               "every step, batch copied from pinned host memory every step, every step's loss read "
                               "on the host (one step behind the device)"}
 
+    if rank == 0 and world == 1:
+        # ---- the reference's default batch (1024 rays, modules/opt.py:35): host-bound regime.  Wall clock per step
+        # (launch overheads are the point here) of the kernel-by-kernel step, of the same step replayed from one
+        # CUDA graph, and of the public API (render_rays + loss classes + backward); inputs on the device ----
+        b1 = {k: v.to(dev) for k, v in synthetic.make_batch(1024, seed=11).items()}
+
+        def wall_ms(fn, reps=40):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps * 1e3
+
+        def api_step_1024():
+            model.engine.mark_dirty()
+            res = render_rays({"coarse": model}, args, b1["rays"], None, semantics=b1["sems"], mode="train",
+                              valid_depth=b1["valid_depth"], target_depths=b1["depths"], target_std=b1["depth_std"])
+            loss = loss_fn(res, b1["rgbs"])[0] + dl(res, b1["depths"][:, 0], b1["depths"][:, 1],
+                                                    target_valid_depth=b1["valid_depth"],
+                                                    target_std=b1["depth_std"])[0] + sl(res, b1["sems"])[0]
+            for p in model.parameters():
+                p.grad = None
+            loss.backward()
+        eager = wall_ms(lambda: train_step.fused_step(model, args, b1, repack=True))
+        launches_1024 = train_step.fused_step(model, args, b1, repack=True)[3]
+        api = wall_ms(api_step_1024)
+        gs = train_step.GraphedStep(model, args, b1)
+        graphed = wall_ms(gs.replay)
+        line["small_batch"] = {"rays": 1024, "fused_step_eager_ms": eager, "fused_step_cuda_graph_ms": graphed,
+                               "public_api_ms": api, "launches_per_step": launches_1024,
+                               "rays_per_s_cuda_graph": 1024 / (graphed / 1e3),
+                               "note": "wall clock per step, inputs on the device; round 1 measured ~34 launches per step"}
+        del gs
+
     # ---- the other BASELINE configurations, through the public API (extra objects; the headline stays C2) ----
     if not a.skip_extra:
         from spnerf_b200 import inference
@@ -485,9 +518,7 @@ def run_ours(a):
                 p_.grad = None
             loss.backward()
             if world > 1:
-                gl = [p_.grad for p_ in model3.parameters()]
-                flat = torch._utils._flatten_dense_tensors(gl)
-                parallel.allreduce_mean_(flat)
+                parallel.allreduce_grads_(model3)
             return loss
         for _ in range(2):
             c3_step()

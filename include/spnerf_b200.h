@@ -216,7 +216,18 @@ typedef struct SpnerfMlpWgrad {
                                 slots fed by g_small_bias / g_emb are not touched                 */
   void* workspace;           /* >= spnerf_mlp_wgrad_workspace_bytes(cfg) bytes                   */
   int64_t workspace_bytes;
+  /* Optional self-cleaning accumulator block (SPNERF_ACCUM_FLOATS floats, zero before the first use): the slots that
+   * are summed with atomics (spnerf_mlp_bwd_data's g_small_bias / g_emb, spnerf_sky_bwd's four outputs) can point
+   * into it at the SPNERF_ACC_* offsets; the reduce kernel of spnerf_mlp_bwd_weights then copies them to their
+   * grads_host slots (rgb_from_xyzdir.2.bias, sun_v_net.6.bias, sigma_from_xyz.0.bias, beta_from_xyz.2.bias,
+   * logit_from_label.2.bias, semantic_embedding.weight, sky_color.*) and clears the block, so a step needs no
+   * memset of the gradient buffer.  `absmax_reset` (optional) is set to 0 by the same kernel (spnerf_composite_bwd
+   * accumulates it with atomicMax).  Both are baked into the tables by spnerf_mlp_wgrad_prepare. */
+  float* accum;
+  float* absmax_reset;
 } SpnerfMlpWgrad;
+enum { SPNERF_ACC_SMALL_BIAS = 0, SPNERF_ACC_EMB = 16, SPNERF_ACC_SKY_W0 = 96, SPNERF_ACC_SKY_B0 = 864,
+       SPNERF_ACC_SKY_W2 = 1120, SPNERF_ACC_SKY_B2 = 1888, SPNERF_ACCUM_FLOATS = 1892 };
 int64_t spnerf_mlp_wgrad_workspace_bytes(const SpnerfNetConfig* cfg);
 /* uploads the GEMM tables into the workspace tail: once per (cfg, grads_host, workspace); syncs the stream */
 int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* args, void* stream);
@@ -295,11 +306,14 @@ typedef struct SpnerfLosses {
   const float* sem_logits; const int64_t* labels; float lambda_ss; int32_t _pad;
   float* g_sem_logits;
   float* losses;               /* 8 floats */
-  void* workspace;             /* >= spnerf_losses_workspace_bytes() bytes */
+  void* workspace;             /* >= spnerf_losses_workspace_bytes() bytes, ZEROED once by the caller; the kernels
+                                  leave it zeroed (no memsets on the stream) */
   /* --GNLL subset variant (metrics.py:76,129-130: GaussianNLLLoss with the predicted STD passed as the variance,
    * eps 1e-6): needs use_all_depth = 0; the gradient reaches the weights through the predicted STD */
   int32_t gnll, _pad2;
   float* g_weights;            /* (n_rays, n_samples), written when gnll != 0 */
+  int64_t target_stride;       /* element stride of target_depth / target_weight (0 = 1); 2 reads the two columns of the
+                                  reference's (n_rays, 2) `depths` tensor in place */
 } SpnerfLosses;
 int64_t spnerf_losses_workspace_bytes(void);
 int spnerf_losses(const SpnerfLosses* args, void* stream);
@@ -351,6 +365,11 @@ int spnerf_loss_uncertainty(const SpnerfLossUncertainty* args, int backward, voi
  * ------------------------------------------------------------------------------------------- */
 int spnerf_sample_coarse(const float* rays, const float* t_table, const float* uniforms, int64_t n_rays,
                          int32_t n_samples, float* z, void* stream);
+/* Same sampler with the uniforms drawn on the device (replaces the torch.rand of rendering.py:143): Philox4x32-10
+ * keyed by rng_state[0] (seed), counter (element, rng_state[1] = step).  rng_state: 3 x uint64 {seed, step, 0};
+ * the launch advances the step itself, so a captured CUDA graph draws fresh numbers on every replay. */
+int spnerf_sample_coarse_rng(const float* rays, const float* t_table, uint64_t* rng_state, int64_t n_rays,
+                             int32_t n_samples, float* z, void* stream);
 
 typedef struct SpnerfGuided {
   const float* rays;          /* (n_rays,11); rays[0,6:8] clamp every ray (rendering.py:95) */

@@ -157,7 +157,8 @@ class Losses(ctypes.Structure):
                 ("target_std", VP), ("valid_depth", VP), ("lambda_ds", F32), ("use_all_depth", I32),
                 ("g_depth", VP),
                 ("sem_logits", VP), ("labels", VP), ("lambda_ss", F32), ("_pad", I32), ("g_sem_logits", VP),
-                ("losses", VP), ("workspace", VP), ("gnll", I32), ("_pad2", I32), ("g_weights", VP)]
+                ("losses", VP), ("workspace", VP), ("gnll", I32), ("_pad2", I32), ("g_weights", VP),
+                ("target_stride", I64)]
 
 
 class LossSolar(ctypes.Structure):
@@ -188,7 +189,12 @@ class MlpBwd(ctypes.Structure):
 
 class MlpWgrad(ctypes.Structure):
     _fields_ = [("cfg", NetConfig), ("n_points", I64), ("saves", VP), ("grad_saves", VP), ("scale", VP),
-                ("grads_host", ctypes.POINTER(VP)), ("workspace", VP), ("workspace_bytes", I64)]
+                ("grads_host", ctypes.POINTER(VP)), ("workspace", VP), ("workspace_bytes", I64),
+                ("accum", VP), ("absmax_reset", VP)]
+
+
+# offsets (floats) into the self-cleaning accumulator block (include/spnerf_b200.h SPNERF_ACC_*)
+ACC_SMALL_BIAS, ACC_EMB, ACC_SKY_W0, ACC_SKY_B0, ACC_SKY_W2, ACC_SKY_B2, ACCUM_FLOATS = 0, 16, 96, 864, 1120, 1888, 1892
 
 
 def _declare_rest(L):
@@ -209,6 +215,8 @@ def _declare_rest(L):
     L.spnerf_mlp_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(NetConfig)]
     L.spnerf_sample_coarse.restype = ctypes.c_int
     L.spnerf_sample_coarse.argtypes = [VP, VP, VP, I64, I32, VP, VP]
+    L.spnerf_sample_coarse_rng.restype = ctypes.c_int
+    L.spnerf_sample_coarse_rng.argtypes = [VP, VP, VP, I64, I32, VP, VP]
     L.spnerf_sky_bwd.restype = ctypes.c_int
     L.spnerf_sky_bwd.argtypes = [VP, ctypes.POINTER(NetConfig), VP, VP, VP, VP, I64, VP, VP, VP, VP, VP]
     L.spnerf_adam_step.restype = I32

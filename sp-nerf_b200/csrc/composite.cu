@@ -703,12 +703,9 @@ __global__ void __launch_bounds__(64) composite_bwd_fast(const BwdP p) {
 
 // grid = the blocks that are resident at once (shared memory bound), each warp strides over ray groups
 template <class K, class P>
-int launch(K kern, const P& p, int64_t n_groups, int wpb, size_t smem, cudaStream_t stream, size_t* configured) {
-  if (smem > 48 * 1024 && smem > *configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -(int)e;
-    *configured = smem;
-  }
+int launch(K kern, const P& p, int64_t n_groups, int wpb, size_t smem, cudaStream_t stream, size_t*) {
+  if (smem > 48 * 1024)
+    if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

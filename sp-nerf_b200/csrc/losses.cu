@@ -19,10 +19,10 @@ struct Workspace {
   float partial[kMaxBlocks][4];
 };
 
-__global__ void count_labels_kernel(const int64_t* __restrict__ labels, int64_t n, Workspace* ws) {
+__global__ void count_labels_kernel(const int64_t* __restrict__ labels, int64_t n, int n_sem, Workspace* ws) {
   unsigned int c = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    c += labels[i] != -100;
+    c += labels[i] >= 0 && labels[i] < n_sem;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ws->n_labelled, c);
@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
       if (lane == 0) s_col += sq;
     }
     if (a.depth) {
-      const float d = a.depth[r], td = a.target_depth[r], tw = a.target_weight[r];
+      const int64_t ts = a.target_stride > 0 ? a.target_stride : 1;
+      const float d = a.depth[r], td = a.target_depth[r * ts], tw = a.target_weight[r * ts];
       bool apply;
       float pstd = 0.f, m1 = 0.f;      // predicted STD and sum_i (z_i - d) w_i (GNLL gradient)
       if (a.use_all_depth) {
@@ -89,8 +90,9 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
       }
     }
     if (a.sem_logits) {                                                                // metrics.py:166,171 CE(ignore_index=-100)
-      const int64_t lab = a.labels[r];
       const int C = a.n_sem;
+      int64_t lab = a.labels[r];
+      if (lab < 0 || lab >= C) lab = -100;          // out-of-range targets are ignored (torch raises on them)
       float lg = lane < C ? a.sem_logits[r * C + lane] : -INFINITY;
       float m = lg;
 #pragma unroll
@@ -127,7 +129,10 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
     if (threadIdx.x == 1) v = lam_d * t * inv_b;
     if (threadIdx.x == 2) v = a.lambda_ss * t / n_lab;
     a.losses[threadIdx.x] = v;
-    if (threadIdx.x == 0) a.losses[4] = a.sem_logits ? n_lab : 0.f;
+    a.losses[4 + threadIdx.x] = (threadIdx.x == 0 && a.sem_logits) ? n_lab : 0.f;
+    // the workspace cleans itself for the next call (no memsets on the stream): every block has read the label
+    // count and taken its ticket by now
+    if (threadIdx.x == 0) { ws->ticket = 0; ws->n_labelled = 0; }
   }
 }
 
@@ -180,8 +185,10 @@ __global__ void __launch_bounds__(kThreads) solar_fwd_kernel(const SpnerfLossSol
     if (lane == 0) { s2 += q; s3 += 1.f - ws_; }
   }
   const float v[2] = {s2, s3};
-  if (block_partials<2>(ws, v) && threadIdx.x < 2)
-    a.losses[threadIdx.x] = a.lambda_sc / 3.f * ordered_total(ws, threadIdx.x) / (float)a.n_rays;
+  if (block_partials<2>(ws, v)) {
+    if (threadIdx.x < 2) a.losses[threadIdx.x] = a.lambda_sc / 3.f * ordered_total(ws, threadIdx.x) / (float)a.n_rays;
+    if (threadIdx.x == 0) ws->ticket = 0;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) solar_bwd_kernel(const SpnerfLossSolar a) {
@@ -214,6 +221,7 @@ __global__ void __launch_bounds__(kThreads) uncertainty_fwd_kernel(const SpnerfL
   if (block_partials<2>(ws, v) && threadIdx.x == 0) {
     a.losses[0] = ordered_total(ws, 0) / (3.f * (float)a.n_rays);
     a.losses[1] = (3.f + ordered_total(ws, 1) / (float)a.n_rays) * 0.5f;
+    ws->ticket = 0;
   }
 }
 
@@ -252,7 +260,6 @@ extern "C" int spnerf_loss_solar(const SpnerfLossSolar* a, int backward, void* s
   if (!backward) {
     if (!a->losses || !a->workspace) return SPNERF_ERR_BAD_ARG;
     Workspace* ws = static_cast<Workspace*>(a->workspace);
-    cudaMemsetAsync(ws, 0, 16, stream);
     solar_fwd_kernel<<<ray_blocks(a->n_rays), kThreads, 0, stream>>>(*a, ws);
   } else {
     if (!a->g_sun) return SPNERF_ERR_BAD_ARG;
@@ -271,7 +278,6 @@ extern "C" int spnerf_loss_uncertainty(const SpnerfLossUncertainty* a, int backw
   if (!backward) {
     if (!a->losses || !a->workspace) return SPNERF_ERR_BAD_ARG;
     Workspace* ws = static_cast<Workspace*>(a->workspace);
-    cudaMemsetAsync(ws, 0, 16, stream);
     uncertainty_fwd_kernel<<<ray_blocks(a->n_rays), kThreads, 0, stream>>>(*a, ws);
   } else {
     if (!a->g_rgb || !a->g_weights || !a->g_beta) return SPNERF_ERR_BAD_ARG;
@@ -292,11 +298,9 @@ extern "C" int spnerf_losses(const SpnerfLosses* a, void* stream_) {
   if (a->sem_logits && (!a->labels || !a->g_sem_logits || a->n_sem < 1 || a->n_sem > 32)) return SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Workspace* ws = static_cast<Workspace*>(a->workspace);
-  cudaMemsetAsync(ws, 0, 16, stream);
-  cudaMemsetAsync(a->losses, 0, 8 * sizeof(float), stream);
   if (a->sem_logits) {
     const int64_t nb = (a->n_rays + kThreads - 1) / kThreads;
-    count_labels_kernel<<<(unsigned)(nb < 592 ? nb : 592), kThreads, 0, stream>>>(a->labels, a->n_rays, ws);
+    count_labels_kernel<<<(unsigned)(nb < 592 ? nb : 592), kThreads, 0, stream>>>(a->labels, a->n_rays, a->n_sem, ws);
   }
   const int64_t need = (a->n_rays + kThreads / 32 - 1) / (kThreads / 32);
   const unsigned blocks = (unsigned)(need < kMaxBlocks ? need : kMaxBlocks);

@@ -17,7 +17,7 @@ namespace {
 struct BwdParams {
   const float* g_out; const float* out; const float* rays; const int64_t* labels; const float* t_emb;
   int64_t n_rays; int64_t n_points; int n_samples;
-  const uint8_t* blob; int64_t blob_stride; int blob_copies; StepTable tab;
+  const uint8_t* blob; StepTable tab;
   const float* small; SmallOffsets so; SaveMap sm; GradMap gm;
   const uint8_t* saves; uint8_t* gsaves;
   const float* absmax; float* scale_out;
@@ -169,10 +169,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  // timing-experiment toggles and the phase clock log exist only in SPNERF_EXPERIMENTS builds (tools/build_variant.sh)
+#ifdef SPNERF_EXPERIMENTS
+  const int dbg = p.debug;
+  long long* const prof = p.prof;
+#else
+  constexpr int dbg = 0;
+  constexpr long long* prof = nullptr;
+#endif
   const Smem sh = carve(smem);
   uint8_t* act = sh.act;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, p.debug);
+  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, dbg);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
@@ -191,10 +199,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
 
   if (warp >= kProducerWarp) ctl_registers();
   if (warp == kProducerWarp) {
-    producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
+    producer_loop(sh, p.blob, p.tab, n_iters, dbg, prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, dbg, prof);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, dbg);
   } else if (warp < 16) {
     epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;
@@ -205,8 +213,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
     const float4* Wsem2 = reinterpret_cast<const float4*>(smem + kOffSem2);
     const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
-    const int wide_cols = (p.debug & 2) ? 32 : 128;
-    EpiSync sync(sh, p.prof);
+    const int wide_cols = (dbg & 2) ? 32 : 128;
+    EpiSync sync(sh, prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
     stagger_start(p.stagger, p.stagger_groups);
@@ -379,19 +387,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       };
       for (int L = 7; L >= 0; --L) {
 #ifdef SPNERF_EXPERIMENTS
-        if (!(p.debug & (1024 | 4096)))
+        if (!(dbg & (1024 | 4096)))
 #endif
         ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
         sync.begin();
         // three of the four column groups store their part of the gradient tile from registers, the last quarter is
         // copied out of shared memory during the next MMAs (alternating A/B on one box: 2 groups 4.68 ms, 3 groups
         // 4.60, all four 4.72; debug & 256 / 512 select 2 / 1 groups)
-        const int ndirect = (p.debug & 256) ? 2 : (p.debug & 512) ? 1 : 3;
+        const int ndirect = (dbg & 256) ? 2 : (dbg & 512) ? 1 : 3;
         uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
 #ifdef SPNERF_EXPERIMENTS
-        if (p.debug & 2048) gdirect = nullptr;
-        if (p.debug & 1024) bwd_columns<3, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else if (p.debug & 4096) bwd_columns<2, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        if (dbg & 2048) gdirect = nullptr;
+        if (dbg & 1024) bwd_columns<3, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else if (dbg & 4096) bwd_columns<2, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
         else
 #endif
         if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
@@ -399,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         const bool more = (L > 0) || p.sem;
         sync.end(more);
 #ifdef SPNERF_EXPERIMENTS
-        if (!(p.debug & 2048))
+        if (!(dbg & 2048))
 #endif
         copy_slabs_out(act, 2 * ndirect, 8 - 2 * ndirect, gs(p.gm.G[L] + 2 * ndirect));
         if (p.sem && L == 4) emb_phase(true);
@@ -408,7 +416,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       // ---- label-embedding gradient: rows of one warp share a ray (hence a label) when n_samples % 32 == 0 ----
       if (p.sem && cg == 0 && p.g_emb) {
         int lab = -1;
-        if (valid && p.labels) { const int64_t l = p.labels[ray]; lab = (l == -100) ? -1 : (int)l; }   // padding row: no grad
+        if (valid && p.labels) { const int64_t l = p.labels[ray]; lab = (l < 0 || l >= p.n_classes) ? -1 : (int)l; }   // padding row / out of range: no grad
         const int lab0 = __shfl_sync(0xffffffffu, lab, 0);
         const bool uniform = __all_sync(0xffffffffu, lab == lab0);
         for (int e = 0; e < p.emb_dim; ++e) {
@@ -449,14 +457,7 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   const StepTable* tab = step_table(a->cfg, 1);
   if (!tab) return SPNERF_ERR_UNSUPPORTED;
   p.tab = *tab;
-  {
-    const char* e = getenv("SPNERF_BLOB_COPIES");      // experiment: replicas of the weight stream (engine.py allocates them)
-    p.blob_copies = e ? atoi(e) : 1;
-    if (p.blob_copies < 1) p.blob_copies = 1;
-    SpnerfNetSizes sz;
-    spnerf_net_sizes(&a->cfg, &sz);
-    p.blob_stride = sz.bwd_blob_bytes;
-  } p.small = a->small;
+  p.small = a->small;
   p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg); p.gm = make_grad_map(a->cfg);
   p.saves = static_cast<const uint8_t*>(a->saves); p.gsaves = static_cast<uint8_t*>(a->grad_saves);
   p.absmax = a->g_absmax; p.scale_out = a->scale_out;
@@ -467,12 +468,7 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   p.debug = a->debug_flags;
   p.prof = g_prof_bwd;
   host_stagger(p.stagger, p.stagger_groups);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return -(int)e;
-    attr_set = true;
-  }
+  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(mlp_bwd_kernel), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -24,7 +24,7 @@ struct FwdParams {
   const float* rays; const float* z; const float* xyz; const float* dir_override;
   const int64_t* labels; const float* t_emb; const float* sky;
   int64_t n_rays; int64_t n_points; int n_samples;
-  const uint8_t* blob; int64_t blob_stride; int blob_copies; StepTable tab;
+  const uint8_t* blob; StepTable tab;
   const float* small; SmallOffsets so; SaveMap sm;
   float* out; uint8_t* saves;
   int mapping, sem, n_classes, emb_dim, beta, t_dim, in_dim, n_out, col_beta, col_sem;
@@ -99,19 +99,27 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  // timing-experiment toggles and the phase clock log exist only in SPNERF_EXPERIMENTS builds (tools/build_variant.sh)
+#ifdef SPNERF_EXPERIMENTS
+  const int dbg = p.debug;
+  long long* const prof = p.prof;
+#else
+  constexpr int dbg = 0;
+  constexpr long long* prof = nullptr;
+#endif
   const Smem sh = carve(smem);
   uint8_t* act = sh.act;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, p.debug);
+  const uint32_t tmem_base = setup(sh, smem, p.small + p.so.smallw, dbg);
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_iters = my_pairs((n_tiles + 1) / 2);     // tile pairs of this cluster
 
   if (warp >= kProducerWarp) ctl_registers();
   if (warp == kProducerWarp) {
-    producer_loop(sh, p.blob + (size_t)((blockIdx.x >> 1) % p.blob_copies) * p.blob_stride, p.tab, n_iters, p.debug, p.prof);
+    producer_loop(sh, p.blob, p.tab, n_iters, dbg, prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
-    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, p.debug, p.prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, p.debug);
+    if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, dbg, prof);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, dbg);
   } else if (warp < 16) {
     epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
@@ -124,7 +132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
     float* scratch = reinterpret_cast<float*>(smem + kSlabInpHi * kSlabBytes);
-    EpiSync sync(sh, p.prof);
+    EpiSync sync(sh, prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
     stagger_start(p.stagger, p.stagger_groups);
@@ -159,7 +167,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         int lab = -1;
         if (p.sem && valid && p.labels) {
           const int64_t l = p.labels[ray];
-          lab = (l == -100) ? p.n_classes : (int)l;       // padding row (models/spnerf.py:310-315)
+          // -100 -> padding row (models/spnerf.py:310-315).  Any other label outside [0, C) would index past the
+          // embedding block (the reference's nn.Embedding raises): it is treated like the padding row
+          lab = (l < 0 || l >= p.n_classes) ? p.n_classes : (int)l;
         }
         const int base = p.mapping ? 60 : 3;
         // this thread fills columns [16*cg, 16*cg+16) of its row
@@ -235,15 +245,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // The saved copy of every activation tile leaves from registers during the epilogue.  (Copying half of it out
       // of shared memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy
       // competes with the MMAs for shared-memory bandwidth.  debug & 128 selects that variant.)
-      const bool direct_all = !(p.debug & 128);
-      epi_cols<1, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]),
+      const bool direct_all = !(dbg & 128);
+      epi_cols<1, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]),
                         (cg < 2 || direct_all) ? sv(p.sm.y[0]) : nullptr, NoEach());
       sync.end(true);
       if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
       // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
+        epi_cols<0, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
                           (cg < 2 || direct_all) ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
         if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
@@ -262,8 +272,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = 0.f;
         const bool wide = p.n_classes > 4;
-        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, (p.debug & 32) ? nullptr : sv(p.sm.sem_x),
-                           (p.debug & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
+        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, (dbg & 32) ? nullptr : sv(p.sm.sem_x),
+                           (dbg & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
           const float4 w = Wsem2[j * 2];
           lg[0] = fmaf(w.x, y, lg[0]); lg[1] = fmaf(w.y, y, lg[1]); lg[2] = fmaf(w.z, y, lg[2]); lg[3] = fmaf(w.w, y, lg[3]);
           if (wide) {
@@ -278,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
       sync.begin();
-      epi_cols<2, true>(taddr, cg * 128, (p.debug & 2) ? 32 : 128, act, 0, row, nullptr,
+      epi_cols<2, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, nullptr,
                         (cg < 2 || direct_all) ? sv(p.sm.f) : nullptr, NoEach());
       sync.end(true);
       if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
@@ -364,14 +374,6 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   const StepTable* tab = step_table(a->cfg, 0);
   if (!tab) return SPNERF_ERR_UNSUPPORTED;
   p.tab = *tab;
-  {
-    const char* e = getenv("SPNERF_BLOB_COPIES");      // experiment: replicas of the weight stream (engine.py allocates them)
-    p.blob_copies = e ? atoi(e) : 1;
-    if (p.blob_copies < 1) p.blob_copies = 1;
-    SpnerfNetSizes sz;
-    spnerf_net_sizes(&a->cfg, &sz);
-    p.blob_stride = sz.fwd_blob_bytes;
-  }
   p.small = a->small; p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg);
   p.out = a->out; p.saves = static_cast<uint8_t*>(a->saves);
   const NetDims d = make_dims(a->cfg);
@@ -383,18 +385,15 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.prof = g_prof_fwd;
   host_stagger(p.stagger, p.stagger_groups);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return -(int)e;
-    attr_set = true;
-  }
+  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(mlp_fwd_kernel), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_pairs = ((p.n_points + kTileM - 1) / kTileM + 1) / 2;
   int64_t clusters = sms / 2;
+#ifdef SPNERF_EXPERIMENTS
   if (const char* e = getenv("SPNERF_MAX_CLUSTERS")) { const int v = atoi(e); if (v > 0 && v < clusters) clusters = v; }
+#endif
   const unsigned grid = 2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters);
   mlp_fwd_kernel<<<grid, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();

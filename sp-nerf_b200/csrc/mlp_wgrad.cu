@@ -72,6 +72,11 @@ struct Segment {                // scatter rule: rows [row0, row0+nrows) of CTA 
   int ld_row, ld_col;
 };
 
+// scratch block -> gradient slot copies done (and cleared) by the reduce kernel; see SpnerfMlpWgrad::accum
+struct Flush { int src_off, n; float* dst; };
+constexpr int kMaxFlush = 12;
+struct FlushTable { int n; int n_progress; float* accum; float* absmax_reset; int* progress; Flush f[kMaxFlush]; };
+
 struct WgradParams {
   const uint8_t* saves; const uint8_t* gsaves;
   int64_t save_stride, grad_stride;      // bytes per point tile
@@ -400,9 +405,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
 constexpr int kMaxSlices = 256;
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const Segment* __restrict__ segs, const Job* __restrict__ jobs,
                                                            const Item* __restrict__ items, const float* __restrict__ ws,
-                                                           const float* __restrict__ scale) {
+                                                           const float* __restrict__ scale, int n_segs,
+                                                           const FlushTable* __restrict__ flush) {
   __shared__ float tile[32][33];
   __shared__ long long offs[kMaxSlices];
+  if ((int)blockIdx.x >= n_segs) {
+    // the atomically accumulated slots: scratch -> gradient tensors, scratch cleared for the next step
+    if (blockIdx.y != 0) return;
+    for (int i = threadIdx.x; i < flush->n_progress; i += blockDim.x) flush->progress[i] = 0;   // rendezvous counters of the GEMM kernel
+    if (!flush->accum) return;
+    for (int k = 0; k < flush->n; ++k) {
+      const Flush fl = flush->f[k];
+      for (int i = threadIdx.x; i < fl.n; i += blockDim.x) {
+        fl.dst[i] = flush->accum[fl.src_off + i];
+        flush->accum[fl.src_off + i] = 0.f;
+      }
+    }
+    if (threadIdx.x == 0 && flush->absmax_reset) *flush->absmax_reset = 0.f;
+    return;
+  }
   const Segment sg = segs[blockIdx.x];
   const Job& job = jobs[sg.job];
   const int ns = job.nitems < kMaxSlices ? job.nitems : kMaxSlices;      // host guarantees nitems <= kMaxSlices
@@ -447,6 +468,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const Segment* __rest
 // host: the list of jobs for a configuration
 // ---------------------------------------------------------------------------------------------
 struct Plan {
+  FlushTable flush{};
   std::vector<Job> jobs;
   std::vector<Item> items;      // launch order, followed by a job-major copy
   int n_launch = 0;
@@ -699,11 +721,12 @@ int n_sms() {
 
 size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 size_t table_bytes(const Plan& pl) {
-  return align16(pl.jobs.size() * sizeof(Job)) + align16(pl.items.size() * sizeof(Item)) + pl.segs.size() * sizeof(Segment) + 64;
+  return align16(pl.jobs.size() * sizeof(Job)) + align16(pl.items.size() * sizeof(Item)) + align16(pl.segs.size() * sizeof(Segment)) +
+         sizeof(FlushTable) + 64;
 }
 constexpr int64_t kTableRoom = 262144, kProgressRoom = 16384;
 
-struct Tables { Job* jobs; Item* items; Segment* segs; };
+struct Tables { Job* jobs; Item* items; Segment* segs; FlushTable* flush; };
 Tables table_ptrs(const Plan& pl, void* workspace) {
   uint8_t* tab = static_cast<uint8_t*>(workspace) + (size_t)pl.ws_floats * 4;
   Tables t;
@@ -712,10 +735,36 @@ Tables table_ptrs(const Plan& pl, void* workspace) {
   t.items = reinterpret_cast<Item*>(tab);
   tab += align16(pl.items.size() * sizeof(Item));
   t.segs = reinterpret_cast<Segment*>(tab);
+  tab += align16(pl.segs.size() * sizeof(Segment));
+  t.flush = reinterpret_cast<FlushTable*>(tab);
   return t;
 }
 
 }  // namespace
+
+// host-side sizes of a plan, cached per (configuration, pair count): the launch path must not rebuild the job lists
+namespace {
+struct PlanCounts { int64_t ws_floats; int n_launch; int n_segs; size_t jobs_bytes, items_bytes, segs_bytes; };
+}  // namespace
+#include <map>
+#include <mutex>
+#include <array>
+static PlanCounts plan_counts(const SpnerfNetConfig& c, float* const* G, int pairs) {
+  static std::mutex mu;
+  static std::map<std::array<int64_t, 11>, PlanCounts> cache;
+  int64_t present = 0;                       // scatter segments exist only for the gradient slots the caller provides
+  for (int i = 0; i < SPNERF_NUM_PARAMS; ++i) present |= (int64_t)(G[i] != nullptr) << i;
+  const std::array<int64_t, 11> key{c.feat, c.layers, c.skip_layer, c.mapping, c.sem, c.num_sem_classes, c.emb_dim, c.beta,
+                                    c.t_dim, pairs, present};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const Plan pl = make_plan(c, G, pairs);
+  PlanCounts pc{pl.ws_floats, pl.n_launch, (int)pl.segs.size(), align16(pl.jobs.size() * sizeof(Job)),
+                align16(pl.items.size() * sizeof(Item)), align16(pl.segs.size() * sizeof(Segment))};
+  cache[key] = pc;
+  return pc;
+}
 
 static long long* g_prof_wgrad = nullptr;
 extern "C" void spnerf_debug_counters_wgrad(long long* dev_buf8_per_pair) { g_prof_wgrad = dev_buf8_per_pair; }
@@ -736,11 +785,36 @@ extern "C" int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* a, void* stream_) 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Plan pl = make_plan(a->cfg, a->grads_host, n_sms() / 2);
   const size_t tb = table_bytes(pl);
-  if ((int64_t)pl.ws_floats * 4 + (int64_t)tb > a->workspace_bytes || (int64_t)tb > kTableRoom) return SPNERF_ERR_WORKSPACE;
+  if ((int64_t)pl.ws_floats * 4 + kTableRoom + kProgressRoom > a->workspace_bytes || (int64_t)tb > kTableRoom ||
+      (int64_t)pl.n_launch * 8 > kProgressRoom)
+    return SPNERF_ERR_WORKSPACE;
   const Tables t = table_ptrs(pl, a->workspace);
   cudaMemcpyAsync(t.jobs, pl.jobs.data(), pl.jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(t.items, pl.items.data(), pl.items.size() * sizeof(Item), cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(t.segs, pl.segs.data(), pl.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream);
+  {
+    // slots summed with atomics: staged in the caller's scratch block, flushed by the reduce kernel
+    FlushTable& ft = pl.flush;
+    ft.accum = a->accum; ft.absmax_reset = a->absmax_reset;
+    float* const* G = a->grads_host;
+    auto add = [&](int slot, int off, int n) { if (a->accum && G[slot] && n > 0 && ft.n < kMaxFlush) ft.f[ft.n++] = Flush{off, n, G[slot]}; };
+    add(SPNERF_P_RGB2_B, SPNERF_ACC_SMALL_BIAS + 0, 3);
+    add(SPNERF_P_SUN0_W + 7, SPNERF_ACC_SMALL_BIAS + 3, 1);
+    add(SPNERF_P_SIGMA_B, SPNERF_ACC_SMALL_BIAS + 4, 1);
+    if (a->cfg.beta) add(SPNERF_P_BETA2_B, SPNERF_ACC_SMALL_BIAS + 5, 1);
+    if (a->cfg.sem) {
+      add(SPNERF_P_SEM2_B, SPNERF_ACC_SMALL_BIAS + 6, a->cfg.num_sem_classes);
+      add(SPNERF_P_SEM_EMB, SPNERF_ACC_EMB, (a->cfg.num_sem_classes + 1) * a->cfg.emb_dim);
+    }
+    add(SPNERF_P_SKY0_W, SPNERF_ACC_SKY_W0, 3 * kHalf);
+    add(SPNERF_P_SKY0_B, SPNERF_ACC_SKY_B0, kHalf);
+    add(SPNERF_P_SKY2_W, SPNERF_ACC_SKY_W2, 3 * kHalf);
+    add(SPNERF_P_SKY2_B, SPNERF_ACC_SKY_B2, 3);
+    ft.progress = reinterpret_cast<int*>(static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4 + kTableRoom);
+    ft.n_progress = pl.n_launch * 2;
+    cudaMemsetAsync(ft.progress, 0, (size_t)ft.n_progress * sizeof(int), stream);     // from then on the reduce kernel re-zeroes them
+    cudaMemcpyAsync(t.flush, &ft, sizeof(FlushTable), cudaMemcpyHostToDevice, stream);
+  }
   cudaError_t e = cudaStreamSynchronize(stream);
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -751,11 +825,18 @@ extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   if (a->n_points <= 0) return a->n_points == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int pairs = n_sms() / 2;
-  Plan pl = make_plan(a->cfg, a->grads_host, pairs);     // host-side counts only; tables were uploaded by _prepare
+  const PlanCounts pl = plan_counts(a->cfg, a->grads_host, pairs);     // the tables themselves were uploaded by _prepare
   if ((int64_t)pl.ws_floats * 4 + kTableRoom + kProgressRoom > a->workspace_bytes ||
       (int64_t)pl.n_launch * 8 > kProgressRoom)
     return SPNERF_ERR_WORKSPACE;
-  const Tables t = table_ptrs(pl, a->workspace);
+  Tables t;
+  {
+    uint8_t* tab = static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4;
+    t.jobs = reinterpret_cast<Job*>(tab); tab += pl.jobs_bytes;
+    t.items = reinterpret_cast<Item*>(tab); tab += pl.items_bytes;
+    t.segs = reinterpret_cast<Segment*>(tab); tab += pl.segs_bytes;
+    t.flush = reinterpret_cast<FlushTable*>(tab);
+  }
   WgradParams p;
   p.saves = static_cast<const uint8_t*>(a->saves); p.gsaves = static_cast<const uint8_t*>(a->grad_saves);
   p.save_stride = (int64_t)make_save_map(a->cfg).total * kSlabBytes;
@@ -766,15 +847,10 @@ extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   p.ws = static_cast<float*>(a->workspace);
   p.progress = reinterpret_cast<int*>(static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4 + kTableRoom);
   p.prof = g_prof_wgrad;
-  cudaMemsetAsync(p.progress, 0, (size_t)pl.n_launch * 2 * sizeof(int), stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW);
-    if (e != cudaSuccess) return -(int)e;
-    attr_set = true;
-  }
+  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(wgrad_kernel), kSmemW); e != cudaSuccess) return -(int)e;
   wgrad_kernel<<<2 * std::min(pairs, pl.n_launch), kWThreads, kSmemW, stream>>>(p);
-  wgrad_reduce_kernel<<<dim3((unsigned)pl.segs.size(), 16), 256, 0, stream>>>(t.segs, t.jobs, t.items, p.ws, a->scale);
+  wgrad_reduce_kernel<<<dim3((unsigned)pl.n_segs + 1, 16), 256, 0, stream>>>(t.segs, t.jobs, t.items, p.ws, a->scale, pl.n_segs,
+                                                                             t.flush);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

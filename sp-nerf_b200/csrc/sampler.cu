@@ -18,10 +18,39 @@
 
 namespace {
 
+// ---- device-side uniforms: Philox4x32-10 keyed by the seed, counter = (element index, step) ------------
+// `state` = {seed, step, arrivals (low 32 bits)}: every block reads the step when it starts and the block that
+// arrives last advances it, so consecutive launches (and replays of a captured graph) draw fresh numbers with no
+// host involvement.  Values are k * 2^-24, k < 2^24, like torch.rand's float32 draws.
+__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t step, uint64_t idx) {
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (float)(c0 >> 8) * 5.9604644775390625e-8f;
+}
+
 // ---- coarse: z = lower + (upper-lower)*u over stratified bins of near*(1-t)+far*t -----------------
 __global__ void coarse_kernel(const float* __restrict__ rays, const float* __restrict__ t_tab,
-                              const float* __restrict__ u, int64_t n_rays, int n, float* __restrict__ z) {
+                              const float* __restrict__ u, unsigned long long* rng_state, int64_t n_rays, int n,
+                              float* __restrict__ z) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned long long seed = 0, step = 0;
+  if (rng_state) {
+    seed = rng_state[0];
+    step = *reinterpret_cast<volatile unsigned long long*>(rng_state + 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int* arrivals = reinterpret_cast<unsigned int*>(rng_state + 2);
+      if (atomicAdd(arrivals, 1u) == gridDim.x - 1) { *arrivals = 0u; rng_state[1] = step + 1; }
+    }
+  }
   if (idx >= n_rays * n) return;
   const int64_t r = idx / n;
   const int i = (int)(idx - r * n);
@@ -33,7 +62,8 @@ __global__ void coarse_kernel(const float* __restrict__ rays, const float* __res
   const float zi = zlin(i);
   const float lower = i == 0 ? zi : __fmul_rn(0.5f, __fadd_rn(zlin(i - 1), zi));        // :138-141
   const float upper = i == n - 1 ? zi : __fmul_rn(0.5f, __fadd_rn(zi, zlin(i + 1)));
-  z[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[idx]));               // :143-144 (perturb = 1)
+  const float ui = rng_state ? philox_uniform(seed, step, (uint64_t)idx) : u[idx];
+  z[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), ui));                   // :143-144 (perturb = 1)
 }
 
 // ---- torch.sum(row) for a contiguous fp32 row (ATen vectorized inner reduction, 8-float vectors) ----
@@ -161,7 +191,18 @@ extern "C" int spnerf_sample_coarse(const float* rays, const float* t_table, con
   if (n_rays <= 0) return n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   const int64_t total = n_rays * n_samples;
   coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      rays, t_table, uniforms, n_rays, n_samples, z);
+      rays, t_table, uniforms, nullptr, n_rays, n_samples, z);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+extern "C" int spnerf_sample_coarse_rng(const float* rays, const float* t_table, uint64_t* rng_state, int64_t n_rays,
+                                        int32_t n_samples, float* z, void* stream) {
+  if (!rays || !t_table || !rng_state || !z || n_samples < 2) return SPNERF_ERR_BAD_ARG;
+  if (n_rays <= 0) return n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
+  const int64_t total = n_rays * n_samples;
+  coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rays, t_table, nullptr, reinterpret_cast<unsigned long long*>(rng_state), n_rays, n_samples, z);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -181,11 +222,14 @@ extern "C" int spnerf_sample_guided(const SpnerfGuided* a, void* stream) {
   p.z_unsort = a->z_unsort; p.z_sorted = a->z_sorted; p.inds_out = a->searchsorted_out;
   const int bs = 32;
   const size_t smem = (size_t)3 * p.n * bs * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[64] = {};      // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t* conf = (dev >= 0 && dev < 64) ? &configured[dev] : nullptr;
+  if (smem > 48 * 1024 && (!conf || smem > *conf)) {
     cudaError_t e = cudaFuncSetAttribute(guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e;
-    configured = smem;
+    if (conf) *conf = smem;
   }
   guided_kernel<<<(unsigned)((p.n_rays + bs - 1) / bs), bs, smem, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();

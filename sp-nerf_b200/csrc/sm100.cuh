@@ -39,6 +39,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Opt a kernel into a large dynamic shared-memory carve-out.  The attribute is per device AND per kernel function
+// (not per function type: kernels with the same parameter list share a pointer type), so the cache is keyed by both;
+// it only remembers the largest size configured so far.
+}  // namespace sm100
+#include <map>
+#include <mutex>
+#include <utility>
+namespace sm100 {
+inline cudaError_t set_max_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> configured;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[{kernel, dev}];
+  if (bytes <= have) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

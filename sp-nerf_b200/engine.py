@@ -23,6 +23,11 @@ def _stream():
 def _require_cuda(t, what):
     if t.device.type != "cuda":
         raise _cabi.SpnerfError(f"{what} must live on a CUDA device: spnerf_b200 has no CPU path")
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        # kernels are launched on the current device's stream: a tensor of another GPU would be dereferenced there
+        raise _cabi.SpnerfError(f"{what} lives on {t.device} but the current CUDA device is "
+                                f"cuda:{torch.cuda.current_device()}: call torch.cuda.set_device first "
+                                "(one process per GPU, or a torch.cuda.device(...) block around the call)")
 
 
 _tables = {}
@@ -50,6 +55,39 @@ def sample_coarse(rays, uniforms, n):
     z = torch.empty(rays.shape[0], n, dtype=torch.float32, device=rays.device)
     _cabi.check(_cabi.lib().spnerf_sample_coarse(_p(rays), _p(t_tab), _p(uniforms), rays.shape[0], n, _p(z), _stream()),
                 "spnerf_sample_coarse")
+    return z
+
+
+_rng_state = {}
+_rng_seed = None
+
+
+def manual_seed(seed):
+    """Restart the sampler's device-side random stream (all devices) from `seed`: the same seed replays the same
+    sample depths.  Without it the stream is seeded from torch's default generator on first use."""
+    global _rng_seed
+    _rng_seed = int(seed)
+    for st in _rng_state.values():      # in place: a captured CUDA graph keeps reading the same words
+        st.copy_(torch.tensor([_rng_seed, 0, 0], dtype=torch.int64))
+
+
+def rng_state(device):
+    """Device-resident {seed, step, 0} of the sampler's Philox stream (one per device)."""
+    key = str(device)
+    if key not in _rng_state:
+        seed = _rng_seed if _rng_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        _rng_state[key] = torch.tensor([seed, 0, 0], dtype=torch.int64, device=device)
+    return _rng_state[key]
+
+
+def sample_coarse_rng(rays, n, state=None):
+    """modules/rendering.py:128-144 with the uniforms of :143 drawn inside the kernel (no torch.rand launch)."""
+    _require_cuda(rays, "rays")
+    t_tab, _ = sampler_tables(n, rays.device)
+    state = rng_state(rays.device) if state is None else state
+    z = torch.empty(rays.shape[0], n, dtype=torch.float32, device=rays.device)
+    _cabi.check(_cabi.lib().spnerf_sample_coarse_rng(_p(rays), _p(t_tab), _p(state), rays.shape[0], n, _p(z), _stream()),
+                "spnerf_sample_coarse_rng")
     return z
 
 
@@ -106,13 +144,15 @@ def composite_fwd(out, z, n_out, col_sem, n_sem, noise=None, noise_std=0.0, want
 
 
 def composite_bwd(out, z, weights, trans, rgb_raw, n_out, col_sem, n_sem, g_rgb=None, g_depth=None, g_sem=None,
-                  g_w=None, g_t=None, g_out_ext=None, noise=None, noise_std=0.0):
-    """Adjoint of composite_fwd.  Returns (g_out, g_sky_ray, absmax scalar)."""
+                  g_w=None, g_t=None, g_out_ext=None, noise=None, noise_std=0.0, absmax=None):
+    """Adjoint of composite_fwd.  Returns (g_out, g_sky_ray, absmax scalar).
+    `absmax`: a zeroed (1,) accumulator to use instead of a fresh one (NetEngine.absmax is reset by the backward)."""
     b, n = z.shape
     dev = z.device
     g_out = torch.empty(b * n, n_out, dtype=torch.float32, device=dev)
     g_sky = torch.empty(b, 3, dtype=torch.float32, device=dev)
-    absmax = torch.zeros(1, dtype=torch.float32, device=dev)
+    if absmax is None:
+        absmax = torch.zeros(1, dtype=torch.float32, device=dev)
     a = _cabi.CompositeBwd()
     a.out, a.z, a.noise, a.weights, a.transparency, a.rgb_raw = _p(out), _p(z), _p(noise), _p(weights), _p(trans), \
         _p(rgb_raw)
@@ -146,6 +186,15 @@ def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, 
     a.n_sem = sem_logits.shape[1] if sem_logits is not None else 0
     a.rgb, a.rgb_target, a.g_rgb = _p(rgb), _p(rgb_target), _p(g_rgb)
     a.depth, a.z, a.weights = _p(depth), _p(z), _p(weights)
+    stride = 1
+    if target_depth is not None and target_depth.dim() == 1 and target_depth.stride(0) != 1:
+        if target_weight.stride(0) == target_depth.stride(0) and target_depth.stride(0) > 0:
+            stride = target_depth.stride(0)          # the two columns of the reference's (B,2) `depths`, read in place
+        else:
+            target_depth, target_weight = target_depth.contiguous(), target_weight.contiguous()
+    elif target_weight is not None and target_weight.dim() == 1 and target_weight.stride(0) != 1:
+        target_weight = target_weight.contiguous()
+    a.target_stride = stride
     a.target_depth, a.target_weight, a.target_std, a.valid_depth = \
         _p(target_depth), _p(target_weight), _p(target_std), _p(valid_depth)
     a.lambda_ds, a.use_all_depth, a.g_depth = lambda_ds, 1 if use_all_depth else 0, _p(g_depth)
@@ -159,7 +208,7 @@ def losses(n_rays, rgb=None, rgb_target=None, depth=None, z=None, weights=None, 
 
 def _loss_workspace(dev):
     if dev not in _loss_ws:
-        _loss_ws[dev] = torch.empty(int(_cabi.lib().spnerf_losses_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _loss_ws[dev] = torch.zeros(int(_cabi.lib().spnerf_losses_workspace_bytes()), dtype=torch.uint8, device=dev)
     return _loss_ws[dev]
 
 
@@ -267,15 +316,17 @@ class NetEngine:
         s = self.sizes
         self.device = device
         u8 = dict(dtype=torch.uint8, device=device)
-        import os
-        self.blob_copies = max(1, int(os.environ.get("SPNERF_BLOB_COPIES", "1")))
-        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16) * self.blob_copies, **u8)
-        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16) * self.blob_copies, **u8)
+        self.fwd_blob = torch.empty(max(int(s.fwd_blob_bytes), 16), **u8)
+        self.bwd_blob = torch.empty(max(int(s.bwd_blob_bytes), 16), **u8)
         self.small = torch.empty(int(s.small_floats), dtype=torch.float32, device=device)
         self.fwd_steps = torch.empty(int(s.steps_bytes), **u8)
         self.bwd_steps = torch.empty(int(s.steps_bytes), **u8)
         self.wgrad_ws = torch.empty(int(_cabi.lib().spnerf_mlp_wgrad_workspace_bytes(ctypes.byref(self.cfg))), **u8)
         self.pack_ws = torch.empty(int(_cabi.lib().spnerf_net_pack_workspace_bytes(ctypes.byref(self.cfg))), **u8)
+        # self-cleaning scratch: slots summed with atomics (flushed and cleared by the weight-gradient reduce kernel)
+        # and the running max |dL/d out| of the compositing adjoint (reset by the same kernel)
+        self.accum = torch.zeros(_cabi.ACCUM_FLOATS, dtype=torch.float32, device=device)
+        self.absmax = torch.zeros(1, dtype=torch.float32, device=device)
         self._packed_key = None
         self._prepared_key = None
         self._grad_key = None
@@ -306,10 +357,6 @@ class NetEngine:
             self._prepared_key = ptrs
         _cabi.check(_cabi.lib().spnerf_net_pack(ctypes.byref(self.cfg), _p(self.pack_ws), _p(self.fwd_blob),
                                                 _p(self.bwd_blob), _p(self.small), _stream()), "spnerf_net_pack")
-        if self.blob_copies > 1:
-            for blob, nbytes in ((self.fwd_blob, int(self.sizes.fwd_blob_bytes)), (self.bwd_blob, int(self.sizes.bwd_blob_bytes))):
-                v = blob.view(self.blob_copies, nbytes)
-                v[1:] = v[0]
         self._packed_key = key
         self.n_packs += 1
 
@@ -370,17 +417,19 @@ class NetEngine:
         return self._gflat
 
     def backward(self, g_out, out, rays, n_samples, saves, absmax, labels=None, t_emb=None, g_sky_ray=None,
-                 sky=None, sky_hidden=None, debug_flags=0, timer=None):
-        """All parameter gradients (+ d t_emb) from dL/d out.  Returns (flat, views, g_t_emb)."""
+                 sky=None, sky_hidden=None, debug_flags=0, timer=None, copy=True):
+        """All parameter gradients (+ d t_emb) from dL/d out.  Returns (flat, views, g_t_emb).
+        Launches: backward-data, sky backward, weight-gradient GEMMs, reduce (+ flush of the atomically summed slots).
+        copy=True returns a private copy (autograd hands the views to the caller for good); copy=False returns the
+        engine's persistent buffer."""
         n_rays = rays.shape[0]
         n_points = n_rays * n_samples
         dev = rays.device
-        work = self._grad_buffer()
-        work.zero_()                      # some slots are accumulated into with atomics
+        work = self._grad_buffer()            # every slot is overwritten below: no memset
         by_name = dict(zip(self.names, self._views(work)))
         gsaves = torch.empty(self.grad_save_bytes(n_points), dtype=torch.uint8, device=dev)
         scale = torch.empty(1, dtype=torch.float32, device=dev)
-        small_bias = torch.zeros(16, dtype=torch.float32, device=dev)
+        acc = self.accum.data_ptr()
         g_t = torch.zeros(n_rays, self.cfg.t_dim, dtype=torch.float32, device=dev) if t_emb is not None else None
         a = _cabi.MlpBwd()
         a.cfg = self.cfg
@@ -388,11 +437,16 @@ class NetEngine:
         a.n_rays, a.n_samples, a.n_steps = n_rays, n_samples, self.sizes.bwd_steps
         a.blob, a.steps, a.small = _p(self.bwd_blob), _p(self.bwd_steps), _p(self.small)
         a.saves, a.grad_saves, a.g_absmax, a.scale_out = _p(saves), _p(gsaves), _p(absmax), _p(scale)
-        a.g_emb = _p(by_name.get("semantic_embedding.weight"))
-        a.g_small_bias, a.g_t_emb, a.debug_flags = _p(small_bias), _p(g_t), debug_flags | _ENV_DEBUG
+        a.g_emb = acc + 4 * _cabi.ACC_EMB if self.module.sem else None
+        a.g_small_bias, a.g_t_emb, a.debug_flags = acc + 4 * _cabi.ACC_SMALL_BIAS, _p(g_t), debug_flags | _ENV_DEBUG
         _cabi.check(_cabi.lib().spnerf_mlp_bwd_data(ctypes.byref(a), _stream()), "spnerf_mlp_bwd_data")
         if timer is not None:
             timer.mark("mlp_bwd_data")
+        if g_sky_ray is not None:             # before the weight-gradient launch: its reduce kernel flushes the scratch
+            _cabi.check(_cabi.lib().spnerf_sky_bwd(
+                _p(self.small), ctypes.byref(self.cfg), _p(rays), _p(sky), _p(sky_hidden), _p(g_sky_ray), n_rays,
+                acc + 4 * _cabi.ACC_SKY_W0, acc + 4 * _cabi.ACC_SKY_B0, acc + 4 * _cabi.ACC_SKY_W2,
+                acc + 4 * _cabi.ACC_SKY_B2, _stream()), "spnerf_sky_bwd")
 
         w = _cabi.MlpWgrad()
         w.cfg = self.cfg
@@ -402,28 +456,17 @@ class NetEngine:
             table[_cabi.PARAM_SLOTS[name]] = v.data_ptr()
         w.grads_host = table
         w.workspace, w.workspace_bytes = _p(self.wgrad_ws), self.wgrad_ws.numel()
+        w.accum, w.absmax_reset = acc, _p(self.absmax)
         # the scatter tables embed the gradient pointers: uploaded once per gradient buffer
-        key = (work.data_ptr(), self.wgrad_ws.data_ptr())
+        key = (work.data_ptr(), self.wgrad_ws.data_ptr(), acc)
         if key != self._grad_key:
             _cabi.check(_cabi.lib().spnerf_mlp_wgrad_prepare(ctypes.byref(w), _stream()), "spnerf_mlp_wgrad_prepare")
             self._grad_key = key
         _cabi.check(_cabi.lib().spnerf_mlp_bwd_weights(ctypes.byref(w), _stream()), "spnerf_mlp_bwd_weights")
         if timer is not None:
             timer.mark("mlp_bwd_weights")
-
-        # biases of the tiny last layers were reduced by the backward-data kernel
-        by_name["rgb_from_xyzdir.2.bias"].copy_(small_bias[0:3])
-        by_name["sun_v_net.6.bias"].copy_(small_bias[3:4])
-        by_name["sigma_from_xyz.0.bias"].copy_(small_bias[4:5])
-        if self.module.beta:
-            by_name["beta_from_xyz.2.bias"].copy_(small_bias[5:6])
-        if self.module.sem:
-            by_name["logit_from_label.2.bias"].copy_(small_bias[6:6 + self.n_sem])
-        if g_sky_ray is not None:
-            _cabi.check(_cabi.lib().spnerf_sky_bwd(
-                _p(self.small), ctypes.byref(self.cfg), _p(rays), _p(sky), _p(sky_hidden), _p(g_sky_ray), n_rays,
-                _p(by_name["sky_color.0.weight"]), _p(by_name["sky_color.0.bias"]),
-                _p(by_name["sky_color.2.weight"]), _p(by_name["sky_color.2.bias"]), _stream()), "spnerf_sky_bwd")
+        if not copy:                          # fused step: the persistent buffer itself (valid until the next backward)
+            return work, self._views(work), g_t
         flat = work.clone()
         if timer is not None:
             timer.mark("grad_tail")

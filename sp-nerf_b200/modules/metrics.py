@@ -31,6 +31,11 @@ def _c(t, dtype=torch.float32):
     return t.detach().to(dtype).contiguous()
 
 
+def _f32(t):
+    """fp32 view without forcing contiguity (the depth-loss kernel reads the two columns of `depths` in place)."""
+    return t.detach() if t.dtype == torch.float32 else t.detach().float()
+
+
 class _SolarTerms(torch.autograd.Function):
     """(sc_term2, sc_term3) of metrics.py:17-24 as one (2,) tensor; differentiable w.r.t. the sun visibility of the
     solar-correction pass only (the reference detaches the transparency and the weights)."""
@@ -156,7 +161,7 @@ class DepthLoss(torch.nn.Module):
             return val, {'coarse_ds': val}
         if not torch.is_tensor(weights):
             weights = torch.full((b,), float(weights), device=depth.device)
-        kw = dict(depth=_c(depth), target_depth=_c(targets), target_weight=_c(weights), lambda_ds=self._lambda_arg,
+        kw = dict(depth=_c(depth), target_depth=_f32(targets), target_weight=_f32(weights), lambda_ds=self._lambda_arg,
                   use_all_depth=self.usealldepth)
         if not self.usealldepth:
             kw.update(z=_c(inputs['z_vals_coarse']), weights=_c(inputs['weights_coarse']), target_std=_c(target_std),

@@ -67,7 +67,10 @@ def render_rays(models, args, rays, ts, semantics=None, mode='test', valid_depth
     b, dev = rays.shape[0], rays.device
     noisy = float(args.noise_std) != 0.0
 
-    z = E.sample_coarse(rays, _draw_uniform(rng, (b, n), dev), n)                          # rendering.py:131-144
+    if rng is not None:                                                                    # rendering.py:131-144
+        z = E.sample_coarse(rays, _draw_uniform(rng, (b, n), dev), n)
+    else:
+        z = E.sample_coarse_rng(rays, n)       # uniforms drawn inside the kernel (Philox), no torch.rand launch
     rays_t = None
     if args.beta:
         rays_t = models['t'](ts) if ts is not None else None                               # rendering.py:155-156

@@ -34,9 +34,32 @@ def shard_batch(batch, rank, world):
 def allreduce_mean_(flat):
     """In-place mean over ranks of the flat gradient buffer (no-op without a process group)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(dist.get_world_size())
+        if flat.is_cuda and dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)      # the division happens inside the collective: no extra launch
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)      # gloo has no AVG
+            flat.div_(dist.get_world_size())
     return flat
+
+
+def allreduce_grads_(module):
+    """Mean over ranks of a module's .grad tensors after loss.backward().  A single-pass step leaves them as slices
+    of the engine's flat gradient buffer (render_pass stores it as engine.last_grad_flat): one in-place all-reduce
+    of that buffer reaches them all.  Otherwise (several passes summed by autograd) they are flattened first."""
+    params = [p for p in module.parameters() if p.grad is not None]
+    if not params or rank_world()[1] == 1:
+        return
+    flat = getattr(getattr(module, "_engine", None), "last_grad_flat", None)
+    if flat is not None:
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+        if all(lo <= p.grad.data_ptr() < hi for p in params) and sum(p.grad.numel() for p in params) == flat.numel():
+            allreduce_mean_(flat)
+            return
+    grads = [p.grad for p in params]
+    flat = torch._utils._flatten_dense_tensors(grads)
+    allreduce_mean_(flat)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
 
 
 def broadcast_(flat, src=0):

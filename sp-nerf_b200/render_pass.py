@@ -48,9 +48,10 @@ class _Pass(torch.autograd.Function):
         g_out, g_sky_ray, absmax = E.composite_bwd(
             out, z, weights, trans, rgb_raw, eng.n_out, eng.col_sem, eng.n_sem, g_rgb=c(g_rgb), g_depth=c(g_depth),
             g_sem=c(g_sem) if eng.n_sem > 0 and g_sem is not None and g_sem.numel() else None, g_w=c(g_w), g_t=c(g_t),
-            g_out_ext=c(g_out_ext), noise=noise, noise_std=ctx.noise_std)
-        _, views, g_temb = eng.backward(g_out, out, rays, n, saves, absmax, labels=labels, t_emb=t_emb,
-                                        g_sky_ray=g_sky_ray, sky=sky, sky_hidden=sky_hidden)
+            g_out_ext=c(g_out_ext), noise=noise, noise_std=ctx.noise_std, absmax=eng.absmax)
+        flat, views, g_temb = eng.backward(g_out, out, rays, n, saves, absmax, labels=labels, t_emb=t_emb,
+                                           g_sky_ray=g_sky_ray, sky=sky, sky_hidden=sky_hidden)
+        eng.last_grad_flat = flat          # the views below are slices of this one buffer (one all-reduce reaches them all)
         return (None, None, None, None, None, None, g_temb if ctx.has_t else None, None, None, None) + tuple(views)
 
 

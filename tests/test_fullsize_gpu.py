@@ -189,3 +189,36 @@ def test_no_grad_passes_save_no_activations():
         p.requires_grad_(False)
     render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="test")
     assert eng.last_saved_bytes == 0                  # frozen parameters: nothing to differentiate
+
+
+def test_graphed_step_replays_the_fused_step():
+    """train_step.GraphedStep (the step captured in one CUDA graph) at the reference's default batch of 1024 rays:
+    same seed -> the replay reproduces the eager fused step (scalars bit-equal, gradient to atomics' round-off);
+    consecutive replays draw different sample depths; a new batch is picked up through the static buffers."""
+    from spnerf_b200 import engine as E
+    args = config.make_args(sem=True, num_sem_classes=3, fc_units=512)
+    model = _model(args)
+    batch = {k: v.to(DEV) for k, v in synthetic.make_batch(1024, seed=35).items()}
+    E.manual_seed(5)
+    flat, _, scalars, launches = train_step.fused_step(model, args, batch, repack=True)
+    want_flat, want_scalars = flat.clone(), scalars.clone()
+    assert launches <= 12, launches
+    gs = train_step.GraphedStep(model, args, batch)
+    E.manual_seed(5)
+    flat, _, scalars = gs()
+    torch.cuda.synchronize()
+    assert torch.equal(scalars[:3], want_scalars[:3])
+    assert float((flat - want_flat).norm() / want_flat.norm()) <= 1e-5
+    first = scalars.clone()
+    flat, _, scalars = gs()                      # next replay: the device-side stream has advanced
+    torch.cuda.synchronize()
+    assert not torch.equal(scalars[:3], first[:3]) and bool(torch.isfinite(scalars[:3]).all())
+    other = {k: v.to(DEV) for k, v in synthetic.make_batch(1024, seed=36).items()}
+    E.manual_seed(5)
+    flat2, _, sc2, _ = train_step.fused_step(model, args, other, repack=True)
+    want2, wsc2 = flat2.clone(), sc2.clone()
+    E.manual_seed(5)
+    flat, _, scalars = gs(other)
+    torch.cuda.synchronize()
+    assert torch.equal(scalars[:3], wsc2[:3])
+    assert float((flat - want2).norm() / want2.norm()) <= 1e-5

@@ -295,7 +295,7 @@ def test_full_size_training_step_properties():
     batch = synthetic.make_batch(b, seed=21, device=DEV)
 
     def step(loss_scale):
-        torch.manual_seed(123)
+        E.manual_seed(123)
         res = render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="train",
                           valid_depth=batch["valid_depth"], target_depths=batch["depths"],
                           target_std=batch["depth_std"])
@@ -581,7 +581,7 @@ def test_full_size_guided_mapping_step_properties():
     batch = synthetic.make_batch(b, seed=33, device=DEV)
 
     def step():
-        torch.manual_seed(5)
+        E.manual_seed(5)
         res = render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="train",
                           valid_depth=batch["valid_depth"], target_depths=batch["depths"],
                           target_std=batch["depth_std"])
@@ -735,3 +735,24 @@ def test_sample_counts_off_the_fast_paths(n_samples, b):
             continue
         rel = float((a.cpu() - w).norm() / w.norm())
         assert rel <= 2e-2, (name, rel)
+
+
+def test_device_side_uniforms_of_the_coarse_sampler():
+    """spnerf_sample_coarse_rng (Philox in the kernel, replaces the torch.rand of rendering.py:143): every depth stays
+    inside its stratified bin, the implied uniforms are uniform, a seed replays, consecutive launches differ."""
+    b, n = 4096, 64
+    rays = synthetic.make_batch(b, seed=3, device=DEV)["rays"]
+    lo = O.stratified_z(rays.cpu(), n, torch.zeros(b, n)).to(DEV)
+    hi = O.stratified_z(rays.cpu(), n, torch.ones(b, n)).to(DEV)
+    E.manual_seed(77)
+    z1 = E.sample_coarse_rng(rays, n)
+    z2 = E.sample_coarse_rng(rays, n)
+    E.manual_seed(77)
+    z1b = E.sample_coarse_rng(rays, n)
+    assert torch.equal(z1, z1b) and not torch.equal(z1, z2)
+    assert bool((z1 >= lo).all()) and bool((z1 <= hi).all())
+    u = ((z1 - lo) / (hi - lo).clamp_min(1e-12))[:, 1:-1]            # interior bins have a non-degenerate width
+    assert abs(float(u.mean()) - 0.5) < 5e-3 and abs(float(u.var()) - 1 / 12) < 3e-3
+    assert abs(float(torch.corrcoef(torch.stack([u[:, :-1].reshape(-1), u[:, 1:].reshape(-1)]))[0, 1])) < 1e-2
+    u2 = ((z2 - lo) / (hi - lo).clamp_min(1e-12))[:, 1:-1]
+    assert abs(float(torch.corrcoef(torch.stack([u.reshape(-1), u2.reshape(-1)]))[0, 1])) < 1e-2
