@@ -394,6 +394,37 @@ typedef struct SpnerfGuided {
 int spnerf_sample_guided(const SpnerfGuided* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Geometry either side of the renderer.  The RPC localisation (rpcm) before the first and
+ * the UTM projection / rasterisation (pyproj, plyflatten) after the second stay on the host.
+ * ------------------------------------------------------------------------------------------- */
+/* Rays from localised pixels (replaces datasets/satellite_scene.py:38-68 get_rays after rpc.localization, the
+ * float32 cast, normalize_rays :415-425 and the sun-direction columns :463-473; geodetic_to_ecef = modules/utils.py:80-100
+ * in fp64).  Row i of `rays`: [origin(3), direction(3), near, far, (sun_dir(3))] float32, row_stride floats apart. */
+typedef struct SpnerfRaysFromGeodetic {
+  const double* lon_near; const double* lat_near;   /* (n) degrees: pixels localised at alt_near = the MAXIMUM altitude */
+  const double* lon_far; const double* lat_far;     /* (n) degrees: the same pixels at alt_far = the minimum altitude   */
+  double alt_near, alt_far;
+  float center[3]; float range;                     /* scene.loc offsets / max scale (satellite_scene.py:122-124)        */
+  int32_t normalize;                                /* 1: apply normalize_rays                                           */
+  int32_t has_sun;                                  /* 1: write sun_dir into columns 8..10                               */
+  float sun_dir[3]; int32_t row_stride;             /* >= 8 (11 with has_sun)                                            */
+  int64_t n_rays;
+  float* rays;
+} SpnerfRaysFromGeodetic;
+int spnerf_rays_from_geodetic(const SpnerfRaysFromGeodetic* args, void* stream);
+
+/* DSM point cloud (replaces datasets/satellite_scene.py:475-505 get_latlonalt_from_nerf_prediction and
+ * modules/utils.py:103-120 ecef_to_latlon_custom): lat / lon in degrees and altitude in metres, fp64. */
+typedef struct SpnerfPointsToGeodetic {
+  const float* rays; int32_t row_stride; int32_t _pad;   /* normalised rays, >= 6 columns                    */
+  const float* depth;                                    /* (n) predicted depth (render_rays' depth_coarse)  */
+  float center[3]; float range;
+  int64_t n_rays;
+  double* lat; double* lon; double* alt;                 /* (n) each                                         */
+} SpnerfPointsToGeodetic;
+int spnerf_points_to_geodetic(const SpnerfPointsToGeodetic* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimiser step over the flat fp32 parameter buffer (replaces torch.optim.Adam(parameters, lr=args.lr,
  * weight_decay=0) of main.py:96-97; torch's update order; bias corrections from `step` >= 1 and the
  * 1 - beta factors are formed in double like torch's).  All four

@@ -173,6 +173,20 @@ class LossUncertainty(ctypes.Structure):
                 ("beta_ray", VP), ("g_rgb", VP), ("g_weights", VP), ("g_beta", VP), ("losses", VP), ("workspace", VP)]
 
 
+F64 = ctypes.c_double
+
+
+class RaysFromGeodetic(ctypes.Structure):
+    _fields_ = [("lon_near", VP), ("lat_near", VP), ("lon_far", VP), ("lat_far", VP), ("alt_near", F64), ("alt_far", F64),
+                ("center", F32 * 3), ("range", F32), ("normalize", I32), ("has_sun", I32), ("sun_dir", F32 * 3),
+                ("row_stride", I32), ("n_rays", I64), ("rays", VP)]
+
+
+class PointsToGeodetic(ctypes.Structure):
+    _fields_ = [("rays", VP), ("row_stride", I32), ("_pad", I32), ("depth", VP), ("center", F32 * 3), ("range", F32),
+                ("n_rays", I64), ("lat", VP), ("lon", VP), ("alt", VP)]
+
+
 class Guided(ctypes.Structure):
     _fields_ = [("rays", VP), ("z", VP), ("weights", VP), ("depth", VP), ("valid_depth", VP),
                 ("target_depth", VP), ("target_depth_stride", I64), ("target_std", VP), ("u_pred", VP),
@@ -205,6 +219,10 @@ def _declare_rest(L):
         f = getattr(L, name)
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.POINTER(st), VP]
+    for name, st in (("spnerf_rays_from_geodetic", RaysFromGeodetic), ("spnerf_points_to_geodetic", PointsToGeodetic)):
+        f = getattr(L, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.POINTER(st), VP]
     for name, st in (("spnerf_loss_solar", LossSolar), ("spnerf_loss_uncertainty", LossUncertainty)):
         f = getattr(L, name)
         f.restype = ctypes.c_int
@@ -226,7 +244,7 @@ def _declare_rest(L):
 
 
 STRUCTS = (UmmaSelftest, NetConfig, NetSizes, MlpFwd, CompositeFwd, CompositeBwd, Losses, Guided, MlpBwd, MlpWgrad,
-           LossSolar, LossUncertainty)
+           LossSolar, LossUncertainty, RaysFromGeodetic, PointsToGeodetic)
 
 _declare_base = _declare
 

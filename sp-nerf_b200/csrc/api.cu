@@ -32,4 +32,6 @@ extern "C" void spnerf_struct_sizes(int32_t* out) {
   out[i++] = (int32_t)sizeof(SpnerfMlpWgrad);
   out[i++] = (int32_t)sizeof(SpnerfLossSolar);
   out[i++] = (int32_t)sizeof(SpnerfLossUncertainty);
+  out[i++] = (int32_t)sizeof(SpnerfRaysFromGeodetic);
+  out[i++] = (int32_t)sizeof(SpnerfPointsToGeodetic);
 }

@@ -28,6 +28,7 @@ struct FwdParams {
   const float* small; SmallOffsets so; SaveMap sm;
   float* out; uint8_t* saves;
   int mapping, sem, n_classes, emb_dim, beta, t_dim, in_dim, n_out, col_beta, col_sem;
+  AuxExtra ax;
   int debug;
   long long* prof;
   int stagger, stagger_groups;      // start delay of cluster c: stagger * (c % groups) / groups cycles
@@ -217,6 +218,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             a[kAuxColOne] = 1.f; a[kAuxColSun] = sun[0]; a[kAuxColSun + 1] = sun[1]; a[kAuxColSun + 2] = sun[2];
             if (p.beta && p.t_emb)
               for (int e = 0; e < p.t_dim; ++e) a[kAuxColT + e] = p.t_emb[ray * p.t_dim + e];
+            // encoded-input columns 64.. (label embedding): high part, residual, high part again (net_plan.h AuxExtra)
+            for (int q = 0; q < p.ax.n; ++q) {
+              const float val = lab >= 0 ? S[p.so.emb + lab * p.emb_dim + (64 + q - base)] : 0.f;
+              const float hi_f = __half2float(__float2half_rn(val));
+              a[p.ax.col_hi[q]] = hi_f; a[p.ax.col_lo[q]] = val - hi_f; a[p.ax.col_dup[q]] = hi_f;
+            }
           }
           if (cg == 1) {                         // operand of this tile's aux steps
             if (valid) a[kAuxColOneLo] = 1.f;
@@ -377,7 +384,9 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.small = a->small; p.so = make_small_offsets(a->cfg); p.sm = make_save_map(a->cfg);
   p.out = a->out; p.saves = static_cast<uint8_t*>(a->saves);
   const NetDims d = make_dims(a->cfg);
-  if (d.in_dim > 64) return SPNERF_ERR_UNSUPPORTED;
+  const AuxExtra ax = make_aux_extra(a->cfg);
+  if (ax.n < 0) return SPNERF_ERR_UNSUPPORTED;
+  p.ax = ax;
   p.mapping = a->cfg.mapping; p.sem = a->cfg.sem; p.n_classes = a->cfg.num_sem_classes; p.emb_dim = a->cfg.emb_dim;
   p.beta = a->cfg.beta; p.t_dim = a->cfg.t_dim; p.in_dim = d.in_dim; p.n_out = d.n_out;
   p.col_beta = d.col_beta; p.col_sem = d.col_sem;

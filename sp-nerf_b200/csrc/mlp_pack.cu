@@ -66,6 +66,11 @@ __device__ __forceinline__ void small_copy_item(const CopyItem& it, float* __res
 struct AuxItem {
   const float* bias; int bias_n;          // bias[row0 + i], valid while row0 + i < bias_n
   const float* wx; int wx_ld, wx_rows, wx_col0, wx_ncols, dst_col;   // B[i][dst_col+e] = wx[row0+i][wx_col0+e]
+  // single columns of a weight matrix (encoded-input columns beyond the input slab, net_plan.h AuxExtra):
+  // B[i][ex_dst[k]] = ex_w[row0+i][ex_src[k]], high part (mode 0) or fp16 residual (mode 1)
+  const float* ex_w; int ex_ld, ex_rows, n_ex;
+  int8_t ex_src_off[12], ex_dst[12], ex_mode[12];
+  int ex_col0;
   int row0, n;
   uint32_t dst_off16;
 };
@@ -85,6 +90,12 @@ __device__ __forceinline__ void aux_pack_item(const AuxItem& it, uint8_t* __rest
     }
     if (it.wx && r < it.wx_rows)
       for (int e = 0; e < it.wx_ncols; ++e) h[it.dst_col + e] = __float2half_rn(it.wx[(size_t)r * it.wx_ld + it.wx_col0 + e]);
+    if (it.ex_w && r < it.ex_rows)
+      for (int k = 0; k < it.n_ex; ++k) {
+        const float w = it.ex_w[(size_t)r * it.ex_ld + it.ex_col0 + it.ex_src_off[k]];
+        const __half hi = __float2half_rn(w);
+        h[it.ex_dst[k]] = it.ex_mode[k] == 0 ? hi : __float2half_rn(w - __half2float(hi));
+      }
     uint8_t* dst = blob + (size_t)it.dst_off16 * 16;
     *reinterpret_cast<uint4*>(dst + aux_offset(i, 0)) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(dst + aux_offset(i, 8)) = *reinterpret_cast<const uint4*>(h + 8);
@@ -115,6 +126,9 @@ struct AuxSpec {
   bool on = false;
   const float* bias = nullptr; int bias_n = 0;
   const float* wx = nullptr; int wx_ld = 0, wx_rows = 0, wx_col0 = 0, wx_ncols = 0, dst_col = 0;
+  const float* ex_w = nullptr; int ex_ld = 0, ex_rows = 0, n_ex = 0, ex_col0 = 0;
+  int8_t ex_src_off[12] = {}, ex_dst[12] = {}, ex_mode[12] = {};
+  void extra(int src_off, int dst, int mode) { ex_src_off[n_ex] = (int8_t)src_off; ex_dst[n_ex] = (int8_t)dst; ex_mode[n_ex] = (int8_t)mode; ++n_ex; }
 };
 inline AuxSpec aux_bias(const float* b, int n) { AuxSpec a; a.on = true; a.bias = b; a.bias_n = n; return a; }
 
@@ -172,6 +186,8 @@ struct Builder {
       it.bias = aux.bias; it.bias_n = aux.bias_n;
       it.wx = aux.wx; it.wx_ld = aux.wx_ld; it.wx_rows = aux.wx_rows; it.wx_col0 = aux.wx_col0;
       it.wx_ncols = aux.wx_ncols; it.dst_col = aux.dst_col;
+      it.ex_w = aux.ex_w; it.ex_ld = aux.ex_ld; it.ex_rows = aux.ex_rows; it.n_ex = aux.n_ex; it.ex_col0 = aux.ex_col0;
+      for (int k = 0; k < aux.n_ex; ++k) { it.ex_src_off[k] = aux.ex_src_off[k]; it.ex_dst[k] = aux.ex_dst[k]; it.ex_mode[k] = aux.ex_mode[k]; }
       it.row0 = row0; it.n = n; it.dst_off16 = off16;
       aux_items.push_back(it);
       off16 += (uint32_t)(n * 32 / 16);
@@ -255,11 +271,18 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     for (int k = 0; k < ncols / 64; ++k) v.push_back({k, 64 * k, 4, 0});
     return v;
   };
-  // layer 0: split-precision product  in_hi*W_hi + in_lo*W_hi + in_hi*W_lo   (models/spnerf.py:202)
-  for (int g = 0; g < 2; ++g)
+  // layer 0: split-precision product  in_hi*W_hi + in_lo*W_hi + in_hi*W_lo   (models/spnerf.py:202); input columns
+  // beyond the slab ride in the aux step with the same three products (net_plan.h AuxExtra)
+  const AuxExtra ax = make_aux_extra(c);
+  for (int g = 0; g < 2; ++g) {
+    AuxSpec a0 = aux_bias(P[SPNERF_P_FC_W0 + 1], kFeat);
+    if (ax.n > 0) {
+      a0.ex_w = P[SPNERF_P_FC_W0]; a0.ex_ld = d.in_dim; a0.ex_rows = kFeat; a0.ex_col0 = 64;
+      for (int q = 0; q < ax.n; ++q) { a0.extra(q, ax.col_hi[q], 0); a0.extra(q, ax.col_lo[q], 0); a0.extra(q, ax.col_dup[q], 1); }
+    }
     b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, g * kHalf, kHalf, g * kHalf,
-            {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}}, false, false,
-            aux_bias(P[SPNERF_P_FC_W0 + 1], kFeat));
+            {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}}, false, false, a0);
+  }
   b.end_phase();
   for (int i = 1; i < 8; ++i) {   // models/spnerf.py:203-208, skip concat [h, input] at :327
     const bool skip = (i == c.skip_layer);
@@ -267,8 +290,12 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     for (int g = 0; g < 2; ++g) {
       auto srcs = act8(kFeat);
       if (skip) srcs.push_back({kSlabInpHi, kFeat, ink, 0});
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs, false, false,
-              aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], kFeat));
+      AuxSpec ai = aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], kFeat);
+      if (skip && ax.n > 0) {        // skip concat [h, input]: input columns 64.. through the aux step (high parts)
+        ai.ex_w = P[SPNERF_P_FC_W0 + 2 * i]; ai.ex_ld = cols; ai.ex_rows = kFeat; ai.ex_col0 = kFeat + 64;
+        for (int q = 0; q < ax.n; ++q) ai.extra(q, ax.col_hi[q], 0);
+      }
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs, false, false, ai);
     }
     b.end_phase();
   }
@@ -339,7 +366,7 @@ int validate(const SpnerfNetConfig* c) {
   if (c->sem && (c->num_sem_classes < 1 || c->num_sem_classes > 8 || c->emb_dim < 1 || c->emb_dim > 8))
     return SPNERF_ERR_UNSUPPORTED;
   if (c->beta && (c->t_dim < 1 || c->t_dim > 8)) return SPNERF_ERR_UNSUPPORTED;
-  if (make_dims(*c).in_dim > 64) return SPNERF_ERR_UNSUPPORTED;
+  if (make_aux_extra(*c).n < 0) return SPNERF_ERR_UNSUPPORTED;      // encoded input beyond the slab + free aux columns
   return 0;
 }
 

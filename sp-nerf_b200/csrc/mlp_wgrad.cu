@@ -523,7 +523,7 @@ void add_group(Plan& pl, const std::vector<BSpec>& bspec, const std::vector<Bloc
           else if (rr.kind == 1 && cr.bias) { s.dst = cr.bias + cr.m0; s.ld_col = 1; }
           else if (rr.kind == 2 && cr.take_sun && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
           else if (rr.kind == 3 && cr.take_t && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
-          else if (rr.kind == 4 && cr.take_inp && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols;
+          else if (rr.kind == 4 && cr.take_inp && cr.W) s.dst = cr.W + (size_t)cr.m0 * cr.ld + cr.in_cols + rr.i0;
           else continue;
           pl.segs.push_back(s);
         }
@@ -574,7 +574,9 @@ Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_pairs) {
     if (c.beta) blk.rows.push_back(RowRange{kAuxColT, c.t_dim, 3, 0});
     if (with_inp) {
       blk.runs.push_back(Run{0, (int16_t)sm.inp, 0, 8, 2, 0});
-      blk.rows.push_back(RowRange{16, d.in_dim, 4, 0});
+      blk.rows.push_back(RowRange{16, d.in_dim < 64 ? d.in_dim : 64, 4, 0});
+      const AuxExtra ax = make_aux_extra(c);            // input columns 64..: their high parts are aux columns
+      for (int q = 0; q < ax.n; ++q) blk.rows.push_back(RowRange{ax.col_hi[q], 1, 4, 64 + q});
     }
     return blk;
   };

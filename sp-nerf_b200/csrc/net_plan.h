@@ -113,7 +113,7 @@ struct GradMap {
 
 struct NetDims {
   int in_dim;      // encoded xyz (3 or 60) + emb_dim
-  int in_ksteps;   // K=16 steps covering in_dim
+  int in_ksteps;   // K=16 steps covering the columns of the encoded input that live in the input slab (<= 64)
   int n_out;       // 8 (+1 beta) (+C sem)
   int col_beta, col_sem;
 };
@@ -121,11 +121,31 @@ struct NetDims {
 inline NetDims make_dims(const SpnerfNetConfig& c) {
   NetDims d;
   d.in_dim = (c.mapping ? 60 : 3) + (c.sem ? c.emb_dim : 0);
-  d.in_ksteps = (d.in_dim + 15) / 16;
+  d.in_ksteps = ((d.in_dim < 64 ? d.in_dim : 64) + 15) / 16;
   d.col_beta = c.beta ? 8 : -1;
   d.col_sem = c.sem ? 8 + (c.beta ? 1 : 0) : -1;
   d.n_out = 8 + (c.beta ? 1 : 0) + (c.sem ? c.num_sem_classes : 0);
   return d;
+}
+
+// Encoded input wider than the 64-column input slab (--mapping with more than 4 semantic classes: 60 + C columns).
+// Columns 64.. are label-embedding values; they travel in free columns of the aux operand instead of a second slab
+// (no shared memory left for one): per extra column an fp16 high part, the residual, and a second copy of the high
+// part, so that the first layer keeps its three-product split precision (hi*W_hi + lo*W_hi + hi*W_lo); the skip
+// layer reads the high part only, like the slab columns.  Free aux columns: 13..15, and the transient-embedding
+// columns a configuration does not use.  n < 0: does not fit (refused).
+struct AuxExtra { int n; int col_hi[4], col_lo[4], col_dup[4]; };
+inline AuxExtra make_aux_extra(const SpnerfNetConfig& c) {
+  AuxExtra x{};
+  const int in_dim = (c.mapping ? 60 : 3) + (c.sem ? c.emb_dim : 0);
+  x.n = in_dim > 64 ? in_dim - 64 : 0;
+  if (x.n == 0) return x;
+  int freec[16], nf = 0;
+  for (int k = 13; k < 16; ++k) freec[nf++] = k;
+  for (int k = kAuxColT + (c.beta ? c.t_dim : 0); k < kAuxColOneLo; ++k) freec[nf++] = k;
+  if (x.n > 4 || 3 * x.n > nf) { x.n = -1; return x; }
+  for (int q = 0; q < x.n; ++q) { x.col_hi[q] = freec[q]; x.col_lo[q] = freec[x.n + q]; x.col_dup[q] = freec[2 * x.n + q]; }
+  return x;
 }
 
 inline SaveMap make_save_map(const SpnerfNetConfig& c) {

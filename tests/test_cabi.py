@@ -48,13 +48,25 @@ def test_plan_sizes_host_only():
 
 
 @pytest.mark.parametrize("kw", [dict(feat=256), dict(layers=6), dict(skip_layer=3), dict(num_sem_classes=9, emb_dim=9),
-                                dict(mapping=1, num_sem_classes=5, emb_dim=5)])
+                                dict(mapping=1, num_sem_classes=8, emb_dim=8),
+                                dict(mapping=1, num_sem_classes=6, emb_dim=6, beta=1, t_dim=8)])
 def test_unsupported_configurations_are_refused(kw):
     base = dict(feat=512, layers=8, skip_layer=4, mapping=0, sem=1, num_sem_classes=3, emb_dim=3, beta=0, t_dim=4)
     base.update(kw)
     cfg = _cabi.NetConfig(**base)
     s = _cabi.NetSizes()
     assert _cabi.lib().spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 2     # SPNERF_ERR_UNSUPPORTED
+
+
+def test_encoded_input_wider_than_the_slab_is_planned():
+    """--mapping with the CLI-default 5 semantic classes: 65 encoded columns (one beyond the 64-column input slab)."""
+    lib = _cabi.lib()
+    for c, beta in ((5, 0), (5, 1), (7, 0)):
+        cfg = _cabi.NetConfig(feat=512, layers=8, skip_layer=4, mapping=1, sem=1, num_sem_classes=c, emb_dim=c, beta=beta,
+                              t_dim=4)
+        s = _cabi.NetSizes()
+        assert lib.spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 0
+        assert s.in_dim == 60 + c and s.n_out == 8 + beta + c
 
 
 def test_bad_arguments_are_refused_without_a_device():

@@ -581,7 +581,8 @@ def test_full_size_guided_mapping_step_properties():
     batch = synthetic.make_batch(b, seed=33, device=DEV)
 
     def step():
-        E.manual_seed(5)
+        torch.manual_seed(5)          # the guided sampler's uniforms come from torch
+        E.manual_seed(5)              # the coarse sampler's from the kernel's own stream
         res = render_rays({"coarse": model}, args, batch["rays"], None, semantics=batch["sems"], mode="train",
                           valid_depth=batch["valid_depth"], target_depths=batch["depths"],
                           target_std=batch["depth_std"])
@@ -651,11 +652,14 @@ def test_full_size_inference_chunk_and_shard_independence():
             assert torch.equal(o[k], ref[k]), k
 
 
-@pytest.mark.parametrize("n_classes", [5, 8])
-def test_wide_semantic_head_forward_and_gradients(n_classes):
+@pytest.mark.parametrize("n_classes,mapping", [(5, False), (8, False), (5, True), (7, True)])
+def test_wide_semantic_head_forward_and_gradients(n_classes, mapping):
     """More than four classes use the second float4 of the tiny last-layer weights (forward sums, backward
-    coefficients) and a wider label embedding: forward rows and parameter gradients against the oracle."""
-    cfg = O.make_cfg(sem=True, num_sem_classes=n_classes, mapping=False, fc_units=512, n_samples=64)
+    coefficients) and a wider label embedding: forward rows and parameter gradients against the oracle.
+    With --mapping the encoded input is 60 + C > 64 columns wide (the CLI defaults give 65, modules/opt.py:89): the
+    columns beyond the input slab travel in free aux columns (net_plan.h AuxExtra) through the first layer, the
+    skip layer and their weight gradients."""
+    cfg = O.make_cfg(sem=True, num_sem_classes=n_classes, mapping=mapping, fc_units=512, n_samples=64)
     args = types.SimpleNamespace(**vars(cfg))
     torch.manual_seed(0)
     model = load_model(args)
