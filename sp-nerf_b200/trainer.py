@@ -135,3 +135,69 @@ class Trainer:
         if self.get_current_epoch(self.train_steps) != epoch_before:
             self.lr *= 0.9                                                                 # StepLR(1, 0.9) per epoch
         return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
+
+
+    # -- checkpoints: the layout Lightning writes for NeRF_pl (main.py:19-59, 314-325): {"state_dict": {"nerf_coarse.<param>":
+    # ..., "embedding_t.weight": ...}, "global_step": ...}; a reference checkpoint loads here and vice versa ------------
+    _PREFIX = {"coarse": "nerf_coarse.", "t": "embedding_t."}
+
+    def state_dict(self):
+        out = {}
+        for key, prefix in self._PREFIX.items():
+            if key in self.models:
+                for name, tensor in self.models[key].state_dict().items():
+                    out[prefix + name] = tensor.detach().clone()
+        return out
+
+    def save_checkpoint(self, path):
+        torch.save({"state_dict": self.state_dict(), "global_step": self.train_steps,
+                    "epoch": self.get_current_epoch(self.train_steps), "lr": self.lr,
+                    "optimizer_states": [{"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                                          "step": self.opt_steps}]}, path)
+
+    def load_checkpoint(self, ckpt, strict=True):
+        """`ckpt`: a path or an already loaded dict, from this trainer or from the reference's Lightning run
+        (resume_from_checkpoint, main.py:325).  Parameters are copied INTO the flat buffer's views, so the optimiser
+        and the packed operands keep working; optimiser moments are restored when the checkpoint is ours."""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location=self.device, weights_only=False)
+        sd = ckpt.get("state_dict", ckpt)
+        for key, prefix in self._PREFIX.items():
+            if key not in self.models:
+                continue
+            part = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+            own = self.models[key].state_dict()
+            missing, unexpected = sorted(set(own) - set(part)), sorted(set(part) - set(own))
+            if strict and (missing or unexpected):
+                raise RuntimeError(f"checkpoint does not match models['{key}']: missing {missing}, unexpected {unexpected}")
+            with torch.no_grad():
+                for name, dst in own.items():
+                    if name in part:
+                        if tuple(part[name].shape) != tuple(dst.shape):
+                            raise RuntimeError(f"{prefix}{name}: shape {tuple(part[name].shape)} != {tuple(dst.shape)}")
+                        dst.copy_(part[name])             # state_dict() tensors alias the parameters (views of self.flat)
+        self.train_steps = int(ckpt.get("global_step", self.train_steps))
+        opt = ckpt.get("optimizer_states")
+        if opt and isinstance(opt[0], dict) and "exp_avg" in opt[0] and opt[0]["exp_avg"].numel() == self.flat.numel():
+            self.exp_avg.copy_(opt[0]["exp_avg"])
+            self.exp_avg_sq.copy_(opt[0]["exp_avg_sq"])
+            self.opt_steps = int(opt[0].get("step", self.opt_steps))
+        if "lr" in ckpt:
+            self.lr = float(ckpt["lr"])
+        if hasattr(self.models["coarse"], "engine") and self.device.type == "cuda":
+            self.models["coarse"].engine.mark_dirty()
+
+    # -- batches: the reference's DataLoader(shuffle=True, batch_size) over the pooled rays of all training images
+    # (datasets/__init__.py, main.py:99-107), as one device-side permutation per epoch ------------------------------
+    def epoch_batches(self, rays_pool, generator=None, drop_last=False):
+        """`rays_pool`: dict of tensors with a common first dimension (the reference's batch keys), resident on the
+        device.  Yields shuffled batches of args.batch_size rays (index_select on the device, no host round trip)."""
+        n = next(iter(rays_pool.values())).shape[0]
+        dev = next(iter(rays_pool.values())).device
+        perm = torch.randperm(n, device=dev, generator=generator)
+        bs = int(self.args.batch_size)
+        for i in range(0, n, bs):
+            idx = perm[i:i + bs]
+            if drop_last and idx.numel() < bs:
+                break
+            yield {k: v.index_select(0, idx) for k, v in rays_pool.items()}

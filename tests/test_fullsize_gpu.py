@@ -222,3 +222,20 @@ def test_graphed_step_replays_the_fused_step():
     torch.cuda.synchronize()
     assert torch.equal(scalars[:3], wsc2[:3])
     assert float((flat - want2).norm() / want2.norm()) <= 1e-5
+
+
+def test_two_gpu_allreduced_gradient_equals_the_mean_of_the_shards():
+    """One process per GPU over NCCL (tests/manual/gpu2_allreduce_check.py under torchrun); skipped on a 1-GPU box."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under `gpurun --gpus 2`); the gloo world-size-2 test covers the host logic")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(root, "tests", "manual", "gpu2_allreduce_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.load(open(os.path.join(root, "gpurun_out", "allreduce_check.json")))
+    assert res["ok"] and res["rel_l2"] <= 1e-6, res

@@ -97,3 +97,60 @@ def test_synthetic_batch_shape_and_statistics():
     assert 0.6 < float((b["valid_depth"] > 0).float().mean()) < 0.76
     assert float(b["rays"][:, 0:3].abs().max()) <= 1.0
     assert torch.equal(b["depth_std"] > 0, b["valid_depth"] > 0)
+
+
+def test_trainer_checkpoint_round_trip_with_the_reference_layout(tmp_path):
+    """A Lightning checkpoint of the reference's NeRF_pl (state_dict keys 'nerf_coarse.<param>' / 'embedding_t.weight',
+    main.py:48-57) loads into the trainer's flat-buffer views; the trainer's own checkpoints use the same layout."""
+    import torch
+    from spnerf_b200 import config
+    from spnerf_b200.models import load_model
+    from spnerf_b200.trainer import Trainer
+    args = config.make_args(sem=True, num_sem_classes=3, fc_units=512, beta=True, t_embbeding_tau=4, lr=5e-4)
+    torch.manual_seed(1)
+    tr = Trainer(args, "cpu")
+    torch.manual_seed(2)                                  # a "reference run" with other weights
+    other = load_model(args)
+    t_other = torch.nn.Embedding(30, 4)
+    ref_ckpt = {"state_dict": {**{"nerf_coarse." + k: v.clone() for k, v in other.state_dict().items()},
+                               "embedding_t.weight": t_other.weight.detach().clone()},
+                "global_step": 1234, "pytorch-lightning_version": "1.3.7"}
+    path = tmp_path / "epoch=27.ckpt"
+    torch.save(ref_ckpt, path)
+    flat_ptr = tr.flat.data_ptr()
+    tr.load_checkpoint(str(path))
+    for (k, v), p in zip(other.state_dict().items(), tr.models["coarse"].parameters()):
+        assert torch.equal(p.detach(), v), k
+        assert flat_ptr <= p.data_ptr() < flat_ptr + tr.flat.numel() * 4      # still a view of the flat buffer
+    assert torch.equal(tr.models["t"].weight.detach(), t_other.weight.detach()) and tr.train_steps == 1234
+    # our own checkpoint: same keys as the reference's, optimiser state restored
+    tr.exp_avg.fill_(0.25)
+    tr.opt_steps = 7
+    mine = tmp_path / "mine.ckpt"
+    tr.save_checkpoint(str(mine))
+    saved = torch.load(mine, weights_only=False)
+    assert sorted(saved["state_dict"]) == sorted(ref_ckpt["state_dict"])
+    torch.manual_seed(3)
+    tr2 = Trainer(args, "cpu")
+    tr2.load_checkpoint(str(mine))
+    assert torch.equal(tr2.flat, tr.flat) and float(tr2.exp_avg[0]) == 0.25 and tr2.opt_steps == 7
+    bad = {"state_dict": {k: v for k, v in ref_ckpt["state_dict"].items() if "sigma" not in k}}
+    import pytest
+    with pytest.raises(RuntimeError):
+        tr2.load_checkpoint(bad)
+
+
+def test_epoch_batches_shuffle_covers_every_ray_once():
+    import torch
+    from spnerf_b200 import config, synthetic
+    from spnerf_b200.trainer import Trainer
+    args = config.make_args(sem=True, num_sem_classes=3, fc_units=512, batch_size=100)
+    tr = Trainer(args, "cpu")
+    pool = synthetic.make_batch(1050, seed=3)
+    pool["index"] = torch.arange(1050)
+    seen = torch.cat([b["index"] for b in tr.epoch_batches(pool, generator=torch.Generator().manual_seed(0))])
+    assert seen.numel() == 1050 and torch.equal(torch.sort(seen).values, torch.arange(1050))
+    assert not torch.equal(seen, torch.arange(1050))
+    b0 = next(iter(tr.epoch_batches(pool, generator=torch.Generator().manual_seed(0))))
+    assert b0["rays"].shape == (100, 11) and torch.equal(b0["rays"], pool["rays"][b0["index"]])
+    assert sum(1 for _ in tr.epoch_batches(pool, drop_last=True)) == 10
