@@ -83,9 +83,12 @@ __device__ __forceinline__ YBatch ybatch_load(const uint8_t* ysave, const uint8_
 #endif
 constexpr int kYWin = SPNERF_YWIN;
 struct YWindow { YBatch b[kYWin]; };
+// NB: batches the column group owns in this layer (a narrow network's head layers have fewer than the window)
+template <int NB>
 __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, const uint8_t* ssave, int j0, int row) {
 #pragma unroll
-  for (int i = 0; i < kYWin; ++i) w.b[i] = ybatch_load(ysave, ssave, j0 + 16 * i, row);
+  for (int i = 0; i < kYWin; ++i)
+    if (i < NB) w.b[i] = ybatch_load(ysave, ssave, j0 + 16 * i, row);
 }
 
 // G[j] = acc[j] * dact(j) for columns [j0, j0 + 16 NB) of a chunk at TMEM address taddr;
@@ -167,7 +170,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// FEAT: trunk width (512 or 256); column-group widths as in mlp_fwd.cu
+template <int FEAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
+  constexpr int H = FEAT / 2, QW = FEAT / 4, HW = FEAT / 8;
+  constexpr int NBQ = QW / 16, NBH = HW / 16;      // 16-column batches per column group: trunk layer / head hidden layer
+  constexpr int SPC = QW / 64;                      // activation slabs per column group of a trunk-wide tile
   extern __shared__ __align__(1024) uint8_t smem[];
   // timing-experiment toggles and the phase clock log exist only in SPNERF_EXPERIMENTS builds (tools/build_variant.sh)
 #ifdef SPNERF_EXPERIMENTS
@@ -213,7 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
     const float4* Wsem2 = reinterpret_cast<const float4*>(smem + kOffSem2);
     const float* Wsun6 = reinterpret_cast<const float*>(smem + kOffSun6);
     const float* Wbeta2 = reinterpret_cast<const float*>(smem + kOffBeta2);
-    const int wide_cols = (dbg & 2) ? 32 : 128;
+    const int wide_cols = (dbg & 2) ? 32 : QW;
     EpiSync sync(sh, prof);
     if (lane == 0) mbar_wait(sh.bar_par, 0, 31);
     __syncwarp();
@@ -300,29 +308,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       // ---- E_in: G_s3 = g_v * W_sun6 * cos(x_s3) -> slabs 0..3 ----
       {
         const float cv = g_v * scale;
-        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * 64, 64, xs(p.sm.sun_y[2]), xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
+        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * HW, HW, xs(p.sm.sun_y[2]), xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
       }
       sync.end(true);
-      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[2]));
+      copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[2]));
       // ---- after sun_v_net.4^T: G_s2 ----
       YWindow win;
-      ywin_load(win, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), cg * 64, row);
+      ywin_load<NBH>(win, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), cg * HW, row);
       sync.begin();
-      bwd_columns<0, 4>(taddr, cg * 64, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
+      bwd_columns<0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
       sync.end(true);
-      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[1]));
+      copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[1]));
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
-      ywin_load(win, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), cg * 64, row);
+      ywin_load<NBH>(win, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), cg * HW, row);
       sync.begin();
-      bwd_columns<0, 4>(taddr, cg * 64, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
+      bwd_columns<0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
       {
         const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
-        gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * 64, 64,
-                    xs(p.sm.rgb_y), xs(p.sm.rgb_x), act, kHalf, row, NoEachG());
+        gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * HW, HW,
+                    xs(p.sm.rgb_y), xs(p.sm.rgb_x), act, H, row, NoEachG());
       }
       sync.end(true);
-      copy_slabs_out(act, 0, 4, gs(p.gm.G_sun[0]));
-      copy_slabs_out(act, 4, 4, gs(p.gm.G_rgb));
+      copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[0]));
+      copy_slabs_out(act, H / 64, H / 64, gs(p.gm.G_rgb));
       if (p.beta) {
         // ---- beta hidden G_b1 -> slabs 0..3 (the sun/albedo GEMMs have retired); d t_emb on the way ----
         sync.begin();
@@ -331,21 +339,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         for (int e = 0; e < 8; ++e) tacc[e] = 0.f;
         const float cb = g_bp * scale;
         const float* wt = S + p.so.beta0_wt;
-        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * 64, 64, xs(p.sm.beta_y), xs(p.sm.beta_x), act, 0, row,
+        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * HW, HW, xs(p.sm.beta_y), xs(p.sm.beta_x), act, 0, row,
                     [&](int j, float g) {
 #pragma unroll
-                      for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * kHalf + j), tacc[e]);
+                      for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * H + j), tacc[e]);
                     });
         if (p.g_t_emb && valid)
           for (int e = 0; e < p.t_dim; ++e) atomicAdd(p.g_t_emb + ray * p.t_dim + e, tacc[e] * inv_scale);
         sync.end(true);
-        copy_slabs_out(act, 0, 4, gs(p.gm.G_beta));
+        copy_slabs_out(act, 0, H / 64, gs(p.gm.G_beta));
       }
       // ---- g_f (linear) -> slabs 0..7 ----
       sync.begin();
-      bwd_columns<2, 8>(taddr, cg * 128, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr, win, wide_cols / 16);
+      bwd_columns<2, NBQ>(taddr, cg * QW, nullptr, nullptr, act, 0, row, cg < 2 ? gs(p.gm.g_f) : nullptr, win, wide_cols / 16);
       sync.end(true);
-      copy_slabs_out(act, 4, 4, gs(p.gm.g_f + 4));
+      copy_slabs_out(act, FEAT / 128, FEAT / 128, gs(p.gm.g_f + FEAT / 128));
       // ---- while g_f * W_feats sits in TMEM: semantic hidden G_sem1 -> slabs 0..3, sigma column -> slab 4 ----
       sync.begin();
       if (p.sem) {
@@ -361,15 +369,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
             a += fmaf(cf[4], u.x, fmaf(cf[5], u.y, fmaf(cf[6], u.z, cf[7] * u.w)));
           }
           return a;
-        }, cg * 64, 64, xs(p.sm.sem_y), xs(p.sm.sem_x), act, 0, row, NoEachG());
+        }, cg * HW, HW, xs(p.sm.sem_y), xs(p.sm.sem_x), act, 0, row, NoEachG());
       }
       if (cg == 3) {
-        *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 0)) =
+        *reinterpret_cast<uint4*>(act + (H / 64) * kSlabBytes + slab_chunk_offset(row, 0)) =
             make_uint4(pack2(g_sp * scale, 0.f), 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(act + 4 * kSlabBytes + slab_chunk_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(act + (H / 64) * kSlabBytes + slab_chunk_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
       sync.end(true);
-      if (p.sem) copy_slabs_out(act, 0, 4, gs(p.gm.G_sem));
+      if (p.sem) copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sem));
       // ---- G_7 = g_h * cos(x_7), then the trunk ----
       float gemb[8];
 #pragma unroll
@@ -389,7 +397,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
 #ifdef SPNERF_EXPERIMENTS
         if (!(dbg & (1024 | 4096)))
 #endif
-        ywin_load(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * 128, row);
+        ywin_load<NBQ>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * QW, row);
         sync.begin();
         // three of the four column groups store their part of the gradient tile from registers, the last quarter is
         // copied out of shared memory during the next MMAs (alternating A/B on one box: 2 groups 4.68 ms, 3 groups
@@ -398,18 +406,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
 #ifdef SPNERF_EXPERIMENTS
         if (dbg & 2048) gdirect = nullptr;
-        if (dbg & 1024) bwd_columns<3, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else if (dbg & 4096) bwd_columns<2, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        if (dbg & 1024) bwd_columns<3, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else if (dbg & 4096) bwd_columns<2, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
         else
 #endif
-        if (L > 0) bwd_columns<0, 8>(taddr, cg * 128, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else       bwd_columns<1, 8>(taddr, cg * 128, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
+        if (L > 0) bwd_columns<0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else       bwd_columns<1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
 #ifdef SPNERF_EXPERIMENTS
         if (!(dbg & 2048))
 #endif
-        copy_slabs_out(act, 2 * ndirect, 8 - 2 * ndirect, gs(p.gm.G[L] + 2 * ndirect));
+        copy_slabs_out(act, SPC * ndirect, SPC * (4 - ndirect), gs(p.gm.G[L] + SPC * ndirect));
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }
@@ -446,7 +454,7 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   if (!a || !a->g_out || !a->out || !a->rays || !a->blob || !a->steps || !a->small || !a->saves || !a->grad_saves ||
       !a->g_absmax || !a->scale_out || !a->g_small_bias)
     return SPNERF_ERR_BAD_ARG;
-  if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (!feat_supported(a->cfg.feat) || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   if (a->cfg.sem && (!a->labels || !a->g_emb)) return SPNERF_ERR_BAD_ARG;
   if (a->cfg.beta && !a->t_emb) return SPNERF_ERR_BAD_ARG;
   if (a->n_rays <= 0 || a->n_samples < 1) return a->n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
@@ -468,13 +476,14 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   p.debug = a->debug_flags;
   p.prof = g_prof_bwd;
   host_stagger(p.stagger, p.stagger_groups);
-  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(mlp_bwd_kernel), kSmemTotal); e != cudaSuccess) return -(int)e;
+  void (*kern)(const BwdParams) = a->cfg.feat == 512 ? mlp_bwd_kernel<512> : mlp_bwd_kernel<256>;
+  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_pairs = ((p.n_points + kTileM - 1) / kTileM + 1) / 2;
   const int64_t clusters = sms / 2;
-  mlp_bwd_kernel<<<2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters), kThreads, kSmemTotal,
+  kern<<<2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters), kThreads, kSmemTotal,
                    static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;

@@ -98,7 +98,11 @@ struct NoEach { __device__ __forceinline__ void operator()(int, float) const {} 
 __device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
 
+// FEAT: trunk width (512 or 256).  The tile geometry follows from it: a column group of the epilogue owns FEAT / 4
+// accumulator columns of a trunk layer and FEAT / 8 of a head's hidden layer (FEAT / 2 wide).
+template <int FEAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  constexpr int H = FEAT / 2, QW = FEAT / 4, HW = FEAT / 8;
   extern __shared__ __align__(1024) uint8_t smem[];
   // timing-experiment toggles and the phase clock log exist only in SPNERF_EXPERIMENTS builds (tools/build_variant.sh)
 #ifdef SPNERF_EXPERIMENTS
@@ -253,23 +257,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // of shared memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy
       // competes with the MMAs for shared-memory bandwidth.  debug & 128 selects that variant.)
       const bool direct_all = !(dbg & 128);
-      epi_cols<1, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[0]),
+      epi_cols<1, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[0]),
                         (cg < 2 || direct_all) ? sv(p.sm.y[0]) : nullptr, NoEach());
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[0] + 4));
+      if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[0] + FEAT / 128));
       // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, sv(p.sm.x[i]),
+        epi_cols<0, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[i]),
                           (cg < 2 || direct_all) ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
-        if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.y[i] + 4));
+        if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[i] + FEAT / 128));
       }
       // ---- heads on h: semantic hidden (accumulator columns 0..255) and sigma (256, 257) ----
       sync.begin();
       if (cg == 3) {
         uint32_t v[16];
-        tmem_ld16(taddr + kHalf, v);
+        tmem_ld16(taddr + H, v);
         tmem_wait_ld();
         const float pre = __uint_as_float(v[0]) + __uint_as_float(v[1]);
         if (valid) orow[3] = softplus_ref(pre);                                   // spnerf.py:333
@@ -279,7 +283,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = 0.f;
         const bool wide = p.n_classes > 4;
-        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, (dbg & 32) ? nullptr : sv(p.sm.sem_x),
+        epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, (dbg & 32) ? nullptr : sv(p.sm.sem_x),
                            (dbg & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
           const float4 w = Wsem2[j * 2];
           lg[0] = fmaf(w.x, y, lg[0]); lg[1] = fmaf(w.y, y, lg[1]); lg[2] = fmaf(w.z, y, lg[2]); lg[3] = fmaf(w.w, y, lg[3]);
@@ -295,10 +299,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
       sync.begin();
-      epi_cols<2, true>(taddr, cg * 128, (dbg & 2) ? 32 : 128, act, 0, row, nullptr,
+      epi_cols<2, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, nullptr,
                         (cg < 2 || direct_all) ? sv(p.sm.f) : nullptr, NoEach());
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, 4, 4, sv(p.sm.f + 4));
+      if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.f + FEAT / 128));
 
       // ---- albedo hidden layer (columns 0..255) + first sun layer or beta hidden layer (256..511) ----
       sync.begin();
@@ -311,15 +315,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         if (!p.beta) {
           // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
           // 0..3, the albedo activations to slabs 4..7 (only read back by the debug & 128 copy-out variant)
-          epi_cols<0, true, 16>(taddr, cg * 64, 64, act, kHalf, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
-          epi_cols<0, true>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
+          epi_cols<0, true, 16>(taddr, cg * HW, HW, act, H, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
+          epi_cols<0, true>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
                             NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
           // feats stay live for the sun layer of the next phase: nothing may be written to the slabs
           float bsum[1] = {0.f};
-          epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
-          epi_cols<0, false, 16>(taddr + kHalf, cg * 64, 64, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
+          epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
+          epi_cols<0, false, 16>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
                              [&](int j, float y) { bsum[0] = fmaf(Wbeta2[j], y, bsum[0]); });
           float r4[4] = {c3[0], c3[1], c3[2], bsum[0]};
           reduce_groups<4>(scratch, r4, cg, row);
@@ -333,23 +337,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       if (p.beta) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
+        epi_cols<0, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
         sync.end(true);
       }
       if (!direct_all) {
-        copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[0]));
-        if (!p.beta) copy_slabs_out(act, 4, 4, sv(p.sm.rgb_y));
+        copy_slabs_out(act, 0, H / 64, sv(p.sm.sun_y[0]));
+        if (!p.beta) copy_slabs_out(act, H / 64, H / 64, sv(p.sm.rgb_y));
       }
       // ---- sun layer 1 ----
       sync.begin();
-      epi_cols<0, true>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
+      epi_cols<0, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, 0, 4, sv(p.sm.sun_y[1]));
+      if (!direct_all) copy_slabs_out(act, 0, H / 64, sv(p.sm.sun_y[1]));
       // ---- sun layer 2 + output unit (256 -> 1, sigmoid) ----
       sync.begin();
       {
         float part[1] = {0.f};
-        epi_cols<0, false, 16>(taddr, cg * 64, 64, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
+        epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
                            [&](int j, float y) { part[0] = fmaf(Wsun6[j], y, part[0]); });
         reduce_groups<1>(scratch, part, cg, row);
         if (cg == 0 && valid) orow[4] = sigmoid_ref(part[0] + S[p.so.sun6_b]);   // spnerf.py:352
@@ -370,7 +374,7 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   if (!a || !a->rays || !a->blob || !a->steps || !a->small || !a->out || !a->sky) return SPNERF_ERR_BAD_ARG;
   if (!a->z && !a->xyz) return SPNERF_ERR_BAD_ARG;
   if (a->n_rays < 0 || a->n_samples < 1) return SPNERF_ERR_BAD_ARG;
-  if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (!feat_supported(a->cfg.feat) || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   if (a->cfg.beta && !a->t_emb) return SPNERF_ERR_BAD_ARG;
   if (a->n_rays == 0) return 0;
   FwdParams p;
@@ -394,7 +398,8 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.prof = g_prof_fwd;
   host_stagger(p.stagger, p.stagger_groups);
 
-  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(mlp_fwd_kernel), kSmemTotal); e != cudaSuccess) return -(int)e;
+  void (*kern)(const FwdParams) = a->cfg.feat == 512 ? mlp_fwd_kernel<512> : mlp_fwd_kernel<256>;
+  if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -404,7 +409,7 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   if (const char* e = getenv("SPNERF_MAX_CLUSTERS")) { const int v = atoi(e); if (v > 0 && v < clusters) clusters = v; }
 #endif
   const unsigned grid = 2u * (unsigned)(n_pairs < clusters ? n_pairs : clusters);
-  mlp_fwd_kernel<<<grid, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  kern<<<grid, kThreads, kSmemTotal, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

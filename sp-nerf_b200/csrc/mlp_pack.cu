@@ -28,14 +28,42 @@ struct PackItem {
 };
 
 __device__ __forceinline__ void pack_item(const PackItem& it, uint8_t* __restrict__ blob) {
+  if (it.transpose) {
+    // backward tiles: tile (r, k) = W[row0 + k][col0 + r].  A thread-per-chunk gather reads 8 floats a row stride apart
+    // (the first version: 130 us per repack, ~8x the traffic of the forward tiles); instead 64 x 64 blocks of W go
+    // through shared memory with reads that run along W's rows.
+    __shared__ float tile[64][65];
+    for (int r0 = blockIdx.y * 64; r0 < it.n; r0 += gridDim.y * 64) {
+      for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int k = i >> 6, rr = i & 63;
+        const int wr = it.row0 + k, wc = it.col0 + r0 + rr;
+        tile[k][rr] = (r0 + rr < it.n && wr < it.rows && wc < it.cols) ? it.src[(size_t)wr * it.ld + wc] : 0.f;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+        const int rr = i & 63, c = i >> 6;
+        if (r0 + rr < it.n) {
+          __half h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float w = tile[c * 8 + e][rr];
+            const __half hi = __float2half_rn(w);
+            h[e] = it.mode == 0 ? hi : __float2half_rn(w - __half2float(hi));
+          }
+          uint8_t* dst = blob + (size_t)it.dst_off16 * 16 + sm100::slab_chunk_offset(it.dst_row0 + r0 + rr, c);
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < it.n * 8; t += gridDim.y * blockDim.x) {
-    const int r = t >> 3, c = t & 7;   // tile row, 16-byte chunk
+    const int r = t >> 3, c = t & 7;   // tile row, 16-byte chunk: 8 threads read 256 contiguous bytes of one row of W
     __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = c * 8 + e;
-      const int wr = it.transpose ? it.row0 + k : it.row0 + r;
-      const int wc = it.transpose ? it.col0 + r : it.col0 + k;
+      const int wr = it.row0 + r, wc = it.col0 + c * 8 + e;
       float w = 0.f;
       if (wr < it.rows && wc < it.cols) w = it.src[(size_t)wr * it.ld + wc];
       __half hi = __float2half_rn(w);
@@ -266,6 +294,8 @@ struct Builder {
 void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) {
   const NetDims d = make_dims(c);
   const int ink = d.in_ksteps;
+  const int F = c.feat, H = F / 2, Q = H / 2;      // trunk width, head width, head chunk width (one chunk per issuer)
+  const int narrow_merge = F == 512 ? 2 : 4;       // K slabs per ring item of a Q-wide chunk: 16 KB per CTA either way
   auto act8 = [](int ncols) {
     std::vector<Builder::Src> v;
     for (int k = 0; k < ncols / 64; ++k) v.push_back({k, 64 * k, 4, 0});
@@ -275,27 +305,28 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   // beyond the slab ride in the aux step with the same three products (net_plan.h AuxExtra)
   const AuxExtra ax = make_aux_extra(c);
   for (int g = 0; g < 2; ++g) {
-    AuxSpec a0 = aux_bias(P[SPNERF_P_FC_W0 + 1], kFeat);
+    AuxSpec a0 = aux_bias(P[SPNERF_P_FC_W0 + 1], F);
     if (ax.n > 0) {
-      a0.ex_w = P[SPNERF_P_FC_W0]; a0.ex_ld = d.in_dim; a0.ex_rows = kFeat; a0.ex_col0 = 64;
+      a0.ex_w = P[SPNERF_P_FC_W0]; a0.ex_ld = d.in_dim; a0.ex_rows = F; a0.ex_col0 = 64;
       for (int q = 0; q < ax.n; ++q) { a0.extra(q, ax.col_hi[q], 0); a0.extra(q, ax.col_lo[q], 0); a0.extra(q, ax.col_dup[q], 1); }
     }
-    b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, g * kHalf, kHalf, g * kHalf,
+    b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, g * H, H, g * H,
             {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}}, false, false, a0);
   }
   b.end_phase();
   for (int i = 1; i < 8; ++i) {   // models/spnerf.py:203-208, skip concat [h, input] at :327
     const bool skip = (i == c.skip_layer);
-    const int cols = kFeat + (skip ? d.in_dim : 0);
+    const int cols = F + (skip ? d.in_dim : 0);
     for (int g = 0; g < 2; ++g) {
-      auto srcs = act8(kFeat);
-      if (skip) srcs.push_back({kSlabInpHi, kFeat, ink, 0});
-      AuxSpec ai = aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], kFeat);
+      auto srcs = act8(F);
+      if (skip) srcs.push_back({kSlabInpHi, F, ink, 0});
+      AuxSpec ai = aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], F);
       if (skip && ax.n > 0) {        // skip concat [h, input]: input columns 64.. through the aux step (high parts)
-        ai.ex_w = P[SPNERF_P_FC_W0 + 2 * i]; ai.ex_ld = cols; ai.ex_rows = kFeat; ai.ex_col0 = kFeat + 64;
+        ai.ex_w = P[SPNERF_P_FC_W0 + 2 * i]; ai.ex_ld = cols; ai.ex_rows = F; ai.ex_col0 = F + 64;
         for (int q = 0; q < ax.n; ++q) ai.extra(q, ax.col_hi[q], 0);
       }
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], kFeat, cols, g * kHalf, kHalf, g * kHalf, srcs, false, false, ai);
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], F, cols, g * H, H, g * H, srcs, false, false, ai);
+      if (!skip && F == 256) b.merge_last_chunk(2);      // 128-wide chunks: two K slabs per ring item (16 KB per CTA)
     }
     b.end_phase();
   }
@@ -304,16 +335,16 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   // it cannot issue at the tensor pipe's pace), two K slabs per ring item; the 1-wide sigma head is one fused item.
   if (c.sem)
     for (int g = 0; g < 2; ++g) {
-      b.chunk(P[SPNERF_P_SEM0_W], kHalf, kFeat, g * 128, 128, g * 128, act8(kFeat), false, false,
-              aux_bias(P[SPNERF_P_SEM0_B], kHalf));
-      b.merge_last_chunk(2);
+      b.chunk(P[SPNERF_P_SEM0_W], H, F, g * Q, Q, g * Q, act8(F), false, false,
+              aux_bias(P[SPNERF_P_SEM0_B], H));
+      b.merge_last_chunk(narrow_merge);
     }
   {
     // sigma: B row 0 = fp16(w), row 1 = residual; the epilogue adds the two accumulator columns
-    auto srcs = act8(kFeat);
+    auto srcs = act8(F);
     const size_t i0 = b.items.size();
-    b.chunk(P[SPNERF_P_SIGMA_W], 1, kFeat, 0, 16, kHalf, srcs, false, false, aux_bias(P[SPNERF_P_SIGMA_B], 1));
-    b.merge_last_chunk(8);            // PackItems are now per (slab, CTA half): rank 0's half holds rows 0..7
+    b.chunk(P[SPNERF_P_SIGMA_W], 1, F, 0, 16, H, srcs, false, false, aux_bias(P[SPNERF_P_SIGMA_B], 1));
+    b.merge_last_chunk(F / 64);       // PackItems are now per (slab, CTA half): rank 0's half holds rows 0..7
     const size_t i1 = b.items.size();
     std::vector<PackItem> kept;
     for (size_t i = i0; i < i1; ++i) {
@@ -329,31 +360,33 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     b.items.insert(b.items.end(), kept.begin(), kept.end());
   }
   b.end_phase();
-  for (int g = 0; g < 2; ++g)   // feats_from_xyz (:215)
-    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, act8(kFeat), false, false,
-            aux_bias(P[SPNERF_P_FEATS_B], kFeat));
+  for (int g = 0; g < 2; ++g) {   // feats_from_xyz (:215)
+    b.chunk(P[SPNERF_P_FEATS_W], F, F, g * H, H, g * H, act8(F), false, false,
+            aux_bias(P[SPNERF_P_FEATS_B], F));
+    if (F == 256) b.merge_last_chunk(2);
+  }
   b.end_phase();
-  AuxSpec sun0 = aux_bias(P[SPNERF_P_SUN0_W + 1], kHalf);          // + sun direction columns (:351)
-  sun0.wx = P[SPNERF_P_SUN0_W]; sun0.wx_ld = kFeat + 3; sun0.wx_rows = kHalf; sun0.wx_col0 = kFeat;
+  AuxSpec sun0 = aux_bias(P[SPNERF_P_SUN0_W + 1], H);          // + sun direction columns (:351)
+  sun0.wx = P[SPNERF_P_SUN0_W]; sun0.wx_ld = F + 3; sun0.wx_rows = H; sun0.wx_col0 = F;
   sun0.wx_ncols = 3; sun0.dst_col = kAuxColSun;
-  b.chunk(P[SPNERF_P_RGB0_W], kHalf, kFeat, 0, kHalf, 0, act8(kFeat), false, false,
-          aux_bias(P[SPNERF_P_RGB0_B], kHalf));                                           // :226-231
+  b.chunk(P[SPNERF_P_RGB0_W], H, F, 0, H, 0, act8(F), false, false,
+          aux_bias(P[SPNERF_P_RGB0_B], H));                                           // :226-231
   if (c.beta) {
-    AuxSpec beta0 = aux_bias(P[SPNERF_P_BETA0_B], kHalf);          // + transient embedding columns (:360)
-    beta0.wx = P[SPNERF_P_BETA0_W]; beta0.wx_ld = kFeat + c.t_dim; beta0.wx_rows = kHalf; beta0.wx_col0 = kFeat;
+    AuxSpec beta0 = aux_bias(P[SPNERF_P_BETA0_B], H);          // + transient embedding columns (:360)
+    beta0.wx = P[SPNERF_P_BETA0_W]; beta0.wx_ld = F + c.t_dim; beta0.wx_rows = H; beta0.wx_col0 = F;
     beta0.wx_ncols = c.t_dim; beta0.dst_col = kAuxColT;
-    b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, 0, kHalf, kHalf, act8(kFeat), false, false, beta0);   // :258-264
+    b.chunk(P[SPNERF_P_BETA0_W], H, F + c.t_dim, 0, H, H, act8(F), false, false, beta0);   // :258-264
     b.end_phase();
-    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, 0, act8(kFeat), false, false, sun0);               // :234-241
+    b.chunk(P[SPNERF_P_SUN0_W], H, F + 3, 0, H, 0, act8(F), false, false, sun0);               // :234-241
     b.end_phase();
   } else {
-    b.chunk(P[SPNERF_P_SUN0_W], kHalf, kFeat + 3, 0, kHalf, kHalf, act8(kFeat), false, false, sun0);
+    b.chunk(P[SPNERF_P_SUN0_W], H, F + 3, 0, H, H, act8(F), false, false, sun0);
     b.end_phase();
   }
   for (int j = 1; j <= 2; ++j) {      // sun layers 1, 2: two 128-wide chunks, one per issuer lane
     for (int g = 0; g < 2; ++g) {
-      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, act8(kHalf), false, false,
-              aux_bias(P[SPNERF_P_SUN0_W + 2 * j + 1], kHalf));
+      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], H, H, g * Q, Q, g * Q, act8(H), false, false,
+              aux_bias(P[SPNERF_P_SUN0_W + 2 * j + 1], H));
       b.merge_last_chunk(2);          // 128-wide chunks: two K slabs (2 x 8 KB per CTA) per ring item
     }
     b.end_phase();
@@ -362,7 +395,7 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
 
 int validate(const SpnerfNetConfig* c) {
   if (!c) return SPNERF_ERR_BAD_ARG;
-  if (c->feat != 512 || c->layers != 8 || c->skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (!feat_supported(c->feat) || c->layers != 8 || c->skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   if (c->sem && (c->num_sem_classes < 1 || c->num_sem_classes > 8 || c->emb_dim < 1 || c->emb_dim > 8))
     return SPNERF_ERR_UNSUPPORTED;
   if (c->beta && (c->t_dim < 1 || c->t_dim > 8)) return SPNERF_ERR_UNSUPPORTED;
@@ -461,6 +494,7 @@ struct PackPlan {
 };
 
 void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan& pl) {
+  const int F = cfg->feat, H = F / 2;
   build_forward(*cfg, P, pl.f);
   build_backward(*cfg, P, pl.bsteps, &pl.bitems, &pl.boff);
   const SmallOffsets o = make_small_offsets(*cfg);
@@ -468,39 +502,39 @@ void make_pack_plan(const SpnerfNetConfig* cfg, const float* const* P, PackPlan&
   auto add = [&](int slot, int dst, int rows, int cols, int ld, int col0 = 0, int transpose = 0, int dst_ld = 0) {
     pl.cp.push_back({P[slot] ? P[slot] + col0 : nullptr, dst, rows, cols, ld, transpose, dst_ld ? dst_ld : rows});
   };
-  for (int i = 0; i < 8; ++i) add(SPNERF_P_FC_W0 + 2 * i + 1, o.fc_b[i], 1, kFeat, kFeat);
+  for (int i = 0; i < 8; ++i) add(SPNERF_P_FC_W0 + 2 * i + 1, o.fc_b[i], 1, F, F);
   add(SPNERF_P_SIGMA_B, o.sigma_b, 1, 1, 1);
-  add(SPNERF_P_FEATS_B, o.feats_b, 1, kFeat, kFeat);
+  add(SPNERF_P_FEATS_B, o.feats_b, 1, F, F);
   if (cfg->sem) {
-    add(SPNERF_P_SEM0_B, o.sem0_b, 1, kHalf, kHalf);
-    add(SPNERF_P_SEM2_W, o.sem2_w, cfg->num_sem_classes, kHalf, kHalf);
+    add(SPNERF_P_SEM0_B, o.sem0_b, 1, H, H);
+    add(SPNERF_P_SEM2_W, o.sem2_w, cfg->num_sem_classes, H, H);
     add(SPNERF_P_SEM2_B, o.sem2_b, 1, cfg->num_sem_classes, cfg->num_sem_classes);
     add(SPNERF_P_SEM_EMB, o.emb, cfg->num_sem_classes + 1, cfg->emb_dim, cfg->emb_dim);
   }
-  add(SPNERF_P_RGB0_B, o.rgb0_b, 1, kHalf, kHalf);
-  add(SPNERF_P_RGB2_W, o.rgb2_w, 3, kHalf, kHalf);
+  add(SPNERF_P_RGB0_B, o.rgb0_b, 1, H, H);
+  add(SPNERF_P_RGB2_W, o.rgb2_w, 3, H, H);
   add(SPNERF_P_RGB2_B, o.rgb2_b, 1, 3, 3);
-  add(SPNERF_P_SUN0_W + 1, o.sun0_b, 1, kHalf, kHalf);
-  add(SPNERF_P_SUN0_W, o.sun0_wsun, kHalf, 3, kFeat + 3, kFeat, 1);          // -> [3][256]
-  add(SPNERF_P_SUN0_W + 3, o.sun2_b, 1, kHalf, kHalf);
-  add(SPNERF_P_SUN0_W + 5, o.sun4_b, 1, kHalf, kHalf);
-  add(SPNERF_P_SUN0_W + 6, o.sun6_w, 1, kHalf, kHalf);
+  add(SPNERF_P_SUN0_W + 1, o.sun0_b, 1, H, H);
+  add(SPNERF_P_SUN0_W, o.sun0_wsun, H, 3, F + 3, F, 1);          // -> [3][256]
+  add(SPNERF_P_SUN0_W + 3, o.sun2_b, 1, H, H);
+  add(SPNERF_P_SUN0_W + 5, o.sun4_b, 1, H, H);
+  add(SPNERF_P_SUN0_W + 6, o.sun6_w, 1, H, H);
   add(SPNERF_P_SUN0_W + 7, o.sun6_b, 1, 1, 1);
   if (cfg->beta) {
-    add(SPNERF_P_BETA0_B, o.beta0_b, 1, kHalf, kHalf);
-    add(SPNERF_P_BETA0_W, o.beta0_wt, kHalf, cfg->t_dim, kFeat + cfg->t_dim, kFeat, 1);   // -> [t][256]
-    add(SPNERF_P_BETA2_W, o.beta2_w, 1, kHalf, kHalf);
+    add(SPNERF_P_BETA0_B, o.beta0_b, 1, H, H);
+    add(SPNERF_P_BETA0_W, o.beta0_wt, H, cfg->t_dim, F + cfg->t_dim, F, 1);   // -> [t][256]
+    add(SPNERF_P_BETA2_W, o.beta2_w, 1, H, H);
     add(SPNERF_P_BETA2_B, o.beta2_b, 1, 1, 1);
   }
-  add(SPNERF_P_SKY0_W, o.sky0_w, kHalf, 3, 3, 0, 1);                           // -> [3][256]
-  add(SPNERF_P_SKY0_B, o.sky0_b, 1, kHalf, kHalf);
-  add(SPNERF_P_SKY2_W, o.sky2_w, 3, kHalf, kHalf);
+  add(SPNERF_P_SKY0_W, o.sky0_w, H, 3, 3, 0, 1);                           // -> [3][256]
+  add(SPNERF_P_SKY0_B, o.sky0_b, 1, H, H);
+  add(SPNERF_P_SKY2_W, o.sky2_w, 3, H, H);
   add(SPNERF_P_SKY2_B, o.sky2_b, 1, 3, 3);
   // image of the shared-memory parameter region (net_plan.h kOffRgb2..): [j][4] / [j][8] / [j] / [j]
-  add(SPNERF_P_RGB2_W, o.smallw, 3, kHalf, kHalf, 0, 1, 4);
-  if (cfg->sem) add(SPNERF_P_SEM2_W, o.smallw + 1024, cfg->num_sem_classes, kHalf, kHalf, 0, 1, 8);
-  add(SPNERF_P_SUN0_W + 6, o.smallw + 3072, 1, kHalf, kHalf);
-  if (cfg->beta) add(SPNERF_P_BETA2_W, o.smallw + 3328, 1, kHalf, kHalf);
+  add(SPNERF_P_RGB2_W, o.smallw, 3, H, H, 0, 1, 4);
+  if (cfg->sem) add(SPNERF_P_SEM2_W, o.smallw + 1024, cfg->num_sem_classes, H, H, 0, 1, 8);
+  add(SPNERF_P_SUN0_W + 6, o.smallw + 3072, 1, H, H);
+  if (cfg->beta) add(SPNERF_P_BETA2_W, o.smallw + 3328, 1, H, H);
   pl.bytes_f = pl.f.items.size() * sizeof(PackItem);
   pl.bytes_b = pl.bitems.size() * sizeof(PackItem);
   pl.bytes_c = pl.cp.size() * sizeof(CopyItem);
@@ -572,7 +606,8 @@ extern "C" int spnerf_net_pack(const SpnerfNetConfig* cfg, const void* pack_ws, 
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void sky_fwd_kernel(const float* __restrict__ small, SmallOffsets o, const float* __restrict__ rays,
-                               int64_t n_rays, float* __restrict__ sky, float* __restrict__ hidden) {
+                               int64_t n_rays, float* __restrict__ sky, float* __restrict__ hidden, int nh) {
+  // nh = hidden units (feat / 2: 256 or 128), 32 per pass of the warp
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -581,16 +616,17 @@ __global__ void sky_fwd_kernel(const float* __restrict__ small, SmallOffsets o, 
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
+      if (u * 32 >= nh) break;
       const int j = u * 32 + lane;
       float h = small[o.sky0_b + j];
       h = fmaf(small[o.sky0_w + j], sx, h);
-      h = fmaf(small[o.sky0_w + kHalf + j], sy, h);
-      h = fmaf(small[o.sky0_w + 2 * kHalf + j], sz, h);
+      h = fmaf(small[o.sky0_w + nh + j], sy, h);
+      h = fmaf(small[o.sky0_w + 2 * nh + j], sz, h);
       h = fmaxf(h, 0.f);
-      if (hidden) hidden[r * kHalf + j] = h;
+      if (hidden) hidden[r * nh + j] = h;
       acc0 = fmaf(small[o.sky2_w + j], h, acc0);
-      acc1 = fmaf(small[o.sky2_w + kHalf + j], h, acc1);
-      acc2 = fmaf(small[o.sky2_w + 2 * kHalf + j], h, acc2);
+      acc1 = fmaf(small[o.sky2_w + nh + j], h, acc1);
+      acc2 = fmaf(small[o.sky2_w + 2 * nh + j], h, acc2);
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -615,7 +651,7 @@ extern "C" int spnerf_sky_fwd(const float* small, const SpnerfNetConfig* cfg, co
   const int threads = 256;
   const int64_t blocks = (n_rays * 32 + threads - 1) / threads;
   sky_fwd_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      small, make_small_offsets(*cfg), rays, n_rays, sky, hidden);
+      small, make_small_offsets(*cfg), rays, n_rays, sky, hidden, cfg->feat / 2);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -629,6 +665,8 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   Builder b;
   const NetDims d = make_dims(c);
   const int base = c.mapping ? 60 : 3;
+  const int F = c.feat, H = F / 2, Q = H / 2;      // trunk width, head width, head chunk width
+  const int SF = F / 64, SH = H / 64;              // K slabs of a trunk-wide / head-wide gradient tile
   using Src = Builder::Src;
   auto ks = [](int first_slab, int nslabs) {
     std::vector<Src> v;
@@ -638,53 +676,58 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   // sun_v_net.4 and .2 (256x256): G_s3 -> g_s2 -> g_s1
   for (int j = 2; j >= 1; --j) {      // two 128-wide chunks, one per issuer lane
     for (int g = 0; g < 2; ++g) {
-      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], kHalf, kHalf, g * 128, 128, g * 128, ks(0, 4), true);
-      b.merge_last_chunk(2);
+      b.chunk(P[SPNERF_P_SUN0_W + 2 * j], H, H, g * Q, Q, g * Q, ks(0, SH), true);
+      b.merge_last_chunk(SH >= 4 ? 2 : SH);
     }
     b.end_phase();
   }
   // g_f = G_s1 * W_sun0[:, :512] + G_r1 * W_rgb0 (+ G_b1 * W_beta0[:, :512] in a second phase)
   for (int g = 0; g < 2; ++g) {
     std::vector<Src> v;
-    for (int k = 0; k < 4; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SUN0_W], kHalf, kFeat + 3});
-    for (int k = 0; k < 4; ++k) v.push_back(Src{4 + k, 64 * k, 4, 0, P[SPNERF_P_RGB0_W], kHalf, kFeat});
-    b.chunk(nullptr, 0, 0, g * kHalf, kHalf, g * kHalf, v, true);
+    for (int k = 0; k < SH; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SUN0_W], H, F + 3});
+    for (int k = 0; k < SH; ++k) v.push_back(Src{SH + k, 64 * k, 4, 0, P[SPNERF_P_RGB0_W], H, F});
+    b.chunk(nullptr, 0, 0, g * H, H, g * H, v, true);
+    if (F == 256) b.merge_last_chunk(2);        // 128-wide chunks: two K slabs per ring item
   }
   b.end_phase();
   if (c.beta) {
     for (int g = 0; g < 2; ++g)
-      b.chunk(P[SPNERF_P_BETA0_W], kHalf, kFeat + c.t_dim, g * kHalf, kHalf, g * kHalf, ks(0, 4), true, true);
+      b.chunk(P[SPNERF_P_BETA0_W], H, F + c.t_dim, g * H, H, g * H, ks(0, SH), true, true);
     b.end_phase();
   }
   // g_h = g_f * W_feats (+ G_sem1 * W_sem0 + g_sigma_pre * W_sigma accumulated in the next phase)
-  for (int g = 0; g < 2; ++g)
-    b.chunk(P[SPNERF_P_FEATS_W], kFeat, kFeat, g * kHalf, kHalf, g * kHalf, ks(0, 8), true);
+  for (int g = 0; g < 2; ++g) {
+    b.chunk(P[SPNERF_P_FEATS_W], F, F, g * H, H, g * H, ks(0, SF), true);
+    if (F == 256) b.merge_last_chunk(2);
+  }
   b.end_phase();
   for (int g = 0; g < 2; ++g) {
     std::vector<Src> v;
     if (c.sem)
-      for (int k = 0; k < 4; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SEM0_W], kHalf, kFeat});
-    v.push_back(Src{4, 0, 1, 0, P[SPNERF_P_SIGMA_W], 1, kFeat});
-    b.chunk(nullptr, 0, 0, g * kHalf, kHalf, g * kHalf, v, true, true);
+      for (int k = 0; k < SH; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SEM0_W], H, F});
+    v.push_back(Src{SH, 0, 1, 0, P[SPNERF_P_SIGMA_W], 1, F});       // the sigma column sits in the slab after the semantic hidden gradient
+    b.chunk(nullptr, 0, 0, g * H, H, g * H, v, true, true);
   }
   b.end_phase();
   // trunk, layers 7..1; the label-embedding columns of the skip layer and of layer 0 get their own
   // 16-wide mini phases (only when the embedding exists)
   for (int L = 7; L >= 1; --L) {
     const bool skip = (L == c.skip_layer);
-    const int cols = kFeat + (skip ? d.in_dim : 0);
+    const int cols = F + (skip ? d.in_dim : 0);
     if (skip && c.sem) {
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, kFeat + base, 16, 0, ks(0, 8), true);
-      b.merge_last_chunk(8);
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], F, cols, F + base, 16, 0, ks(0, SF), true);
+      b.merge_last_chunk(SF);
       b.end_phase();
     }
-    for (int g = 0; g < 2; ++g)
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], kFeat, cols, g * kHalf, kHalf, g * kHalf, ks(0, 8), true);
+    for (int g = 0; g < 2; ++g) {
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], F, cols, g * H, H, g * H, ks(0, SF), true);
+      if (F == 256) b.merge_last_chunk(2);
+    }
     b.end_phase();
   }
   if (c.sem) {
-    b.chunk(P[SPNERF_P_FC_W0], kFeat, d.in_dim, base, 16, 0, ks(0, 8), true);
-    b.merge_last_chunk(8);
+    b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, base, 16, 0, ks(0, SF), true);
+    b.merge_last_chunk(SF);
     b.end_phase();
   }
   steps = b.steps;
@@ -701,9 +744,9 @@ __global__ void __launch_bounds__(256) sky_bwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ rays, const float* __restrict__ sky,
                                                       const float* __restrict__ hidden, const float* __restrict__ g_sky,
                                                       int64_t n_rays, float* g_w0, float* g_b0, float* g_w2,
-                                                      float* g_b2) {
-  __shared__ float acc[3 * kHalf + kHalf + 3 * kHalf + 4];   // w0 [256][3] | b0 [256] | w2 [3][256] | b2
-  for (int i = threadIdx.x; i < 7 * kHalf + 4; i += blockDim.x) acc[i] = 0.f;
+                                                      float* g_b2, int nh) {
+  __shared__ float acc[3 * kHalf + kHalf + 3 * kHalf + 4];   // w0 [nh][3] | b0 [nh] | w2 [3][nh] | b2  (nh = feat / 2 <= 256)
+  for (int i = threadIdx.x; i < 7 * kHalf + 4; i += blockDim.x) acc[i] = 0.f;   // (whole array)
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -726,13 +769,14 @@ __global__ void __launch_bounds__(256) sky_bwd_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
+      if (u * 32 >= nh) break;
       const int j = u * 32 + lane;
-      const float h = hidden[r * kHalf + j];
+      const float h = hidden[r * nh + j];
       float gh = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         aw2[c][u] = fmaf(gp[c], h, aw2[c][u]);
-        gh = fmaf(gp[c], small[o.sky2_w + c * kHalf + j], gh);
+        gh = fmaf(gp[c], small[o.sky2_w + c * nh + j], gh);
       }
       gh = h > 0.f ? gh : 0.f;
       ab0[u] += gh;
@@ -742,23 +786,24 @@ __global__ void __launch_bounds__(256) sky_bwd_kernel(const float* __restrict__ 
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
+    if (u * 32 >= nh) break;
     const int j = u * 32 + lane;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       atomicAdd(&acc[j * 3 + c], aw0[u][c]);
-      atomicAdd(&acc[4 * kHalf + c * kHalf + j], aw2[c][u]);
+      atomicAdd(&acc[4 * nh + c * nh + j], aw2[c][u]);
     }
-    atomicAdd(&acc[3 * kHalf + j], ab0[u]);
+    atomicAdd(&acc[3 * nh + j], ab0[u]);
   }
   if (lane == 0)
-    for (int c = 0; c < 3; ++c) atomicAdd(&acc[7 * kHalf + c], ab2[c]);
+    for (int c = 0; c < 3; ++c) atomicAdd(&acc[7 * nh + c], ab2[c]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * kHalf; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 3 * nh; i += blockDim.x) {
     atomicAdd(g_w0 + i, acc[i]);
-    atomicAdd(g_w2 + i, acc[4 * kHalf + i]);
+    atomicAdd(g_w2 + i, acc[4 * nh + i]);
   }
-  for (int i = threadIdx.x; i < kHalf; i += blockDim.x) atomicAdd(g_b0 + i, acc[3 * kHalf + i]);
-  if (threadIdx.x < 3) atomicAdd(g_b2 + threadIdx.x, acc[7 * kHalf + threadIdx.x]);
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) atomicAdd(g_b0 + i, acc[3 * nh + i]);
+  if (threadIdx.x < 3) atomicAdd(g_b2 + threadIdx.x, acc[7 * nh + threadIdx.x]);
 }
 }  // namespace
 
@@ -771,7 +816,7 @@ extern "C" int spnerf_sky_bwd(const float* small, const SpnerfNetConfig* cfg, co
   if (n_rays <= 0) return n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   const int64_t blocks = (n_rays + 63) / 64;     // >= 8 rays per warp
   sky_bwd_kernel<<<(unsigned)(blocks > 148 ? 148 : blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      small, make_small_offsets(*cfg), rays, sky, hidden, g_sky, n_rays, g_w0, g_b0, g_w2, g_b2);
+      small, make_small_offsets(*cfg), rays, sky, hidden, g_sky, n_rays, g_w0, g_b0, g_w2, g_b2, cfg->feat / 2);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -555,6 +555,18 @@ Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_pairs) {
   const SaveMap sm = make_save_map(c);
   const GradMap gm = make_grad_map(c);
   const NetDims d = make_dims(c);
+  const int F = c.feat, H = F / 2;                  // trunk width (512 or 256), head width
+  // B' of a trunk-wide gradient tile: 512 columns are two MMAs of 256 (the second half starts 4 slabs further), 256 one
+  auto wide_b = [&](int unit) {
+    std::vector<BSpec> v{{1, unit, 256}};
+    if (F == 512) v.push_back({1, unit + 4, 256});
+    return v;
+  };
+  auto wide_cols = [&](float* w, int ld, float* bias, int in_cols, bool inp) {
+    std::vector<ColRange> v{ColRange{0, 0, 256, w, ld, 0, bias, in_cols, false, false, inp}};
+    if (F == 512) v.push_back(ColRange{1, 0, 256, w, ld, 256, bias, in_cols, false, false, inp});
+    return v;
+  };
   auto W = [&](int slot) { return G[slot]; };
   // 128-row blocks of a saved activation of `width` features starting at unit `unit`
   auto act_blocks = [&](int unit, int width, std::vector<Block>& out) {
@@ -590,65 +602,61 @@ Plan make_plan(const SpnerfNetConfig& c, float* const* G, int n_pairs) {
     float* w = W(SPNERF_P_FC_W0 + 2 * L);
     float* bptr = W(SPNERF_P_FC_W0 + 2 * L + 1);
     const bool skip = (L == c.skip_layer);
-    const int ld = (L == 0) ? d.in_dim : kFeat + (skip ? d.in_dim : 0);
+    const int ld = (L == 0) ? d.in_dim : F + (skip ? d.in_dim : 0);
     std::vector<Block> blocks;
-    if (L > 0) act_blocks(sm.y[L - 1], kFeat, blocks);
+    if (L > 0) act_blocks(sm.y[L - 1], F, blocks);
     const bool extras = (L == 0 || skip);           // encoded-input columns need the extras rows
     if (extras) blocks.push_back(extras_block(true));
-    std::vector<ColRange> cols = {col(0, 0, kHalf, w, ld, 0, bptr, L == 0 ? 0 : kFeat, false, false, true),
-                                  col(1, 0, kHalf, w, ld, kHalf, bptr, L == 0 ? 0 : kFeat, false, false, true)};
-    add_group(pl, {{1, gm.G[L], kHalf}, {1, gm.G[L] + 4, kHalf}}, blocks, cols, groups, !extras);
+    add_group(pl, wide_b(gm.G[L]), blocks, wide_cols(w, ld, bptr, L == 0 ? 0 : F, true), groups, !extras);
   }
   {  // feats_from_xyz
     std::vector<Block> blocks;
-    act_blocks(sm.y[7], kFeat, blocks);
-    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_FEATS_W), kFeat, 0, W(SPNERF_P_FEATS_B), kFeat),
-                                  col(1, 0, kHalf, W(SPNERF_P_FEATS_W), kFeat, kHalf, W(SPNERF_P_FEATS_B), kFeat)};
-    add_group(pl, {{1, gm.g_f, kHalf}, {1, gm.g_f + 4, kHalf}}, blocks, cols, groups, true);
+    act_blocks(sm.y[7], F, blocks);
+    add_group(pl, wide_b(gm.g_f), blocks, wide_cols(W(SPNERF_P_FEATS_W), F, W(SPNERF_P_FEATS_B), F, false), groups, true);
   }
   {  // heads reading h: logit_from_label.0 (if any) and sigma_from_xyz.0 (column 4 of the small-gradient tile)
     std::vector<Block> blocks;
-    act_blocks(sm.y[7], kFeat, blocks);
+    act_blocks(sm.y[7], F, blocks);
     std::vector<ColRange> cols;
     std::vector<BSpec> bs;
     if (c.sem) {
-      bs.push_back({1, gm.G_sem, kHalf});
-      cols.push_back(col(0, 0, kHalf, W(SPNERF_P_SEM0_W), kFeat, 0, W(SPNERF_P_SEM0_B), kFeat));
+      bs.push_back({1, gm.G_sem, H});
+      cols.push_back(col(0, 0, H, W(SPNERF_P_SEM0_W), F, 0, W(SPNERF_P_SEM0_B), F));
     }
     const int mma = (int)bs.size();
     bs.push_back({1, gm.gsmall, 16});
-    cols.push_back(col(mma, 4, 1, W(SPNERF_P_SIGMA_W), kFeat, 0, nullptr, kFeat));
+    cols.push_back(col(mma, 4, 1, W(SPNERF_P_SIGMA_W), F, 0, nullptr, F));
     add_group(pl, bs, blocks, cols, groups, true);
   }
   {  // heads reading feats: rgb_from_xyzdir.0 and sun_v_net.0 (input [feats, sun_dir])
     std::vector<Block> blocks;
-    act_blocks(sm.f, kFeat, blocks);
+    act_blocks(sm.f, F, blocks);
     blocks.push_back(extras_block(false));
-    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_RGB0_W), kFeat, 0, W(SPNERF_P_RGB0_B), kFeat),
-                                  col(1, 0, kHalf, W(SPNERF_P_SUN0_W), kFeat + 3, 0, W(SPNERF_P_SUN0_W + 1), kFeat, true)};
-    add_group(pl, {{1, gm.G_rgb, kHalf}, {1, gm.G_sun[0], kHalf}}, blocks, cols, groups);
+    std::vector<ColRange> cols = {col(0, 0, H, W(SPNERF_P_RGB0_W), F, 0, W(SPNERF_P_RGB0_B), F),
+                                  col(1, 0, H, W(SPNERF_P_SUN0_W), F + 3, 0, W(SPNERF_P_SUN0_W + 1), F, true)};
+    add_group(pl, {{1, gm.G_rgb, H}, {1, gm.G_sun[0], H}}, blocks, cols, groups);
   }
   if (c.beta) {  // beta_from_xyz.0: input [feats, t_emb]
     std::vector<Block> blocks;
-    act_blocks(sm.f, kFeat, blocks);
+    act_blocks(sm.f, F, blocks);
     blocks.push_back(extras_block(false));
-    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_BETA0_W), kFeat + c.t_dim, 0, W(SPNERF_P_BETA0_B), kFeat,
+    std::vector<ColRange> cols = {col(0, 0, H, W(SPNERF_P_BETA0_W), F + c.t_dim, 0, W(SPNERF_P_BETA0_B), F,
                                       false, true)};
-    add_group(pl, {{1, gm.G_beta, kHalf}}, blocks, cols, groups);
+    add_group(pl, {{1, gm.G_beta, H}}, blocks, cols, groups);
   }
   for (int j = 1; j < 3; ++j) {  // sun_v_net.2 / .4
     std::vector<Block> blocks;
-    act_blocks(sm.sun_y[j - 1], kHalf, blocks);
-    std::vector<ColRange> cols = {col(0, 0, kHalf, W(SPNERF_P_SUN0_W + 2 * j), kHalf, 0, W(SPNERF_P_SUN0_W + 2 * j + 1), kHalf)};
-    add_group(pl, {{1, gm.G_sun[j], kHalf}}, blocks, cols, groups, true);
+    act_blocks(sm.sun_y[j - 1], H, blocks);
+    std::vector<ColRange> cols = {col(0, 0, H, W(SPNERF_P_SUN0_W + 2 * j), H, 0, W(SPNERF_P_SUN0_W + 2 * j + 1), H)};
+    add_group(pl, {{1, gm.G_sun[j], H}}, blocks, cols, groups, true);
   }
   // tiny last layers: rows = hidden activations, columns = the small-gradient tile
   // [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8)]
   auto small_head = [&](int unit, int c0, int ncols, float* w2) {
     std::vector<Block> blocks;
-    act_blocks(unit, kHalf, blocks);
+    act_blocks(unit, H, blocks);
     std::vector<ColRange> cols;
-    for (int k = 0; k < ncols; ++k) cols.push_back(col(0, c0 + k, 1, w2 ? w2 + (size_t)k * kHalf : nullptr, 0, 0, nullptr, kHalf));
+    for (int k = 0; k < ncols; ++k) cols.push_back(col(0, c0 + k, 1, w2 ? w2 + (size_t)k * H : nullptr, 0, 0, nullptr, H));
     add_group(pl, {{1, gm.gsmall, 16}}, blocks, cols, groups);
   };
   small_head(sm.rgb_y, 0, 3, W(SPNERF_P_RGB2_W));
@@ -783,7 +791,7 @@ extern "C" int64_t spnerf_mlp_wgrad_workspace_bytes(const SpnerfNetConfig* cfg) 
 // gradient pointers, workspace); synchronises the stream (the tables come from pageable memory).
 extern "C" int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* a, void* stream_) {
   if (!a || !a->grads_host || !a->workspace) return SPNERF_ERR_BAD_ARG;
-  if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (!feat_supported(a->cfg.feat) || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Plan pl = make_plan(a->cfg, a->grads_host, n_sms() / 2);
   const size_t tb = table_bytes(pl);
@@ -808,9 +816,10 @@ extern "C" int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* a, void* stream_) 
       add(SPNERF_P_SEM2_B, SPNERF_ACC_SMALL_BIAS + 6, a->cfg.num_sem_classes);
       add(SPNERF_P_SEM_EMB, SPNERF_ACC_EMB, (a->cfg.num_sem_classes + 1) * a->cfg.emb_dim);
     }
-    add(SPNERF_P_SKY0_W, SPNERF_ACC_SKY_W0, 3 * kHalf);
-    add(SPNERF_P_SKY0_B, SPNERF_ACC_SKY_B0, kHalf);
-    add(SPNERF_P_SKY2_W, SPNERF_ACC_SKY_W2, 3 * kHalf);
+    const int nh = a->cfg.feat / 2;
+    add(SPNERF_P_SKY0_W, SPNERF_ACC_SKY_W0, 3 * nh);
+    add(SPNERF_P_SKY0_B, SPNERF_ACC_SKY_B0, nh);
+    add(SPNERF_P_SKY2_W, SPNERF_ACC_SKY_W2, 3 * nh);
     add(SPNERF_P_SKY2_B, SPNERF_ACC_SKY_B2, 3);
     ft.progress = reinterpret_cast<int*>(static_cast<uint8_t*>(a->workspace) + (size_t)pl.ws_floats * 4 + kTableRoom);
     ft.n_progress = pl.n_launch * 2;
@@ -823,7 +832,7 @@ extern "C" int spnerf_mlp_wgrad_prepare(const SpnerfMlpWgrad* a, void* stream_) 
 
 extern "C" int spnerf_mlp_bwd_weights(const SpnerfMlpWgrad* a, void* stream_) {
   if (!a || !a->saves || !a->grad_saves || !a->scale || !a->grads_host || !a->workspace) return SPNERF_ERR_BAD_ARG;
-  if (a->cfg.feat != 512 || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
+  if (!feat_supported(a->cfg.feat) || a->cfg.layers != 8 || a->cfg.skip_layer != 4) return SPNERF_ERR_UNSUPPORTED;
   if (a->n_points <= 0) return a->n_points == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int pairs = n_sms() / 2;

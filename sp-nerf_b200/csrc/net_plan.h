@@ -33,8 +33,11 @@ static_assert(kSmemTotal <= 232448, "shared memory budget");
 // fp32 block mirrored into the parameter region at kernel start (floats): rgb2 | sem2 | sun6 | beta2
 constexpr int kSmallWFloats = 1024 + 2048 + 256 + 256;
 
-constexpr int kFeat = 512;
-constexpr int kHalf = 256;
+constexpr int kFeat = 512;           // widest trunk the shared-memory / tensor-memory map is sized for
+constexpr int kHalf = 256;           // ... and its head width; a configuration's own widths are cfg.feat and cfg.feat / 2
+// trunk widths the kernels are instantiated for: 512 (modules/opt.py:44 default) and 256 (the SPNeRF class default,
+// models/spnerf.py:163); everything below is parameterised by cfg.feat
+inline bool feat_supported(int feat) { return feat == 512 || feat == 256; }
 constexpr int kMaxSteps = 384;
 constexpr int kAuxSlab = 255;        // MmaStep::a_slab value naming the aux operand
 
@@ -92,10 +95,10 @@ struct SmallOffsets {
 struct SaveMap {
   int inp;         // encoded input (hi)                          1 unit
   int aux;         // [1, sun_dir(3), t_emb(t_dim), 0...]          1 unit (16 columns used)
-  int y[8];        // post-activation of trunk layer i            8 units each
+  int y[8];        // post-activation of trunk layer i            feat / 64 units each (8 at 512)
   int x[8];        // sign bits of cos(sine argument), layer i    1 unit each
-  int f;           // feats_from_xyz output                       8 units
-  int sem_x, sem_y, rgb_x, rgb_y, beta_x, beta_y;   // *_y: 4 units, *_x (sign bits): 1 unit (-1 if absent)
+  int f;           // feats_from_xyz output                       feat / 64 units
+  int sem_x, sem_y, rgb_x, rgb_y, beta_x, beta_y;   // *_y: feat / 128 units, *_x (sign bits): 1 unit (-1 if absent)
   int sun_x[3], sun_y[3];
   int total;
 };
@@ -103,9 +106,9 @@ struct SaveMap {
 // Per-tile gradient save area written by the backward-data kernel, in slabs: every entry is a
 // pre-activation gradient tile (fp16, scaled), the A operand of one weight-gradient GEMM.
 struct GradMap {
-  int G[8];        // trunk layers                         8 slabs each
-  int g_f;         // feats_from_xyz output gradient       8 slabs
-  int G_sem, G_rgb, G_beta;   // 256-wide hidden layers    4 slabs each (-1 if absent)
+  int G[8];        // trunk layers                         feat / 64 slabs each
+  int g_f;         // feats_from_xyz output gradient       feat / 64 slabs
+  int G_sem, G_rgb, G_beta;   // hidden layers of the heads feat / 128 slabs each (-1 if absent)
   int G_sun[3];
   int gsmall;      // [g_u(3), g_v, g_sigma_pre, g_beta_pre, 0, 0, g_logit(8), 0...]   1 slab
   int total;
@@ -151,11 +154,12 @@ inline AuxExtra make_aux_extra(const SpnerfNetConfig& c) {
 inline SaveMap make_save_map(const SpnerfNetConfig& c) {
   SaveMap m;
   int s = 0;
+  const int wide = c.feat / 64, narrow = c.feat / 128;      // units of a trunk-wide / head-wide activation
   m.inp = s++;
   m.aux = s++;
-  for (int i = 0; i < 8; ++i) { m.y[i] = s; s += 8; m.x[i] = s; s += 1; }
-  m.f = s; s += 8;
-  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += 4; return r; };
+  for (int i = 0; i < 8; ++i) { m.y[i] = s; s += wide; m.x[i] = s; s += 1; }
+  m.f = s; s += wide;
+  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += narrow; return r; };
   auto one = [&](bool on) { int r = on ? s : -1; if (on) s += 1; return r; };
   m.sem_x = one(c.sem); m.sem_y = four(c.sem);
   m.rgb_x = one(true); m.rgb_y = four(true);
@@ -168,9 +172,10 @@ inline SaveMap make_save_map(const SpnerfNetConfig& c) {
 inline GradMap make_grad_map(const SpnerfNetConfig& c) {
   GradMap m;
   int s = 0;
-  for (int i = 0; i < 8; ++i) { m.G[i] = s; s += 8; }
-  m.g_f = s; s += 8;
-  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += 4; return r; };
+  const int wide = c.feat / 64, narrow = c.feat / 128;
+  for (int i = 0; i < 8; ++i) { m.G[i] = s; s += wide; }
+  m.g_f = s; s += wide;
+  auto four = [&](bool on) { int r = on ? s : -1; if (on) s += narrow; return r; };
   m.G_sem = four(c.sem); m.G_rgb = four(true); m.G_beta = four(c.beta);
   for (int i = 0; i < 3; ++i) m.G_sun[i] = four(true);
   m.gsmall = s++;
@@ -182,6 +187,8 @@ inline SmallOffsets make_small_offsets(const SpnerfNetConfig& c) {
   SmallOffsets o;
   int s = 0;
   auto take = [&](int n) { int r = s; s += (n + 3) & ~3; return r; };   // keep float4 alignment
+  // sized for the widest configuration whatever cfg.feat is: the offsets are compile-time facts of the kernels'
+  // parameter structs, only the first feat (feat / 2) entries of a block are used by a narrower network
   for (int i = 0; i < 8; ++i) o.fc_b[i] = take(kFeat);
   o.sigma_b = take(1);
   o.feats_b = take(kFeat);

@@ -301,7 +301,8 @@ class NetEngine:
             beta=1 if module.beta else 0, t_dim=module.t_embedding_dims)
         self.sizes = _cabi.NetSizes()
         _cabi.check(_cabi.lib().spnerf_net_sizes(ctypes.byref(self.cfg), ctypes.byref(self.sizes)),
-                    "spnerf_net_sizes (only fc_units=512, fc_layers=8, skip 4, encoded input <= 64 are built)")
+                    "spnerf_net_sizes (built: fc_units 512 or 256, fc_layers 8, skip 4, <= 8 classes, encoded input up to 64 "
+                    "columns plus what fits the free aux columns: --mapping with <= 7 classes, <= 6 with --beta)")
         self.n_out = self.sizes.n_out
         self.col_sem = 8 + (1 if module.beta else 0) if module.sem else -1
         self.n_sem = module.num_sem_classes if module.sem else 0
@@ -374,7 +375,7 @@ class NetEngine:
     def sky(self, rays):
         n = rays.shape[0]
         sky = torch.empty(n, 3, dtype=torch.float32, device=rays.device)
-        hidden = torch.empty(n, 256, dtype=torch.float32, device=rays.device)
+        hidden = torch.empty(n, self.cfg.feat // 2, dtype=torch.float32, device=rays.device)
         _cabi.check(_cabi.lib().spnerf_sky_fwd(_p(self.small), ctypes.byref(self.cfg), _p(rays), n, _p(sky),
                                                _p(hidden), _stream()), "spnerf_sky_fwd")
         return sky, hidden

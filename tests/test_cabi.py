@@ -47,7 +47,7 @@ def test_plan_sizes_host_only():
     assert lib.spnerf_mlp_wgrad_workspace_bytes(ctypes.byref(cfg)) > 0
 
 
-@pytest.mark.parametrize("kw", [dict(feat=256), dict(layers=6), dict(skip_layer=3), dict(num_sem_classes=9, emb_dim=9),
+@pytest.mark.parametrize("kw", [dict(feat=128), dict(feat=384), dict(layers=6), dict(skip_layer=3), dict(num_sem_classes=9, emb_dim=9),
                                 dict(mapping=1, num_sem_classes=8, emb_dim=8),
                                 dict(mapping=1, num_sem_classes=6, emb_dim=6, beta=1, t_dim=8)])
 def test_unsupported_configurations_are_refused(kw):
@@ -67,6 +67,18 @@ def test_encoded_input_wider_than_the_slab_is_planned():
         s = _cabi.NetSizes()
         assert lib.spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 0
         assert s.in_dim == 60 + c and s.n_out == 8 + beta + c
+
+
+def test_class_default_width_is_planned():
+    """feat = 256 (the SPNeRF class default, models/spnerf.py:163): half of every tile."""
+    lib = _cabi.lib()
+    small, big = _cabi.NetSizes(), _cabi.NetSizes()
+    for feat, s in ((256, small), (512, big)):
+        cfg = _cabi.NetConfig(feat=feat, layers=8, skip_layer=4, mapping=1, sem=1, num_sem_classes=3, emb_dim=3, beta=0, t_dim=4)
+        assert lib.spnerf_net_sizes(ctypes.byref(cfg), ctypes.byref(s)) == 0
+    assert small.n_out == big.n_out == 11
+    assert small.save_slabs_per_tile < big.save_slabs_per_tile and small.grad_slabs_per_tile < big.grad_slabs_per_tile
+    assert 0.2 < small.fwd_blob_bytes / big.fwd_blob_bytes < 0.35          # ~4x fewer weights in the trunk
 
 
 def test_bad_arguments_are_refused_without_a_device():
@@ -90,7 +102,8 @@ def _step_table(cfg, backward):
 
 
 @pytest.mark.parametrize("kw", [dict(mapping=0, sem=1), dict(mapping=1, sem=1), dict(mapping=0, sem=0),
-                                dict(mapping=1, sem=1, beta=1)])
+                                dict(mapping=1, sem=1, beta=1), dict(feat=256, mapping=1, sem=1),
+                                dict(feat=256, mapping=0, sem=1, beta=1), dict(mapping=1, sem=1, num_sem_classes=5, emb_dim=5)])
 @pytest.mark.parametrize("backward", [0, 1])
 def test_step_table_keeps_accumulation_order_deterministic(kw, backward):
     """The two MMA issuer warps must never accumulate into the same accumulator columns inside a phase: the

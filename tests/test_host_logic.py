@@ -33,11 +33,12 @@ def test_seeded_init_reproduces_reference_weights(name):
     assert state_hash(model.state_dict()) == meta["state_sha256"]
 
 
-def test_class_default_width_constructs_but_is_not_built():
+def test_class_default_width_is_built_and_odd_widths_are_refused():
     m = SPNeRF()                      # feat=256 (models/spnerf.py:163)
     assert m.fc_net[0].weight.shape == (256, 3)
+    assert m.engine.sizes.n_out == 8 and m.engine.cfg.feat == 256
     with pytest.raises(_cabi.SpnerfError):
-        m.engine
+        SPNeRF(feat=384).engine
 
 
 def test_no_cpu_fallback():

@@ -760,3 +760,76 @@ def test_device_side_uniforms_of_the_coarse_sampler():
     assert abs(float(torch.corrcoef(torch.stack([u[:, :-1].reshape(-1), u[:, 1:].reshape(-1)]))[0, 1])) < 1e-2
     u2 = ((z2 - lo) / (hi - lo).clamp_min(1e-12))[:, 1:-1]
     assert abs(float(torch.corrcoef(torch.stack([u.reshape(-1), u2.reshape(-1)]))[0, 1])) < 1e-2
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(mapping=True), dict(mapping=True, num_sem_classes=5, beta=True, sc_lambda=0.05),
+                                dict(sem=False, guidedsample=True)])
+def test_class_default_width_forward_and_gradients(kw):
+    """fc_units = 256 (the SPNeRF class default, models/spnerf.py:163): every tile is half as wide (4 activation slabs,
+    128-wide heads, 64 / 32 accumulator columns per epilogue column group, one weight-gradient job per layer).
+    render_rays outputs, losses and every parameter gradient against the oracle on the same draws."""
+    base = dict(sem=True, num_sem_classes=3, fc_units=256, n_samples=64)
+    base.update(kw)
+    cfg = O.make_cfg(**base)
+    args = types.SimpleNamespace(**vars(cfg))
+    torch.manual_seed(0)
+    model = load_model(args)
+    t_mod = torch.nn.Embedding(30, cfg.t_embbeding_tau) if cfg.beta else None
+    with torch.no_grad():
+        model.sigma_from_xyz[0].bias.fill_(3.0)
+        model.sigma_from_xyz[0].weight.mul_(4.0)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    t_table = t_mod.weight.detach().clone().requires_grad_(True) if cfg.beta else None
+    model = model.to(DEV)
+    b, n = 200, cfg.n_samples                                  # 100 tiles: an even number of pairs, ragged last ray tile
+    batch = synthetic.make_batch(b, seed=17)
+    gen = torch.Generator().manual_seed(18)
+    if cfg.sem:
+        batch["sems"] = torch.randint(0, cfg.num_sem_classes, (b,), generator=gen)
+        batch["sems"][::13] = -100
+    n_valid = int((batch["valid_depth"] > 0).sum())
+    uni, nor = [torch.rand(b, n, generator=gen)], [torch.randn(b, n, generator=gen)]
+    if cfg.guidedsample:
+        uni += [torch.rand(b, n, generator=gen), torch.rand(n_valid, n, generator=gen)]
+        nor += [torch.randn(b, 2 * n, generator=gen)]
+    if cfg.sc_lambda > 0:
+        nor += [torch.randn(b, n, generator=gen)]
+    sems = batch["sems"] if cfg.sem else None
+    ts = batch["ts"] if cfg.beta else None
+    want = O.render(P, cfg, batch["rays"], ts, sems, "train", batch["valid_depth"], batch["depths"], batch["depth_std"],
+                    O.Draws([u.clone() for u in uni], [x.clone() for x in nor]), t_table=t_table)
+    want_loss = O.colour_loss(want, batch["rgbs"], cfg.sc_lambda, cfg.beta)[0] + O.depth_loss(
+        want, batch["depths"][:, 0], batch["depths"][:, 1], batch["valid_depth"], batch["depth_std"], 1.0, False)[0]
+    if cfg.sem:
+        want_loss = want_loss + O.semantic_loss(want, sems, 1.0)[0]
+    leaves = list(P.values()) + ([t_table] if cfg.beta else [])
+    want_grads = torch.autograd.grad(want_loss, leaves, allow_unused=True)
+    d = {k: v.to(DEV) for k, v in batch.items()}
+    args._rng = O.Draws([u.to(DEV) for u in uni], [x.to(DEV) for x in nor])
+    models = {"coarse": model}
+    if cfg.beta:
+        models["t"] = t_mod.to(DEV)
+    got = render_rays(models, args, d["rays"], d["ts"] if cfg.beta else None, semantics=d["sems"] if cfg.sem else None,
+                      mode="train", valid_depth=d["valid_depth"], target_depths=d["depths"], target_std=d["depth_std"])
+    assert sorted(got) == sorted(want)
+    for key, w in want.items():
+        base_key = key[:-len("_coarse")]
+        if base_key.startswith("z_vals"):
+            assert float((got[key].cpu() - w).abs().max()) <= (5e-4 if cfg.guidedsample else 0.0), key
+            continue
+        assert float((got[key].detach().cpu() - w.detach()).abs().max()) <= TOL[base_key.replace("_sc", "")], key
+    loss = metrics.load_loss(args)(got, d["rgbs"])[0] + metrics.DepthLoss(1.0, usealldepth=False)(
+        got, d["depths"][:, 0], d["depths"][:, 1], target_valid_depth=d["valid_depth"], target_std=d["depth_std"])[0]
+    if cfg.sem:
+        loss = loss + metrics.SemanticLoss(1.0)(got, d["sems"])[0]
+    params = list(model.parameters()) + ([models["t"].weight] if cfg.beta else [])
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    assert abs(float(loss) - float(want_loss)) <= 2e-3 * abs(float(want_loss))
+    names = [k for k, _ in model.named_parameters()] + (["t_table"] if cfg.beta else [])
+    top = max(float(w.norm()) for w in want_grads if w is not None)
+    for name, a, w in zip(names, grads, want_grads):
+        if w is None or float(w.norm()) < 1e-3 * top:
+            continue
+        assert a is not None, name
+        rel = float((a.cpu() - w).norm() / w.norm())
+        assert rel <= 2e-2, (name, rel)

@@ -1,4 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2_a.json 2> gpurun_out/bench_r2_a.err; tail -c 3000 gpurun_out/bench_r2_a.err; cat gpurun_out/bench_r2_a.json | cut -c1-6000
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 900 python bench.py --steps 20 --warmup 3 --skip-extra > gpurun_out/bench_r2_b.json 2> gpurun_out/bench_r2_b.err; tail -c 500 gpurun_out/bench_r2_b.err; python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_r2_b.json"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels_ms"], d["roofline"]["frac"], d["small_batch"])
+PY
