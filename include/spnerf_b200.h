@@ -78,15 +78,16 @@ void spnerf_debug_phase_clocks_bwd(long long* dev_buf2048);
  * models/spnerf.py:83-113, i.e. the chunked per-point MLP call of inference()).
  * ------------------------------------------------------------------------------------------- */
 typedef struct SpnerfNetConfig {
-  int32_t feat;            /* fc_units; only 512 is built (modules/opt.py:43)                 */
+  int32_t feat;            /* fc_units: 512 (modules/opt.py:43) or 256 (the class default)    */
   int32_t layers;          /* fc_layers; only 8 (modules/opt.py:45)                           */
   int32_t skip_layer;      /* 4 (models/spnerf.py:164 skips=[4])                              */
   int32_t mapping;         /* 1: 10-frequency positional encoding (models/spnerf.py:5-37)     */
   int32_t sem;             /* 1: label embedding input + semantic head                        */
   int32_t num_sem_classes; /* C <= 8                                                          */
-  int32_t emb_dim;         /* C * s_embedding_factor; encoded input width must stay <= 64     */
+  int32_t emb_dim;         /* C * s_embedding_factor; encoded input beyond 64 columns rides in free aux columns */
   int32_t beta;            /* 1: uncertainty head                                             */
   int32_t t_dim;           /* t_embbeding_tau <= 8                                            */
+  int32_t relu;            /* 0: SIREN activations (siren=True, what load_model builds); 1: ReLU (models/spnerf.py:178) */
 } SpnerfNetConfig;
 
 /* Parameter slots, in the reference's state_dict order. */

@@ -102,6 +102,9 @@ CASES = {
     "beta_512": dict(B=64, mode="train", seed=16, trained_like=True,
                      cfg=dict(sem=True, num_sem_classes=3, fc_units=512, beta=True, mapping=True, sc_lambda=0.05,
                               t_embbeding_tau=4)),
+    # ReLU variant of the network (models/spnerf.py:178 `nl`): not reachable through load_model, built from the class
+    "relu_512": dict(B=64, mode="train", seed=17, siren=False,
+                     cfg=dict(sem=True, num_sem_classes=3, fc_units=512, mapping=True, siren=False)),
 }
 # parameters whose FULL gradient is stored whatever their size (two trunk-sized matrices; the rest of the
 # large ones are pinned by norm + a random probe)
@@ -121,7 +124,12 @@ def run_case(name, spec, ref_models, ref_rendering, ref_metrics):
     n_valid = int((batch["valid_depth"] > 0).sum())
 
     torch.manual_seed(0)
-    ref_model = ref_models.load_model(args)
+    if spec.get("siren", True):
+        ref_model = ref_models.load_model(args)
+    else:
+        ref_model = ref_models.SPNeRF(num_sem_classes=args.num_sem_classes, s_embedding_factor=args.s_embedding_factor,
+                                      layers=args.fc_layers, feat=args.fc_units, mapping=args.mapping,
+                                      t_embedding_dims=args.t_embbeding_tau, beta=args.beta, sem=args.sem, siren=False)
     t_table = None
     models = {"coarse": ref_model}
     if cfg.beta:

@@ -29,7 +29,7 @@ def make_cfg(**kw):
     d = dict(n_samples=64, n_importance=0, model="sp-nerf", beta=False, guidedsample=False, sc_lambda=0.0,
              margin=1e-4, stdscale=1.0, chunk=5120, noise_std=0.0, num_sem_classes=3, s_embedding_factor=1,
              fc_layers=8, fc_units=512, mapping=False, t_embbeding_tau=4, sem=False, mapping_freqs=10,
-             skips=(4,))
+             skips=(4,), siren=True)
     d.update(kw)
     return SimpleNamespace(**d)
 
@@ -82,30 +82,34 @@ def point_network(P, cfg, xyz, sun_d, labels=None, t_emb=None):
         x_in = torch.cat((enc, emb), dim=1)
     else:
         x_in = enc
+    siren = getattr(cfg, "siren", True)
+    # `nl` of models/spnerf.py:178: Siren (sin(w0 x), w0 = 1) or ReLU for every hidden activation; with siren the
+    # first trunk layer is Siren(w0=30) (:202)
+    nl = torch.sin if siren else torch.relu
     h = x_in
     for i in range(cfg.fc_layers):                                                      # :325-329
         if i in cfg.skips:
             h = torch.cat([h, x_in], -1)
         h = _lin(P, f"fc_net.{2 * i}", h)
-        h = torch.sin((30.0 if i == 0 else 1.0) * h)                                    # :40-46, :202
+        h = torch.sin((30.0 if i == 0 else 1.0) * h) if siren else torch.relu(h)        # :40-46, :202
     sigma = F.softplus(_lin(P, "sigma_from_xyz.0", h))                                  # :333
     feats = _lin(P, "feats_from_xyz", h)                                                # :338
-    rgb = torch.sigmoid(_lin(P, "rgb_from_xyzdir.2", torch.sin(_lin(P, "rgb_from_xyzdir.0", feats))))
+    rgb = torch.sigmoid(_lin(P, "rgb_from_xyzdir.2", nl(_lin(P, "rgb_from_xyzdir.0", feats))))
     rgb = rgb * (1 + 2 * 0.001) - 0.001                                                 # :346-347
     out = torch.cat([rgb, sigma], 1)
     s = torch.cat([feats, sun_d], -1)                                                   # :351-352
-    s = torch.sin(_lin(P, "sun_v_net.0", s))
-    s = torch.sin(_lin(P, "sun_v_net.2", s))
-    s = torch.sin(_lin(P, "sun_v_net.4", s))
+    s = nl(_lin(P, "sun_v_net.0", s))
+    s = nl(_lin(P, "sun_v_net.2", s))
+    s = nl(_lin(P, "sun_v_net.4", s))
     sun_v = torch.sigmoid(_lin(P, "sun_v_net.6", s))
     sky = torch.sigmoid(_lin(P, "sky_color.2", torch.relu(_lin(P, "sky_color.0", sun_d))))  # :355
     out = torch.cat([out, sun_v, sky], 1)
     if cfg.beta:                                                                        # :359-362
         b = torch.cat([feats, t_emb], -1)
-        b = F.softplus(_lin(P, "beta_from_xyz.2", torch.sin(_lin(P, "beta_from_xyz.0", b))))
+        b = F.softplus(_lin(P, "beta_from_xyz.2", nl(_lin(P, "beta_from_xyz.0", b))))
         out = torch.cat([out, b], 1)
     if cfg.sem:                                                                         # :365-367
-        lg = _lin(P, "logit_from_label.2", torch.sin(_lin(P, "logit_from_label.0", h)))
+        lg = _lin(P, "logit_from_label.2", nl(_lin(P, "logit_from_label.0", h)))
         out = torch.cat([out, lg], 1)
     return out
 

@@ -92,7 +92,7 @@ for _j in range(4):
 
 class NetConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("feat", "layers", "skip_layer", "mapping", "sem", "num_sem_classes", "emb_dim", "beta", "t_dim")]
+                ("feat", "layers", "skip_layer", "mapping", "sem", "num_sem_classes", "emb_dim", "beta", "t_dim", "relu")]
 
 
 class NetSizes(ctypes.Structure):

@@ -55,7 +55,10 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 // derivative of a sine layer from its saved output: |cos| = sqrt(1 - y^2), sign from the saved bit
+// RELU: the activation was max(x, 0) and the saved bit is x > 0: the derivative is the bit itself
+template <bool RELU = false>
 __device__ __forceinline__ float dsin(float y, uint32_t sb, int k) {
+  if (RELU) return (float)((sb >> k) & 1u);
   float c;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(__saturatef(fmaf(-y, y, 1.f))));     // one MUFU
   return __uint_as_float(__float_as_uint(c) ^ ((sb >> k) << 31));
@@ -93,6 +96,7 @@ __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, cons
 
 // G[j] = acc[j] * dact(j) for columns [j0, j0 + 16 NB) of a chunk at TMEM address taddr;
 // MODE 0: dact = cos(x) rebuilt from (ysave, ssave)     MODE 1: dact = 30 cos(30 x), same     MODE 2: dact = 1
+// MODE 4: dact = [x > 0] (ReLU network; the saved outputs are loaded like the sine layers' but only the bits matter)
 // result -> fp16 -> shared slab at column dst_col0 + j (copied to the gradient save area afterwards)
 // `win`: batches j0 .. j0 + 16 kYWin, loaded by the caller before it waited for the accumulator
 template <int MODE, int NB>
@@ -120,8 +124,8 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
           unpack8(cur.y[c], y);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float d = dsin(y[e], cur.sb, c * 8 + e);
-            g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 0 ? d : 30.f * d);
+            const float d = dsin<MODE == 4>(y[e], cur.sb, c * 8 + e);
+            g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 1 ? 30.f * d : d);
           }
         } else {
 #pragma unroll
@@ -138,7 +142,7 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
 // Gradient entering a 256-wide hidden layer from its tiny output layer (CUDA cores):
 //   G[j] = coefw(j) * cos(x[j])   for j in [j0, j0+ncols),  coefw(j) = sum_c g_c * W2[c][j] from shared memory
 // `each(j, G)` lets the caller fold further per-row reductions (t_emb gradient).
-template <class CoefW, class Each>
+template <bool RELU, class CoefW, class Each>
 __device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, const uint8_t* ysave, const uint8_t* ssave,
                                             uint8_t* act, int dst_col0, int row, Each each) {
   // 16-column batches, the next one requested before the current one is used (the saved activations come
@@ -154,7 +158,7 @@ __device__ __forceinline__ void gen_columns(CoefW coefw, int j0, int ncols, cons
       unpack8(cur.y[c], y);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        g[e] = coefw(jb + c * 8 + e) * dsin(y[e], cur.sb, c * 8 + e);
+        g[e] = coefw(jb + c * 8 + e) * dsin<RELU>(y[e], cur.sb, c * 8 + e);
         each(jb + c * 8 + e, g[e]);
       }
       *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) =
@@ -171,7 +175,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // FEAT: trunk width (512 or 256); column-group widths as in mlp_fwd.cu
-template <int FEAT>
+template <int FEAT, bool RELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ BwdParams p) {
   constexpr int H = FEAT / 2, QW = FEAT / 4, HW = FEAT / 8;
   constexpr int NBQ = QW / 16, NBH = HW / 16;      // 16-column batches per column group: trunk layer / head hidden layer
@@ -308,7 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       // ---- E_in: G_s3 = g_v * W_sun6 * cos(x_s3) -> slabs 0..3 ----
       {
         const float cv = g_v * scale;
-        gen_columns([&](int j) { return cv * Wsun6[j]; }, cg * HW, HW, xs(p.sm.sun_y[2]), xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
+        gen_columns<RELU>([&](int j) { return cv * Wsun6[j]; }, cg * HW, HW, xs(p.sm.sun_y[2]), xs(p.sm.sun_x[2]), act, 0, row, NoEachG());
       }
       sync.end(true);
       copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[2]));
@@ -316,16 +320,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       YWindow win;
       ywin_load<NBH>(win, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), cg * HW, row);
       sync.begin();
-      bwd_columns<0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
+      bwd_columns<RELU ? 4 : 0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
       sync.end(true);
       copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[1]));
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
       ywin_load<NBH>(win, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), cg * HW, row);
       sync.begin();
-      bwd_columns<0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
+      bwd_columns<RELU ? 4 : 0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
       {
         const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
-        gen_columns([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * HW, HW,
+        gen_columns<RELU>([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * HW, HW,
                     xs(p.sm.rgb_y), xs(p.sm.rgb_x), act, H, row, NoEachG());
       }
       sync.end(true);
@@ -339,7 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         for (int e = 0; e < 8; ++e) tacc[e] = 0.f;
         const float cb = g_bp * scale;
         const float* wt = S + p.so.beta0_wt;
-        gen_columns([&](int j) { return cb * Wbeta2[j]; }, cg * HW, HW, xs(p.sm.beta_y), xs(p.sm.beta_x), act, 0, row,
+        gen_columns<RELU>([&](int j) { return cb * Wbeta2[j]; }, cg * HW, HW, xs(p.sm.beta_y), xs(p.sm.beta_x), act, 0, row,
                     [&](int j, float g) {
 #pragma unroll
                       for (int e = 0; e < 8; ++e) tacc[e] = fmaf(g, __ldg(wt + e * H + j), tacc[e]);
@@ -361,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) cf[c] = g_lg[c] * scale;
         const bool wide = p.n_classes > 4;
-        gen_columns([&](int j) {
+        gen_columns<RELU>([&](int j) {
           const float4 w = Wsem2[j * 2];
           float a = fmaf(cf[0], w.x, fmaf(cf[1], w.y, fmaf(cf[2], w.z, cf[3] * w.w)));
           if (wide) {
@@ -410,8 +414,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         else if (dbg & 4096) bwd_columns<2, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
         else
 #endif
-        if (L > 0) bwd_columns<0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else       bwd_columns<1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
+        if (L > 0) bwd_columns<RELU ? 4 : 0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+        else       bwd_columns<RELU ? 4 : 1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
         sync.end(more);
 #ifdef SPNERF_EXPERIMENTS
@@ -476,7 +480,8 @@ extern "C" int spnerf_mlp_bwd_data(const SpnerfMlpBwd* a, void* stream) {
   p.debug = a->debug_flags;
   p.prof = g_prof_bwd;
   host_stagger(p.stagger, p.stagger_groups);
-  void (*kern)(const BwdParams) = a->cfg.feat == 512 ? mlp_bwd_kernel<512> : mlp_bwd_kernel<256>;
+  void (*kern)(const BwdParams) = a->cfg.feat == 512 ? (a->cfg.relu ? mlp_bwd_kernel<512, true> : mlp_bwd_kernel<512, false>)
+                                                     : (a->cfg.relu ? mlp_bwd_kernel<256, true> : mlp_bwd_kernel<256, false>);
   if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -37,6 +37,7 @@ struct FwdParams {
 // 32 accumulator columns [j0, j0+32) of one chunk (column 0 of the chunk at TMEM address `taddr`)
 // for this thread's row:  y = ACT(acc) ; y -> fp16 -> shared slab(s) at column dst_col0 + j
 // ACT 0: y = sin(x)      ACT 1: y = sin(30 x)  (first layer, Siren w0 = 30)      ACT 2: y = x  (feats_from_xyz)
+// ACT 3: y = max(x, 0)   (the ReLU variant of the network, models/spnerf.py:178; the saved bit is x > 0)
 // ssave: sign of the derivative cos(argument), one bit per column (the backward rebuilds
 //        |cos| = sqrt(1 - y^2)); the sign is the parity of rint(argument / pi), read off the mantissa
 //        LSB after adding 1.5 * 2^23
@@ -64,7 +65,10 @@ __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, 
     for (int e = 0; e < 8; ++e) {
       const float x = __uint_as_float(v[c * 8 + e]);
       if (ACT == 2) y[e] = x;
-      else {
+      else if (ACT == 3) {
+        y[e] = fmaxf(x, 0.f);
+        if (BITS) sb = __funnelshift_r(sb, x > 0.f ? 1u : 0u, 1);
+      } else {
         const float a = (ACT == 1) ? 30.f * x : x;
         y[e] = __sinf(a);
         if (BITS) sb = __funnelshift_r(sb, __float_as_uint(fmaf(a, 0.318309886f, 12582912.f)), 1);   // bit (c*8+e) <- parity
@@ -100,9 +104,10 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf
 
 // FEAT: trunk width (512 or 256).  The tile geometry follows from it: a column group of the epilogue owns FEAT / 4
 // accumulator columns of a trunk layer and FEAT / 8 of a head's hidden layer (FEAT / 2 wide).
-template <int FEAT>
+template <int FEAT, bool RELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   constexpr int H = FEAT / 2, QW = FEAT / 4, HW = FEAT / 8;
+  constexpr int A0 = RELU ? 3 : 1, AH = RELU ? 3 : 0;      // activation of the first trunk layer / of every other hidden layer
   extern __shared__ __align__(1024) uint8_t smem[];
   // timing-experiment toggles and the phase clock log exist only in SPNERF_EXPERIMENTS builds (tools/build_variant.sh)
 #ifdef SPNERF_EXPERIMENTS
@@ -257,14 +262,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // of shared memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy
       // competes with the MMAs for shared-memory bandwidth.  debug & 128 selects that variant.)
       const bool direct_all = !(dbg & 128);
-      epi_cols<1, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[0]),
+      epi_cols<A0, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[0]),
                         (cg < 2 || direct_all) ? sv(p.sm.y[0]) : nullptr, NoEach());
       sync.end(true);
       if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[0] + FEAT / 128));
       // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[i]),
+        epi_cols<AH, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[i]),
                           (cg < 2 || direct_all) ? sv(p.sm.y[i]) : nullptr, NoEach());
         sync.end(true);
         if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[i] + FEAT / 128));
@@ -283,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
 #pragma unroll
         for (int c = 0; c < 8; ++c) lg[c] = 0.f;
         const bool wide = p.n_classes > 4;
-        epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, (dbg & 32) ? nullptr : sv(p.sm.sem_x),
+        epi_cols<AH, false, 16>(taddr, cg * HW, HW, act, 0, row, (dbg & 32) ? nullptr : sv(p.sm.sem_x),
                            (dbg & 16) ? nullptr : sv(p.sm.sem_y), [&](int j, float y) {
           const float4 w = Wsem2[j * 2];
           lg[0] = fmaf(w.x, y, lg[0]); lg[1] = fmaf(w.y, y, lg[1]); lg[2] = fmaf(w.z, y, lg[2]); lg[3] = fmaf(w.w, y, lg[3]);
@@ -315,15 +320,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         if (!p.beta) {
           // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
           // 0..3, the albedo activations to slabs 4..7 (only read back by the debug & 128 copy-out variant)
-          epi_cols<0, true, 16>(taddr, cg * HW, HW, act, H, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
-          epi_cols<0, true>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
+          epi_cols<AH, true, 16>(taddr, cg * HW, HW, act, H, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
+          epi_cols<AH, true>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
                             NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
           // feats stay live for the sun layer of the next phase: nothing may be written to the slabs
           float bsum[1] = {0.f};
-          epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
-          epi_cols<0, false, 16>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
+          epi_cols<AH, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
+          epi_cols<AH, false, 16>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.beta_x), sv(p.sm.beta_y),
                              [&](int j, float y) { bsum[0] = fmaf(Wbeta2[j], y, bsum[0]); });
           float r4[4] = {c3[0], c3[1], c3[2], bsum[0]};
           reduce_groups<4>(scratch, r4, cg, row);
@@ -337,7 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       if (p.beta) {
         sync.begin();
-        epi_cols<0, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
+        epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
         sync.end(true);
       }
       if (!direct_all) {
@@ -346,14 +351,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       }
       // ---- sun layer 1 ----
       sync.begin();
-      epi_cols<0, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
+      epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
       sync.end(true);
       if (!direct_all) copy_slabs_out(act, 0, H / 64, sv(p.sm.sun_y[1]));
       // ---- sun layer 2 + output unit (256 -> 1, sigmoid) ----
       sync.begin();
       {
         float part[1] = {0.f};
-        epi_cols<0, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
+        epi_cols<AH, false, 16>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[2]), sv(p.sm.sun_y[2]),
                            [&](int j, float y) { part[0] = fmaf(Wsun6[j], y, part[0]); });
         reduce_groups<1>(scratch, part, cg, row);
         if (cg == 0 && valid) orow[4] = sigmoid_ref(part[0] + S[p.so.sun6_b]);   // spnerf.py:352
@@ -398,7 +403,8 @@ extern "C" int spnerf_mlp_fwd(const SpnerfMlpFwd* a, void* stream) {
   p.prof = g_prof_fwd;
   host_stagger(p.stagger, p.stagger_groups);
 
-  void (*kern)(const FwdParams) = a->cfg.feat == 512 ? mlp_fwd_kernel<512> : mlp_fwd_kernel<256>;
+  void (*kern)(const FwdParams) = a->cfg.feat == 512 ? (a->cfg.relu ? mlp_fwd_kernel<512, true> : mlp_fwd_kernel<512, false>)
+                                                     : (a->cfg.relu ? mlp_fwd_kernel<256, true> : mlp_fwd_kernel<256, false>);
   if (cudaError_t e = sm100::set_max_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemTotal); e != cudaSuccess) return -(int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -298,7 +298,7 @@ class NetEngine:
             feat=module.feat, layers=module.layers, skip_layer=module.skips[0] if len(module.skips) == 1 else -1,
             mapping=1 if module.uses_mapping else 0, sem=1 if module.sem else 0,
             num_sem_classes=module.num_sem_classes, emb_dim=module.semantic_size if module.sem else 0,
-            beta=1 if module.beta else 0, t_dim=module.t_embedding_dims)
+            beta=1 if module.beta else 0, t_dim=module.t_embedding_dims, relu=0 if getattr(module, "siren", True) else 1)
         self.sizes = _cabi.NetSizes()
         _cabi.check(_cabi.lib().spnerf_net_sizes(ctypes.byref(self.cfg), ctypes.byref(self.sizes)),
                     "spnerf_net_sizes (built: fc_units 512 or 256, fc_layers 8, skip 4, <= 8 classes, encoded input up to 64 "

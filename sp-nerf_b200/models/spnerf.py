@@ -57,8 +57,7 @@ class SPNeRF(nn.Module):
     def __init__(self, num_sem_classes=3, s_embedding_factor=1, layers=8, feat=256, mapping=False,
                  mapping_sizes=[10, 4], skips=[4], siren=True, t_embedding_dims=16, beta=False, sem=False):
         super().__init__()
-        if not siren:
-            raise NotImplementedError("only the SIREN variant (siren=True, the load_model default) is built")
+        self.siren = bool(siren)
         self.layers, self.skips, self.feat = layers, list(skips), feat
         self.t_embedding_dims = t_embedding_dims
         self.input_sizes = [3, 0]
@@ -79,27 +78,31 @@ class SPNeRF(nn.Module):
                                                    padding_idx=num_sem_classes)
         self.input_size = xyz_width + self.semantic_size
         half = feat // 2
+        # `nl` of models/spnerf.py:178: every hidden activation is a sine (w0 = 1; 30 in the first trunk layer) or,
+        # with siren=False, a ReLU.  Marker modules only: the kernels apply the activation.
+        def act(w0=1.0):
+            return Sine(w0) if self.siren else nn.ReLU()
         trunk = []
         for i in range(layers):
             fan_in = self.input_size if i == 0 else feat + (self.input_size if i in self.skips else 0)
-            trunk += [nn.Linear(fan_in, feat), Sine(30.0 if i == 0 else 1.0)]
+            trunk += [nn.Linear(fan_in, feat), act(30.0 if i == 0 else 1.0)]
         self.fc_net = nn.Sequential(*trunk)
         self.sigma_from_xyz = nn.Sequential(nn.Linear(feat, 1), nn.Softplus())
         self.feats_from_xyz = nn.Linear(feat, feat)
         if sem:
-            self.logit_from_label = _mlp([feat, half, num_sem_classes], [Sine(), None])
-        self.rgb_from_xyzdir = _mlp([feat, half, 3], [Sine(), nn.Sigmoid()])
-        self.sun_v_net = _mlp([feat + 3, half, half, half, 1], [Sine(), Sine(), Sine(), nn.Sigmoid()])
+            self.logit_from_label = _mlp([feat, half, num_sem_classes], [act(), None])
+        self.rgb_from_xyzdir = _mlp([feat, half, 3], [act(), nn.Sigmoid()])
+        self.sun_v_net = _mlp([feat + 3, half, half, half, 1], [act(), act(), act(), nn.Sigmoid()])
         self.sky_color = _mlp([3, half, 3], [nn.ReLU(), nn.Sigmoid()])
         # SIREN ranges (models/spnerf.py:49-60, 251-255): all trunk / sun layers U(+-sqrt(6/fan_in)),
         # then the first layer of each U(+-1/fan_in)
-        for net in (self.fc_net, self.sun_v_net):
+        for net in (self.fc_net, self.sun_v_net) if self.siren else ():     # models/spnerf.py:251-255: only with siren
             lins = [m for m in net if isinstance(m, nn.Linear)]
             for m in lins:
                 _uniform_(m, math.sqrt(6 / m.weight.size(-1)))
             _uniform_(lins[0], 1 / lins[0].weight.size(-1))
         if beta:
-            self.beta_from_xyz = _mlp([t_embedding_dims + feat, half, 1], [Sine(), nn.Softplus()])
+            self.beta_from_xyz = _mlp([t_embedding_dims + feat, half, 1], [act(), nn.Softplus()])
         self.number_of_outputs = 8 + (1 if beta else 0) + (num_sem_classes if sem else 0)
         self._engine = None
 

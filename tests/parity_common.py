@@ -48,7 +48,13 @@ def build_model(meta, device):
     from spnerf_b200.models import load_model
     args = make_args(meta)
     torch.manual_seed(0)
-    model = load_model(args)
+    if getattr(args, "siren", True):
+        model = load_model(args)
+    else:               # the ReLU variant is only reachable through the class (load_model never passes siren)
+        from spnerf_b200.models import SPNeRF
+        model = SPNeRF(num_sem_classes=args.num_sem_classes, s_embedding_factor=args.s_embedding_factor,
+                       layers=args.fc_layers, feat=args.fc_units, mapping=args.mapping,
+                       t_embedding_dims=args.t_embbeding_tau, beta=args.beta, sem=args.sem, siren=False)
     t_table = None
     if args.beta:
         t_table = torch.nn.Embedding(30, args.t_embbeding_tau)

@@ -8,7 +8,7 @@ import torch
 from oracle import spnerf_oracle as O
 from parity_common import GOLDEN, build_model, load_case, make_args, state_hash
 
-CASES = ["c1_test_sem", "c2_train_depth_sem", "c3_train_guided_mapping_sc", "guided_test_nosem", "beta_small", "beta_512"]
+CASES = ["c1_test_sem", "c2_train_depth_sem", "c3_train_guided_mapping_sc", "guided_test_nosem", "beta_small", "beta_512", "relu_512"]
 
 
 def _params(name, g, meta):
