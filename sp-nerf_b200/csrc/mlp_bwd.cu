@@ -99,9 +99,12 @@ __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, cons
 // MODE 4: dact = [x > 0] (ReLU network; the saved outputs are loaded like the sine layers' but only the bits matter)
 // result -> fp16 -> shared slab at column dst_col0 + j (copied to the gradient save area afterwards)
 // `win`: batches j0 .. j0 + 16 kYWin, loaded by the caller before it waited for the accumulator
+// keep: (split phases) the packed fp16 gradients stay in the caller's registers (2 x uint4 per batch) instead of going
+//       to shared memory
 template <int MODE, int NB>
 __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_t* ysave, const uint8_t* ssave,
-                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave, YWindow& win, int nb_run = NB) {
+                                            uint8_t* act, int dst_col0, int row, uint8_t* gsave, YWindow& win, int nb_run = NB,
+                                            uint4* keep = nullptr) {
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     if (b < nb_run) {
@@ -132,7 +135,8 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
           for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(v[c * 8 + e]);
         }
         const uint4 gp = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
-        *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
+        if (keep) keep[2 * b + c] = gp;
+        else *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
         if (gsave) stg16(gsave + xsave_off(jb + c * 8, row), gp);
       }
     }
@@ -214,7 +218,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
     producer_loop(sh, p.blob, p.tab, n_iters, dbg, prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
     if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, dbg, prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, dbg);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab, n_iters, dbg);
   } else if (warp < 16) {
     epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;
@@ -398,30 +402,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         if (signal) sync.end(true);
       };
       for (int L = 7; L >= 0; --L) {
-#ifdef SPNERF_EXPERIMENTS
-        if (!(dbg & (1024 | 4096)))
-#endif
-        ywin_load<NBQ>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * QW, row);
-        sync.begin();
-        // three of the four column groups store their part of the gradient tile from registers, the last quarter is
+        // three of the four column groups store their part of the gradient tile from registers, the last one's is
         // copied out of shared memory during the next MMAs (alternating A/B on one box: 2 groups 4.68 ms, 3 groups
         // 4.60, all four 4.72; debug & 256 / 512 select 2 / 1 groups)
         const int ndirect = (dbg & 256) ? 2 : (dbg & 512) ? 1 : 3;
         uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
-#ifdef SPNERF_EXPERIMENTS
-        if (dbg & 2048) gdirect = nullptr;
-        if (dbg & 1024) bwd_columns<3, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else if (dbg & 4096) bwd_columns<2, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else
-#endif
-        if (L > 0) bwd_columns<RELU ? 4 : 0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-        else       bwd_columns<RELU ? 4 : 1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
         const bool more = (L > 0) || p.sem;
-        sync.end(more);
+        if constexpr (kSplitBwd) {
+          // Split phase (net_plan.h): this thread owns H / 4 columns of each accumulator half.  The first half is
+          // turned into gradients (kept in registers, stored to the gradient save area) while the tensor pipe still
+          // works on the second half; the shared-memory tile -- the A operand the MMAs are reading -- is touched only
+          // after the whole phase has retired.
+          constexpr int CW = H / 4, NBC = CW / 16;
+          if (CW % 64 != 0) gdirect = gs(p.gm.G[L]);      // narrow network: a group's columns are less than a slab, all direct
+          uint4 keep[2 * NBC];
+          ywin_load<NBC>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * CW, row);
+          sync.begin_half();
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC>(taddr, cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, NBC, keep);
+          else       bwd_columns<RELU ? 4 : 1, NBC>(taddr, cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, NBC, keep);
+          ywin_load<NBC>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), H + cg * CW, row);
+          sync.begin();
+#pragma unroll
+          for (int q = 0; q < 2 * NBC; ++q) *reinterpret_cast<uint4*>(act + slab_off(cg * CW + 8 * q, row)) = keep[q];
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC>(taddr, H + cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win);
+          else       bwd_columns<RELU ? 4 : 1, NBC>(taddr, H + cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win);
+          sync.end(more);
+          // column groups >= ndirect: their H / 4 columns of each half leave from shared memory during the next MMAs
+          if (ndirect < 4) {
+            constexpr int SC = CW / 64 > 0 ? CW / 64 : 1;       // slabs per column group and half
+            if constexpr (CW % 64 == 0) {
+              copy_slabs_out(act, SC * ndirect, SC * (4 - ndirect), gs(p.gm.G[L] + SC * ndirect));
+              copy_slabs_out(act, H / 64 + SC * ndirect, SC * (4 - ndirect), gs(p.gm.G[L] + H / 64 + SC * ndirect));
+            }
+          }
+        } else {
 #ifdef SPNERF_EXPERIMENTS
-        if (!(dbg & 2048))
+          if (!(dbg & (1024 | 4096)))
 #endif
-        copy_slabs_out(act, SPC * ndirect, SPC * (4 - ndirect), gs(p.gm.G[L] + SPC * ndirect));
+          ywin_load<NBQ>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * QW, row);
+          sync.begin();
+#ifdef SPNERF_EXPERIMENTS
+          if (dbg & 2048) gdirect = nullptr;
+          if (dbg & 1024) bwd_columns<3, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+          else if (dbg & 4096) bwd_columns<2, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+          else
+#endif
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+          else       bwd_columns<RELU ? 4 : 1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
+          sync.end(more);
+#ifdef SPNERF_EXPERIMENTS
+          if (!(dbg & 2048))
+#endif
+          copy_slabs_out(act, SPC * ndirect, SPC * (4 - ndirect), gs(p.gm.G[L] + SPC * ndirect));
+        }
         if (p.sem && L == 4) emb_phase(true);
         if (p.sem && L == 0) emb_phase(false);
       }

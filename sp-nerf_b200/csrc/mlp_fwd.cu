@@ -49,9 +49,10 @@ struct FwdParams {
 // W:    accumulator columns per batch, 32 or 16.  The phases that also feed a tiny last layer through `each`
 //       use 16: with 32 accumulator values in registers next to the layer's partial sums the training variant
 //       spilled inside the loop (semantic head epilogue 17.6 k cycles against 5.8 k without the saves)
+// keep: (split phases) the packed fp16 outputs stay in the caller's registers instead of going to shared memory
 template <int ACT, bool TO_SMEM, bool BITS, int W, class Each>
 __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, int dst_col0, int row, uint8_t* ssave,
-                                          uint8_t* ysave, Each each) {
+                                          uint8_t* ysave, Each each, uint4* keep = nullptr) {
   uint32_t v[W];
   if (W == 32) tmem_ld32(taddr + j0, reinterpret_cast<uint32_t(&)[32]>(v));
   else tmem_ld16(taddr + j0, reinterpret_cast<uint32_t(&)[16]>(v));
@@ -77,6 +78,7 @@ __device__ __forceinline__ void epi_batch(uint32_t taddr, int j0, uint8_t* act, 
     }
     const uint4 yp = make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
     if (TO_SMEM) *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + j, row)) = yp;
+    if (keep) keep[c] = yp;
     if (ysave) stg16(ysave + xsave_off(j, row), yp);
   }
   if (BITS && ACT != 2) {
@@ -98,6 +100,36 @@ __device__ __forceinline__ void epi_cols(uint32_t taddr, int j0, int ncols, uint
 }
 
 struct NoEach { __device__ __forceinline__ void operator()(int, float) const {} };
+
+// Epilogue of a layer that fills the whole accumulator (2 H columns: trunk layers, feats_from_xyz), including the waits
+// for the MMA phase.  Split phases (net_plan.h): the thread owns H / 4 columns of each accumulator half.  The first
+// half is complete when issuer 0 signals bar_half; it is converted (and saved to global memory) while the tensor pipe
+// still works on the second half, but its shared-memory image -- the next layer's A operand, in place of the one the
+// MMAs are still reading -- is written only after the whole phase has retired.
+template <int ACT, int H, class Sync>
+__device__ __forceinline__ void epi_full_layer(Sync& sync, uint32_t taddr, int cg, uint8_t* act, int row, uint8_t* xsave,
+                                               uint8_t* ysave, int dbg) {
+  if constexpr (kSplitFwd) {
+    constexpr int CW = H / 4, NB = CW / 32;       // columns per thread and half; 32-column batches
+    uint4 keep[NB][4];
+    sync.begin_half();
+    const bool bits = ACT != 2 && xsave;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (bits) epi_batch<ACT, false, true, 32>(taddr, cg * CW + 32 * b, act, 0, row, xsave, ysave, NoEach(), keep[b]);
+      else epi_batch<ACT, false, false, 32>(taddr, cg * CW + 32 * b, act, 0, row, nullptr, ysave, NoEach(), keep[b]);
+    }
+    sync.begin();
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(act + slab_off(cg * CW + 32 * b + 8 * c, row)) = keep[b][c];
+    epi_cols<ACT, true>(taddr, H + cg * CW, (dbg & 2) ? 32 : CW, act, 0, row, xsave, ysave, NoEach());
+  } else {
+    sync.begin();
+    epi_cols<ACT, true>(taddr, cg * (H / 2), (dbg & 2) ? 32 : H / 2, act, 0, row, xsave, ysave, NoEach());
+  }
+}
 
 __device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
@@ -129,7 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     producer_loop(sh, p.blob, p.tab, n_iters, dbg, prof);
   } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
     if (sh.rank == 0) mma_loop(sh, tmem_base, p.tab, warp - kIssuerWarp0, n_iters, dbg, prof);
-    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab.n, n_iters, dbg);
+    else if (warp == kIssuerWarp0) relay_loop(sh, p.tab, n_iters, dbg);
   } else if (warp < 16) {
     epi_registers();
     const int cg = (warp - kEpiWarp0) >> 2;    // column group of this warp
@@ -254,25 +286,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       }
       sync.end(true);
 
-      // ---- trunk layer 0: sin(30 (W0 x + b0))  (spnerf.py:202, Siren w0=30) ----
-      sync.begin();
-      // half of the tile leaves from registers during the epilogue, the other half from shared memory
-      // during the next MMA phase: global stores are the scarce resource (~13 B/cycle/SM chip-wide)
-      // The saved copy of every activation tile leaves from registers during the epilogue.  (Copying half of it out
-      // of shared memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy
-      // competes with the MMAs for shared-memory bandwidth.  debug & 128 selects that variant.)
-      const bool direct_all = !(dbg & 128);
-      epi_cols<A0, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[0]),
-                        (cg < 2 || direct_all) ? sv(p.sm.y[0]) : nullptr, NoEach());
+      // ---- trunk: layer 0 = sin(30 (W0 x + b0)) (spnerf.py:202, Siren w0 = 30), layers 1..7 = sin(W h + b).  The saved
+      // copy of every activation tile leaves from registers during the epilogue (copying part of it out of shared
+      // memory during the next MMA phase, as the backward does, made the forward 2 % slower: the copy competes with
+      // the MMAs for shared-memory bandwidth) ----
+      epi_full_layer<A0, H>(sync, taddr, cg, act, row, sv(p.sm.x[0]), sv(p.sm.y[0]), dbg);
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[0] + FEAT / 128));
-      // ---- trunk layers 1..7 ----
       for (int i = 1; i < 8; ++i) {
-        sync.begin();
-        epi_cols<AH, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, sv(p.sm.x[i]),
-                          (cg < 2 || direct_all) ? sv(p.sm.y[i]) : nullptr, NoEach());
+        epi_full_layer<AH, H>(sync, taddr, cg, act, row, sv(p.sm.x[i]), sv(p.sm.y[i]), dbg);
         sync.end(true);
-        if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.y[i] + FEAT / 128));
       }
       // ---- heads on h: semantic hidden (accumulator columns 0..255) and sigma (256, 257) ----
       sync.begin();
@@ -303,11 +325,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       }
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
-      sync.begin();
-      epi_cols<2, true>(taddr, cg * QW, (dbg & 2) ? 32 : QW, act, 0, row, nullptr,
-                        (cg < 2 || direct_all) ? sv(p.sm.f) : nullptr, NoEach());
+      epi_full_layer<2, H>(sync, taddr, cg, act, row, nullptr, sv(p.sm.f), dbg);
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, FEAT / 128, FEAT / 128, sv(p.sm.f + FEAT / 128));
 
       // ---- albedo hidden layer (columns 0..255) + first sun layer or beta hidden layer (256..511) ----
       sync.begin();
@@ -320,8 +339,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         if (!p.beta) {
           // every input of this phase has been consumed: the sun activations (next layer's operand) go to slabs
           // 0..3, the albedo activations to slabs 4..7 (only read back by the debug & 128 copy-out variant)
-          epi_cols<AH, true, 16>(taddr, cg * HW, HW, act, H, row, sv(p.sm.rgb_x), direct_all ? sv(p.sm.rgb_y) : nullptr, rgb_each);
-          epi_cols<AH, true>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr,
+          epi_cols<AH, true, 16>(taddr, cg * HW, HW, act, H, row, sv(p.sm.rgb_x), sv(p.sm.rgb_y), rgb_each);
+          epi_cols<AH, true>(taddr + H, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), sv(p.sm.sun_y[0]),
                             NoEach());
           reduce_groups<3>(scratch, c3, cg, row);
         } else {
@@ -342,18 +361,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       sync.end(true);
       if (p.beta) {
         sync.begin();
-        epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), direct_all ? sv(p.sm.sun_y[0]) : nullptr, NoEach());
+        epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[0]), sv(p.sm.sun_y[0]), NoEach());
         sync.end(true);
-      }
-      if (!direct_all) {
-        copy_slabs_out(act, 0, H / 64, sv(p.sm.sun_y[0]));
-        if (!p.beta) copy_slabs_out(act, H / 64, H / 64, sv(p.sm.rgb_y));
       }
       // ---- sun layer 1 ----
       sync.begin();
-      epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[1]), direct_all ? sv(p.sm.sun_y[1]) : nullptr, NoEach());
+      epi_cols<AH, true>(taddr, cg * HW, HW, act, 0, row, sv(p.sm.sun_x[1]), sv(p.sm.sun_y[1]), NoEach());
       sync.end(true);
-      if (!direct_all) copy_slabs_out(act, 0, H / 64, sv(p.sm.sun_y[1]));
       // ---- sun layer 2 + output unit (256 -> 1, sigmoid) ----
       sync.begin();
       {

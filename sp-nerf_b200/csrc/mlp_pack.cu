@@ -266,9 +266,36 @@ struct Builder {
   // Closes a phase.  Its chunks (independent accumulator column ranges) are dealt to the two issuer
   // lanes, balancing step counts, and the ring order interleaves the lanes so that both issuers
   // always have an item in flight.  The order of the steps inside a chunk is preserved.
-  void end_phase() {
+  // split = true (four chunks of a quarter of the accumulator each): the first two chunks -- one per issuer, interleaved
+  // -- make up the first accumulator half, the last two the second; the last item of the first half carries the `half`
+  // mark.  Otherwise every chunk belongs to one issuer and the two lanes are interleaved over the whole phase.
+  void end_phase(bool split = false) {
     const size_t e = steps.size();
     chunk_begin.push_back(e);
+    split = split && chunk_begin.size() == 5;      // the caller built four chunks because its direction splits
+    if (split) {
+      std::vector<MmaStep> out;
+      for (int part = 0; part < 2; ++part) {
+        std::vector<MmaStep> ls[2];
+        for (int l = 0; l < 2; ++l)
+          for (size_t i = chunk_begin[2 * part + l]; i < chunk_begin[2 * part + l + 1]; ++i) {
+            MmaStep st = steps[i];
+            st.lane = (uint8_t)l;
+            ls[l].push_back(st);
+          }
+        size_t a = 0, b = 0;
+        while (a < ls[0].size() || b < ls[1].size()) {
+          if (a < ls[0].size()) out.push_back(ls[0][a++]);
+          if (b < ls[1].size()) out.push_back(ls[1][b++]);
+        }
+        if (part == 0) out.back().half = 1;
+      }
+      for (size_t k = 0; k < out.size(); ++k) steps[phase_begin + k] = out[k];
+      steps[e - 1].last = 1;
+      chunk_begin.clear();
+      phase_begin = e;
+      return;
+    }
     std::vector<MmaStep> lane_steps[2];
     for (size_t c = 0; c + 1 < chunk_begin.size(); ++c) {
       const int lane = lane_steps[0].size() <= lane_steps[1].size() ? 0 : 1;
@@ -296,6 +323,8 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   const int ink = d.in_ksteps;
   const int F = c.feat, H = F / 2, Q = H / 2;      // trunk width, head width, head chunk width (one chunk per issuer)
   const int narrow_merge = F == 512 ? 2 : 4;       // K slabs per ring item of a Q-wide chunk: 16 KB per CTA either way
+  // a layer that fills the whole accumulator: two chunks of H columns, or (split phases, net_plan.h) four of Q
+  const int parts = kSplitFwd ? 4 : 2, PW = 2 * H / parts;
   auto act8 = [](int ncols) {
     std::vector<Builder::Src> v;
     for (int k = 0; k < ncols / 64; ++k) v.push_back({k, 64 * k, 4, 0});
@@ -304,20 +333,20 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
   // layer 0: split-precision product  in_hi*W_hi + in_lo*W_hi + in_hi*W_lo   (models/spnerf.py:202); input columns
   // beyond the slab ride in the aux step with the same three products (net_plan.h AuxExtra)
   const AuxExtra ax = make_aux_extra(c);
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < parts; ++g) {
     AuxSpec a0 = aux_bias(P[SPNERF_P_FC_W0 + 1], F);
     if (ax.n > 0) {
       a0.ex_w = P[SPNERF_P_FC_W0]; a0.ex_ld = d.in_dim; a0.ex_rows = F; a0.ex_col0 = 64;
       for (int q = 0; q < ax.n; ++q) { a0.extra(q, ax.col_hi[q], 0); a0.extra(q, ax.col_lo[q], 0); a0.extra(q, ax.col_dup[q], 1); }
     }
-    b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, g * H, H, g * H,
+    b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, g * PW, PW, g * PW,
             {{kSlabInpHi, 0, ink, 0}, {kSlabInpLo, 0, ink, 0}, {kSlabInpHi, 0, ink, 1}}, false, false, a0);
   }
-  b.end_phase();
+  b.end_phase(true);
   for (int i = 1; i < 8; ++i) {   // models/spnerf.py:203-208, skip concat [h, input] at :327
     const bool skip = (i == c.skip_layer);
     const int cols = F + (skip ? d.in_dim : 0);
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < parts; ++g) {
       auto srcs = act8(F);
       if (skip) srcs.push_back({kSlabInpHi, F, ink, 0});
       AuxSpec ai = aux_bias(P[SPNERF_P_FC_W0 + 2 * i + 1], F);
@@ -325,10 +354,12 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
         ai.ex_w = P[SPNERF_P_FC_W0 + 2 * i]; ai.ex_ld = cols; ai.ex_rows = F; ai.ex_col0 = F + 64;
         for (int q = 0; q < ax.n; ++q) ai.extra(q, ax.col_hi[q], 0);
       }
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], F, cols, g * H, H, g * H, srcs, false, false, ai);
-      if (!skip && F == 256) b.merge_last_chunk(2);      // 128-wide chunks: two K slabs per ring item (16 KB per CTA)
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * i], F, cols, g * PW, PW, g * PW, srcs, false, false, ai);
+      // chunks narrower than 256 columns: several K slabs per ring item (16 KB per CTA); the skip layer's trailing
+      // input-slab step stays on its own (the activation slabs before it pair up evenly)
+      if (256 / PW > 1) b.merge_last_chunk(256 / PW);
     }
-    b.end_phase();
+    b.end_phase(true);
   }
   // heads reading the trunk output h: semantic hidden (:218-223) and sigma (:212).  The 256-wide hidden layer
   // runs as two 128-wide chunks, one per issuer (a single 256-wide chunk left one issuer alone with 9 items, which
@@ -360,12 +391,12 @@ void build_forward(const SpnerfNetConfig& c, const float* const* P, Builder& b) 
     b.items.insert(b.items.end(), kept.begin(), kept.end());
   }
   b.end_phase();
-  for (int g = 0; g < 2; ++g) {   // feats_from_xyz (:215)
-    b.chunk(P[SPNERF_P_FEATS_W], F, F, g * H, H, g * H, act8(F), false, false,
+  for (int g = 0; g < parts; ++g) {   // feats_from_xyz (:215)
+    b.chunk(P[SPNERF_P_FEATS_W], F, F, g * PW, PW, g * PW, act8(F), false, false,
             aux_bias(P[SPNERF_P_FEATS_B], F));
-    if (F == 256) b.merge_last_chunk(2);
+    if (256 / PW > 1) b.merge_last_chunk(256 / PW);
   }
-  b.end_phase();
+  b.end_phase(true);
   AuxSpec sun0 = aux_bias(P[SPNERF_P_SUN0_W + 1], H);          // + sun direction columns (:351)
   sun0.wx = P[SPNERF_P_SUN0_W]; sun0.wx_ld = F + 3; sun0.wx_rows = H; sun0.wx_col0 = F;
   sun0.wx_ncols = 3; sun0.dst_col = kAuxColSun;
@@ -450,7 +481,7 @@ extern "C" int spnerf_debug_step_table(const SpnerfNetConfig* cfg, int backward,
   for (int i = 0; i < t->n && i < max_steps && out; ++i) {
     const MmaStep& s = t->s[i];
     int32_t* o = out + 8 * i;
-    o[0] = s.n; o[1] = s.tmem_col; o[2] = s.a_slab; o[3] = s.ksteps; o[4] = s.first; o[5] = s.last; o[6] = s.lane; o[7] = 0;
+    o[0] = s.n; o[1] = s.tmem_col; o[2] = s.a_slab; o[3] = s.ksteps; o[4] = s.first; o[5] = s.last; o[6] = s.lane; o[7] = s.half;
   }
   return t->n;
 }
@@ -667,6 +698,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
   const int base = c.mapping ? 60 : 3;
   const int F = c.feat, H = F / 2, Q = H / 2;      // trunk width, head width, head chunk width
   const int SF = F / 64, SH = H / 64;              // K slabs of a trunk-wide / head-wide gradient tile
+  const int parts = kSplitBwd ? 4 : 2, PW = 2 * H / parts;      // chunks of a split-capable full-width phase
   using Src = Builder::Src;
   auto ks = [](int first_slab, int nslabs) {
     std::vector<Src> v;
@@ -701,14 +733,15 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     if (F == 256) b.merge_last_chunk(2);
   }
   b.end_phase();
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < parts; ++g) {
     std::vector<Src> v;
     if (c.sem)
       for (int k = 0; k < SH; ++k) v.push_back(Src{k, 64 * k, 4, 0, P[SPNERF_P_SEM0_W], H, F});
     v.push_back(Src{SH, 0, 1, 0, P[SPNERF_P_SIGMA_W], 1, F});       // the sigma column sits in the slab after the semantic hidden gradient
-    b.chunk(nullptr, 0, 0, g * H, H, g * H, v, true, true);
+    b.chunk(nullptr, 0, 0, g * PW, PW, g * PW, v, true, true);
+    if (c.sem && 256 / PW > 1 && SH % (256 / PW) == 0) b.merge_last_chunk(256 / PW);   // the sigma step stays on its own
   }
-  b.end_phase();
+  b.end_phase(true);
   // trunk, layers 7..1; the label-embedding columns of the skip layer and of layer 0 get their own
   // 16-wide mini phases (only when the embedding exists)
   for (int L = 7; L >= 1; --L) {
@@ -719,11 +752,11 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
       b.merge_last_chunk(SF);
       b.end_phase();
     }
-    for (int g = 0; g < 2; ++g) {
-      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], F, cols, g * H, H, g * H, ks(0, SF), true);
-      if (F == 256) b.merge_last_chunk(2);
+    for (int g = 0; g < parts; ++g) {
+      b.chunk(P[SPNERF_P_FC_W0 + 2 * L], F, cols, g * PW, PW, g * PW, ks(0, SF), true);
+      if (256 / PW > 1) b.merge_last_chunk(256 / PW);
     }
-    b.end_phase();
+    b.end_phase(true);
   }
   if (c.sem) {
     b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, base, 16, 0, ks(0, SF), true);

@@ -38,11 +38,12 @@ struct Smem {
   uint8_t* act;
   uint8_t* aux;
   uint8_t* wst;
-  uint64_t* bar_full;    // [4] weight stage landed (rank 0: both halves, see setup)
+  uint64_t* bar_full;    // [2][4] weight stage landed, one set per issuer lane at [lane * 8 + stage] (rank 0: both halves, see setup)
   uint64_t* bar_empty;   // [4] weight stage consumed (arrives from the issuer's commit, both CTAs)
   uint64_t* bar_mma;     // MMA phase retired -> epilogue (both CTAs)
   uint64_t* bar_epi;     // rank 0 only: both epilogues done -> MMA
   uint64_t* bar_par;     // parameter region landed (once)
+  uint64_t* bar_half;    // split phases: the first half of the accumulator retired (both issuers) -> epilogue (both CTAs)
   uint32_t* tmem_slot;
   uint32_t rank;
 };
@@ -54,7 +55,7 @@ __device__ __forceinline__ Smem carve(uint8_t* smem) {
   s.wst = smem + kOffWst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   s.bar_full = bars; s.bar_empty = bars + 4;
-  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14;
+  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14; s.bar_half = bars + 15;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   s.rank = cluster_ctarank();
   return s;
@@ -69,8 +70,9 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
     for (int i = 0; i < kNumWStages; ++i) {
       // issuer CTA: its own copy (arrive.expect_tx) + the peer's relay; peer CTA: its own copy only
       mbar_init(&s.bar_full[i], (s.rank == 0 && !(debug & 8)) ? 2 : 1); mbar_init(&s.bar_empty[i], 1);
+      mbar_init(&s.bar_full[8 + i], (s.rank == 0 && !(debug & 8)) ? 2 : 1);
     }
-    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1);
+    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1); mbar_init(s.bar_half, 2);
     fence_mbar_init();
     mbar_expect_tx(s.bar_par, kSmallWFloats * 4);
     bulk_g2s(smem + kOffRgb2, smallw, 3072 * 4, s.bar_par);              // rgb2 | sem2
@@ -104,14 +106,18 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob
     for (int i = 0; i < n_steps; ++i) {
       const uint32_t w_off16 = tab.s[i].w_off16;
       const uint32_t bytes = (uint32_t)tab.s[i].bytes16 * 8u;     // half of the item
+      // "landed" barriers are per issuer lane: a wait tells mbarrier phases apart by one parity bit only, so every
+      // barrier must be waited on, phase after phase, by ONE consumer.  With a barrier per stage and the two issuers'
+      // items interleaved unevenly (split phases), an issuer that skipped the other one's use of a stage could take the
+      // stage's previous completed phase for its own (seen as a rare hang).
+      uint64_t* full = &s.bar_full[(uint32_t)tab.s[i].lane * 8u + stage];
       mbar_wait(&s.bar_empty[stage], phase ^ 1, 10);
       if (prof && it == 2 && i < 256 && blockIdx.x == 0 && (threadIdx.x & 31) == 0) prof[512 + i] = clock64();
       if (elect_one()) {
-        if (debug & 1) { mbar_arrive(&s.bar_full[stage]); }
+        if (debug & 1) { mbar_arrive(full); }
         else {
-          mbar_expect_tx(&s.bar_full[stage], bytes);
-          bulk_g2s(s.wst + stage * kWStageBytes, blob + (size_t)w_off16 * 16 + (size_t)s.rank * bytes, bytes,
-                   &s.bar_full[stage]);
+          mbar_expect_tx(full, bytes);
+          bulk_g2s(s.wst + stage * kWStageBytes, blob + (size_t)w_off16 * 16 + (size_t)s.rank * bytes, bytes, full);
         }
       }
       __syncwarp();
@@ -123,16 +129,19 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const uint8_t* blob
 
 // warp 1, rank 1: tell the issuer that this CTA's half of each item has landed (second arrival on
 // the issuer's stage barrier)
-__device__ __forceinline__ void relay_loop(const Smem& s, int n_steps, int64_t n_iters, int debug = 0) {
-  uint32_t stage = 0, phase = 0;
+__device__ __forceinline__ void relay_loop(const Smem& s, const StepTable& tab, int64_t n_iters, int debug = 0) {
+  uint32_t stage = 0, par[2] = {0u, 0u};      // one parity bit per (lane, stage) barrier
   if (debug & 8) return;      // timing experiment: the issuer does not wait for this CTA's operands
   const uint32_t remote0 = mapa_shared(smem_u32(&s.bar_full[0]), 0);
+  const int n_steps = tab.n;
   for (int64_t it = 0; it < n_iters; ++it)
     for (int i = 0; i < n_steps; ++i) {
-      mbar_wait(&s.bar_full[stage], phase, 22);
-      if (elect_one()) mbar_arrive_remote(remote0 + stage * 8u);
+      const uint32_t l = tab.s[i].lane, slot = l * 8u + stage;
+      mbar_wait(&s.bar_full[slot], (par[l] >> stage) & 1u, 22);
+      par[l] ^= 1u << stage;
+      if (elect_one()) mbar_arrive_remote(remote0 + slot * 8u);
       __syncwarp();
-      if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
+      if (++stage == kNumWStages) stage = 0;
     }
 }
 
@@ -144,7 +153,8 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
   constexpr uint64_t tmpl = make_smem_desc_template(16, 1024, kSwizzle128B);
   constexpr uint64_t tmpl_aux = make_smem_desc_template(128, 256, kSwizzleNone);   // 16-column no-swizzle operand
   const uint32_t act_addr = smem_u32(s.act), wst_addr = smem_u32(s.wst), aux_addr = smem_u32(s.aux);
-  uint32_t stage = 0, phase = 0, epi_par = 0;
+  uint32_t stage = 0, phase = 0, epi_par = 0, full_par = 0;      // full_par: parity bits of this lane's stage barriers
+  uint64_t* const my_full = &s.bar_full[my_lane * 8];
   const bool plog = prof && blockIdx.x == 0 && (threadIdx.x & 31) == 0;     // per-step log, iteration 2, both lanes
   long long w_epi = 0, w_full = 0, t_all = prof ? clock64() : 0;
   for (int64_t it = 0; it < n_iters; ++it) {
@@ -157,12 +167,13 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
       bool last;
       do {
         const uint32_t n = tab.s[i].n, tcol = tab.s[i].tmem_col, a_slab = tab.s[i].a_slab, ksteps = tab.s[i].ksteps;
-        const uint32_t first = tab.s[i].first, lane = tab.s[i].lane;
+        const uint32_t first = tab.s[i].first, lane = tab.s[i].lane, half = tab.s[i].half;
         last = tab.s[i].last;
         ++i;
         if ((int)lane == my_lane) {
           t0 = prof ? clock64() : 0;
-          mbar_wait_cluster(&s.bar_full[stage], phase, 21);      // both halves of the item have landed
+          mbar_wait_cluster(&my_full[stage], (full_par >> stage) & 1u, 21);      // both halves of the item have landed
+          full_par ^= 1u << stage;
           if (prof) {
             const long long t1 = clock64();
             w_full += t1 - t0;
@@ -172,16 +183,20 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
           const uint32_t b0 = wst_addr + stage * kWStageBytes;
           const uint32_t idesc = make_idesc_f16(256, n, 0, 0);
           if (elect_one()) {
-            if (!(debug & 4)) {
-              if (a_slab == kAuxSlab) {
-                umma2_f16(tmem_base + tcol, smem_desc(tmpl_aux, aux_addr), smem_desc(tmpl_aux, b0), idesc, first ? 0u : 1u);
-              } else {
-                // K = 16 steps: 4 per 64-wide slab; a fused item (mlp_pack.cu merge_last_chunk) runs on over the
-                // following A slabs, its B tiles (this CTA's n / 2 rows x 128 bytes per slab) back to back
-                const uint32_t a0 = act_addr + a_slab * kSlabBytes, b_slab = (n >> 1) * 128u;
-                for (uint32_t k = 0; k < ksteps; ++k)
+            const uint32_t acc0 = first ? 0u : 1u;
+            if (a_slab == kAuxSlab) {
+              const uint64_t ad = smem_desc(tmpl_aux, aux_addr), bd = smem_desc(tmpl_aux, b0);
+              if (!(debug & 4)) umma2_f16(tmem_base + tcol, ad, bd, idesc, acc0);
+            } else {
+              // K = 16 steps: 4 per 64-wide slab; a fused item (mlp_pack.cu merge_last_chunk) runs on over the
+              // following A slabs, its B tiles (this CTA's n / 2 rows x 128 bytes per slab) back to back
+              const uint32_t a0 = act_addr + a_slab * kSlabBytes, b_slab = (n >> 1) * 128u;
+              const uint64_t ad0 = smem_desc(tmpl, a0), bd0 = smem_desc(tmpl, b0);
+              if (!(debug & 4)) {
+                umma2_f16(tmem_base + tcol, ad0, bd0, idesc, acc0);
+                for (uint32_t k = 1; k < ksteps; ++k)
                   umma2_f16(tmem_base + tcol, smem_desc(tmpl, a0 + (k >> 2) * kSlabBytes + (k & 3) * 32),
-                            smem_desc(tmpl, b0 + (k >> 2) * b_slab + (k & 3) * 32), idesc, (first && k == 0) ? 0u : 1u);
+                            smem_desc(tmpl, b0 + (k >> 2) * b_slab + (k & 3) * 32), idesc, 1u);
               }
             }
             umma2_commit(&s.bar_empty[stage]);
@@ -189,6 +204,9 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
           __syncwarp();
           if (plog && it == 2 && i <= 256) prof[1280 + i - 1] = clock64();       // commit issued
         }
+        // split phases: the first half of the accumulator is complete once both issuers' MMAs up to here have retired
+        if (half && elect_one()) umma2_commit(s.bar_half);
+        __syncwarp();
         if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
       } while (!last);
       if (elect_one()) umma2_commit(s.bar_mma);      // this issuer's share of the phase (possibly empty) has retired
@@ -207,7 +225,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 struct EpiSync {
   const Smem& s;
   bool issuer;
-  uint32_t mma_par = 0;
+  uint32_t mma_par = 0, half_par = 0;
   long long* prof;        // optional phase clock log (block 0 only)
   int prof_i = 0;
   uint32_t epi_remote;    // rank 1: the issuer CTA's bar_epi
@@ -225,6 +243,14 @@ struct EpiSync {
   __device__ __forceinline__ void begin() {
     if (issuer) mbar_wait(s.bar_mma, mma_par, 30);
     mma_par ^= 1;
+    epi_bar_sync();
+    tc_fence_after();
+    stamp();
+  }
+  // split phases: the first half of the accumulator (issuer 0's chunk) is complete
+  __device__ __forceinline__ void begin_half() {
+    if (issuer) mbar_wait(s.bar_half, half_par, 32);
+    half_par ^= 1;
     epi_bar_sync();
     tc_fence_after();
     stamp();

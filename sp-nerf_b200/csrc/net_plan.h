@@ -52,8 +52,28 @@ struct __align__(16) MmaStep {
   uint8_t last;       // 1: last item of a phase (in ring order) -> both issuers signal the epilogue
   uint16_t bytes16;   // item size in 16-byte units
   uint8_t lane;       // which of the two MMA issuer warps owns this item (its accumulation chunk)
-  uint8_t _pad;
+  uint8_t half;       // 1: last item of the first accumulator half in a split phase: both issuers signal bar_half when they
+                      //    pass it (the epilogue starts on that half while the tensor pipe works on the second one)
 };
+
+// Split phases (SPNERF_SPLIT, default on).  A phase that fills the whole accumulator (trunk layers, feats_from_xyz and
+// their transposes) is cut into four chunks of a quarter of the columns.  Chunks 0 and 1 -- one per MMA issuer,
+// interleaved in the ring -- make up the first accumulator half, chunks 2 and 3 the second.  When the first half has
+// retired (bar_half) the epilogue converts it into registers (and saves it to global memory) while the tensor pipe
+// works on the second half; its shared-memory image -- the next layer's A operand, in place of the one the MMAs are
+// still reading -- is written only after the whole phase has retired.  Every chunk still belongs to ONE issuer, so the
+// fp32 summation order, hence the result bits, stay deterministic.
+// Measured (round 2, C2 shape): quarter-width chunks (N = 128) run the MMA phase of a 512-wide layer in 11.8 k cycles
+// instead of 9.45 k (the A operand is re-read from shared memory twice as often).  The forward's epilogue is short
+// (5-6 k cycles), so hiding half of it does not pay for that: the forward keeps whole phases.  The backward's epilogue is
+// 11.8 k cycles (it streams the saved activations from HBM), so there the split wins.
+#ifndef SPNERF_SPLIT_FWD
+#define SPNERF_SPLIT_FWD 0
+#endif
+#ifndef SPNERF_SPLIT_BWD
+#define SPNERF_SPLIT_BWD 1
+#endif
+constexpr bool kSplitFwd = SPNERF_SPLIT_FWD != 0, kSplitBwd = SPNERF_SPLIT_BWD != 0;
 
 // The step list travels to the kernels as a launch parameter (constant bank): the producer and the
 // MMA issuer read one entry per item, and a dependent global load per item would cap the issue rate.

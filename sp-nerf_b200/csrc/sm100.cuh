@@ -102,7 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
       if (t0 == 0) t0 = now;
       else if (now - t0 > SPNERF_WATCHDOG_CYCLES) {
         atomicCAS(&g_watchdog_code, 0u, code);
+#ifdef SPNERF_WATCHDOG_NOTRAP
+        return;                      // debugging: let the kernel run on (with garbage) so the code can be read back
+#else
         __trap();
+#endif
       }
     }
   }
@@ -167,7 +171,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       if (t0 == 0) t0 = now;
       else if (now - t0 > SPNERF_WATCHDOG_CYCLES) {
         atomicCAS(&g_watchdog_code, 0u, code);
+#ifdef SPNERF_WATCHDOG_NOTRAP
+        return;
+#else
         __trap();
+#endif
       }
     }
   }
