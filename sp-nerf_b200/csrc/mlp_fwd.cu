@@ -131,6 +131,43 @@ __device__ __forceinline__ void epi_full_layer(Sync& sync, uint32_t taddr, int c
   }
 }
 
+// sin / cos of the positional encoding (models/spnerf.py:32-37), accurate to ~1 ulp over the whole float range like
+// sinf / cosf, but without their Payne-Hanek path (a table in local memory: 160 LDL / STL in this kernel's SASS).
+// |a| <= 105615: three-constant Cody-Waite reduction by pi/2 in fp32 FMAs and the cephes minimax polynomials on
+// [-pi/4, pi/4].  Beyond (scene-normalised coordinates times 2^9 never get there): reduction in double.
+__device__ __forceinline__ float pe_sincos(float a, int quadrant_shift) {
+  float r;
+  int q;
+  if (fabsf(a) > 105615.0f) {
+    const double t = (double)a;
+    const double k = rint(t * 0.6366197723675814);
+    double rr = fma(-k, 1.5707963267948966, t);
+    rr = fma(-k, 6.123233995736766e-17, rr);
+    r = (float)rr;
+    q = (int)fmod(k, 4.0);
+  } else {
+    const float j = rintf(a * 0.636619772f);
+    r = fmaf(j, -1.57079601e+00f, a);
+    r = fmaf(j, -3.13916473e-07f, r);
+    r = fmaf(j, -5.39030253e-15f, r);
+    q = (int)j;
+  }
+  q += quadrant_shift;      // cos(a) = sin(a + pi/2)
+  const float s = r * r;
+  float v;
+  if (q & 1) {
+    v = fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    v = fmaf(v, s, 4.166664568298827e-2f);
+    v = fmaf(v, s, -0.5f);
+    v = fmaf(v, s, 1.0f);
+  } else {
+    v = fmaf(s, -1.9515295891e-4f, 8.3321608736e-3f);
+    v = fmaf(v, s, -1.6666654611e-1f);
+    v = fmaf(v * s, r, r);
+  }
+  return (q & 2) ? -v : v;
+}
+
 __device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch Softplus
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -227,9 +264,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
               if (col < base) {
                 if (p.mapping) {                        // [sin(f x)(3), cos(f x)(3)] per f = 2^k (spnerf.py:32-37)
                   const int k = col / 6, w = col % 6;
-                  const float a = __fmul_rn((float)(1 << k), q[w % 3]);
-                  val = (w < 3) ? sinf(a) : cosf(a);
-                } else val = q[col];
+                  const int w3 = w % 3;
+                  const float a = __fmul_rn((float)(1 << k), w3 == 0 ? q[0] : w3 == 1 ? q[1] : q[2]);
+                  val = pe_sincos(a, w < 3 ? 0 : 1);
+                } else val = col == 0 ? q[0] : col == 1 ? q[1] : q[2];
               } else if (col < p.in_dim && lab >= 0) {
                 val = S[p.so.emb + lab * p.emb_dim + (col - base)];
               }
@@ -257,13 +295,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           for (int e = 0; e < 16; ++e) a[e] = 0.f;
           if (valid) {
             a[kAuxColOne] = 1.f; a[kAuxColSun] = sun[0]; a[kAuxColSun + 1] = sun[1]; a[kAuxColSun + 2] = sun[2];
-            if (p.beta && p.t_emb)
-              for (int e = 0; e < p.t_dim; ++e) a[kAuxColT + e] = p.t_emb[ray * p.t_dim + e];
+            // (every index into a[] is a compile-time constant so that the array stays in registers)
+            if (p.beta && p.t_emb) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (e < p.t_dim) a[kAuxColT + e] = p.t_emb[ray * p.t_dim + e];
+            }
             // encoded-input columns 64.. (label embedding): high part, residual, high part again (net_plan.h AuxExtra)
-            for (int q = 0; q < p.ax.n; ++q) {
-              const float val = lab >= 0 ? S[p.so.emb + lab * p.emb_dim + (64 + q - base)] : 0.f;
-              const float hi_f = __half2float(__float2half_rn(val));
-              a[p.ax.col_hi[q]] = hi_f; a[p.ax.col_lo[q]] = val - hi_f; a[p.ax.col_dup[q]] = hi_f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < p.ax.n) {
+                const float val = lab >= 0 ? S[p.so.emb + lab * p.emb_dim + (64 + q - base)] : 0.f;
+                const float hi_f = __half2float(__float2half_rn(val));
+#pragma unroll
+                for (int e = kAuxColT; e < 16; ++e) {
+                  if (e == p.ax.col_hi[q] || e == p.ax.col_dup[q]) a[e] = hi_f;
+                  else if (e == p.ax.col_lo[q]) a[e] = val - hi_f;
+                }
+              }
             }
           }
           if (cg == 1) {                         // operand of this tile's aux steps
@@ -321,7 +370,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         });
         reduce_groups<8>(scratch, lg, cg, row);
         if (cg == 0 && valid)
-          for (int c = 0; c < p.n_classes; ++c) orow[p.col_sem + c] = lg[c] + S[p.so.sem2_b + c];   // spnerf.py:365-367
+#pragma unroll
+          for (int c = 0; c < 8; ++c)      // static indices keep lg[] in registers
+            if (c < p.n_classes) orow[p.col_sem + c] = lg[c] + S[p.so.sem2_b + c];   // spnerf.py:365-367
       }
       sync.end(true);
       // ---- feats_from_xyz: linear, overwrites h ----
