@@ -85,6 +85,9 @@ __device__ __forceinline__ YBatch ybatch_load(const uint8_t* ysave, const uint8_
 #define SPNERF_YWIN 3
 #endif
 constexpr int kYWin = SPNERF_YWIN;
+#ifndef SPNERF_BWD_NDIRECT
+#define SPNERF_BWD_NDIRECT 3
+#endif
 struct YWindow { YBatch b[kYWin]; };
 // NB: batches the column group owns in this layer (a narrow network's head layers have fewer than the window)
 template <int NB>
@@ -94,6 +97,32 @@ __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, cons
     if (i < NB) w.b[i] = ybatch_load(ysave, ssave, j0 + 16 * i, row);
 }
 
+// The derivative needs nothing from the accumulator, so the batches that sit in the window while the epilogue warps
+// wait for an MMA phase are converted in place during that wait: y (fp16) -> dact (fp16: cos x or 30 cos x, signed).
+// MUFU, saturate and sign work leave the exposed part of the epilogue; fp16 rounding of the factor (2^-11 relative)
+// is below the error of rebuilding it from the fp16 output.
+template <int MODE>
+__device__ __forceinline__ void ybatch_to_dact(YBatch& b) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float y[8], d[8];
+    unpack8(b.y[c], y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d[e] = dsin<MODE == 4>(y[e], b.sb, c * 8 + e);
+      if (MODE == 1) d[e] *= 30.f;
+    }
+    b.y[c] = make_uint4(pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+  }
+}
+template <int MODE, int NB>
+__device__ __forceinline__ void ywin_to_dact(YWindow& w) {
+#pragma unroll
+  for (int i = 0; i < kYWin; ++i)
+    if (i < NB) ybatch_to_dact<MODE>(w.b[i]);
+}
+template <int NB> struct PreBatches { static constexpr int value = NB < kYWin ? NB : kYWin; };
+
 // G[j] = acc[j] * dact(j) for columns [j0, j0 + 16 NB) of a chunk at TMEM address taddr;
 // MODE 0: dact = cos(x) rebuilt from (ysave, ssave)     MODE 1: dact = 30 cos(30 x), same     MODE 2: dact = 1
 // MODE 4: dact = [x > 0] (ReLU network; the saved outputs are loaded like the sine layers' but only the bits matter)
@@ -101,7 +130,8 @@ __device__ __forceinline__ void ywin_load(YWindow& w, const uint8_t* ysave, cons
 // `win`: batches j0 .. j0 + 16 kYWin, loaded by the caller before it waited for the accumulator
 // keep: (split phases) the packed fp16 gradients stay in the caller's registers (2 x uint4 per batch) instead of going
 //       to shared memory
-template <int MODE, int NB>
+// PRE: the first PRE batches of the window already hold the derivative (ywin_to_dact)
+template <int MODE, int NB, int PRE = 0>
 __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_t* ysave, const uint8_t* ssave,
                                             uint8_t* act, int dst_col0, int row, uint8_t* gsave, YWindow& win, int nb_run = NB,
                                             uint4* keep = nullptr) {
@@ -127,8 +157,11 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
           unpack8(cur.y[c], y);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float d = dsin<MODE == 4>(y[e], cur.sb, c * 8 + e);
-            g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 1 ? 30.f * d : d);
+            if (b < PRE) g[e] = __uint_as_float(v[c * 8 + e]) * y[e];
+            else {
+              const float d = dsin<MODE == 4>(y[e], cur.sb, c * 8 + e);
+              g[e] = __uint_as_float(v[c * 8 + e]) * (MODE == 1 ? 30.f * d : d);
+            }
           }
         } else {
 #pragma unroll
@@ -323,14 +356,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
       // ---- after sun_v_net.4^T: G_s2 ----
       YWindow win;
       ywin_load<NBH>(win, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), cg * HW, row);
+      if (!RELU) ywin_to_dact<0, NBH>(win);
       sync.begin();
-      bwd_columns<RELU ? 4 : 0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
+      bwd_columns<RELU ? 4 : 0, NBH, RELU ? 0 : PreBatches<NBH>::value>(taddr, cg * HW, xs(p.sm.sun_y[1]), xs(p.sm.sun_x[1]), act, 0, row, nullptr, win);
       sync.end(true);
       copy_slabs_out(act, 0, H / 64, gs(p.gm.G_sun[1]));
       // ---- after sun_v_net.2^T: G_s1 -> slabs 0..3 ; albedo hidden G_r1 -> slabs 4..7 ----
       ywin_load<NBH>(win, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), cg * HW, row);
+      if (!RELU) ywin_to_dact<0, NBH>(win);
       sync.begin();
-      bwd_columns<RELU ? 4 : 0, NBH>(taddr, cg * HW, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
+      bwd_columns<RELU ? 4 : 0, NBH, RELU ? 0 : PreBatches<NBH>::value>(taddr, cg * HW, xs(p.sm.sun_y[0]), xs(p.sm.sun_x[0]), act, 0, row, nullptr, win);
       {
         const float c0 = g_u[0] * scale, c1 = g_u[1] * scale, c2 = g_u[2] * scale;
         gen_columns<RELU>([&](int j) { const float4 w = Wrgb2[j]; return fmaf(c0, w.x, fmaf(c1, w.y, c2 * w.z)); }, cg * HW, HW,
@@ -405,7 +440,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
         // three of the four column groups store their part of the gradient tile from registers, the last one's is
         // copied out of shared memory during the next MMAs (alternating A/B on one box: 2 groups 4.68 ms, 3 groups
         // 4.60, all four 4.72; debug & 256 / 512 select 2 / 1 groups)
-        const int ndirect = (dbg & 256) ? 2 : (dbg & 512) ? 1 : 3;
+        const int ndirect = (dbg & 256) ? 2 : (dbg & 512) ? 1 : SPNERF_BWD_NDIRECT;
         uint8_t* gdirect = cg < ndirect ? gs(p.gm.G[L]) : nullptr;
         const bool more = (L > 0) || p.sem;
         if constexpr (kSplitBwd) {
@@ -416,16 +451,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
           constexpr int CW = H / 4, NBC = CW / 16;
           if (CW % 64 != 0) gdirect = gs(p.gm.G[L]);      // narrow network: a group's columns are less than a slab, all direct
           uint4 keep[2 * NBC];
+          constexpr int PC = RELU ? 0 : PreBatches<NBC>::value;
           ywin_load<NBC>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * CW, row);
+          if (!RELU) { if (L > 0) ywin_to_dact<0, NBC>(win); else ywin_to_dact<1, NBC>(win); }
           sync.begin_half();
-          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC>(taddr, cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, NBC, keep);
-          else       bwd_columns<RELU ? 4 : 1, NBC>(taddr, cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, NBC, keep);
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC, PC>(taddr, cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, NBC, keep);
+          else       bwd_columns<RELU ? 4 : 1, NBC, PC>(taddr, cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, NBC, keep);
           ywin_load<NBC>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), H + cg * CW, row);
+          if (!RELU) { if (L > 0) ywin_to_dact<0, NBC>(win); else ywin_to_dact<1, NBC>(win); }
           sync.begin();
 #pragma unroll
           for (int q = 0; q < 2 * NBC; ++q) *reinterpret_cast<uint4*>(act + slab_off(cg * CW + 8 * q, row)) = keep[q];
-          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC>(taddr, H + cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win);
-          else       bwd_columns<RELU ? 4 : 1, NBC>(taddr, H + cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win);
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBC, PC>(taddr, H + cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win);
+          else       bwd_columns<RELU ? 4 : 1, NBC, PC>(taddr, H + cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win);
           sync.end(more);
           // column groups >= ndirect: their H / 4 columns of each half leave from shared memory during the next MMAs
           if (ndirect < 4) {
@@ -440,6 +478,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
           if (!(dbg & (1024 | 4096)))
 #endif
           ywin_load<NBQ>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), cg * QW, row);
+          constexpr int PQ = RELU ? 0 : PreBatches<NBQ>::value;
+#ifdef SPNERF_EXPERIMENTS
+          if (!(dbg & (1024 | 4096)))
+#endif
+          if (!RELU) { if (L > 0) ywin_to_dact<0, NBQ>(win); else ywin_to_dact<1, NBQ>(win); }
           sync.begin();
 #ifdef SPNERF_EXPERIMENTS
           if (dbg & 2048) gdirect = nullptr;
@@ -447,8 +490,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
           else if (dbg & 4096) bwd_columns<2, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
           else
 #endif
-          if (L > 0) bwd_columns<RELU ? 4 : 0, NBQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
-          else       bwd_columns<RELU ? 4 : 1, NBQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
+          if (L > 0) bwd_columns<RELU ? 4 : 0, NBQ, PQ>(taddr, cg * QW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, wide_cols / 16);
+          else       bwd_columns<RELU ? 4 : 1, NBQ, PQ>(taddr, cg * QW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, wide_cols / 16);
           sync.end(more);
 #ifdef SPNERF_EXPERIMENTS
           if (!(dbg & 2048))
