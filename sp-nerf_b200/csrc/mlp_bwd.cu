@@ -85,6 +85,9 @@ __device__ __forceinline__ YBatch ybatch_load(const uint8_t* ysave, const uint8_
 #define SPNERF_YWIN 3
 #endif
 constexpr int kYWin = SPNERF_YWIN;
+#ifndef SPNERF_BWD_HMUL
+#define SPNERF_BWD_HMUL 1
+#endif
 #ifndef SPNERF_BWD_NDIRECT
 #define SPNERF_BWD_NDIRECT 3
 #endif
@@ -152,6 +155,23 @@ __device__ __forceinline__ void bwd_columns(uint32_t taddr, int j0, const uint8_
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float g[8];
+#if SPNERF_BWD_HMUL
+        if (MODE != 2 && b < PRE) {      // factor ready in fp16: convert the accumulator pairwise and multiply as half2
+          const uint32_t* d2 = reinterpret_cast<const uint32_t*>(&cur.y[c]);
+          uint32_t r[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t a2 = pack2(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1]));
+            const __half2 pr = __hmul2(*reinterpret_cast<const __half2*>(&a2), *reinterpret_cast<const __half2*>(&d2[e]));
+            r[e] = *reinterpret_cast<const uint32_t*>(&pr);
+          }
+          const uint4 gp = make_uint4(r[0], r[1], r[2], r[3]);
+          if (keep) keep[2 * b + c] = gp;
+          else *reinterpret_cast<uint4*>(act + slab_off(dst_col0 + jb + c * 8, row)) = gp;
+          if (gsave) stg16(gsave + xsave_off(jb + c * 8, row), gp);
+          continue;
+        }
+#endif
         if (MODE != 2) {
           float y[8];
           unpack8(cur.y[c], y);
