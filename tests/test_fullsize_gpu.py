@@ -79,10 +79,10 @@ def _oracle_step_chunked(P, cfg, batch, z, z_unsort, chunk):
 
 
 def _compare(model, res, loss, grads, want, want_loss, want_grads):
-    assert float((res["rgb_coarse"] - want["rgb"]).abs().max()) <= TOL["rgb"]
-    assert float((res["depth_coarse"] - want["depth"]).abs().max()) <= TOL["depth"]
-    assert float((res["weights_coarse"] - want["weights"]).abs().max()) <= TOL["weights"]
-    assert float((res["sem_logits_coarse"] - want["sem_logits"]).abs().max()) <= TOL["sem_logits"]
+    assert float((res["rgb_coarse"].detach() - want["rgb"]).abs().max()) <= TOL["rgb"]
+    assert float((res["depth_coarse"].detach() - want["depth"]).abs().max()) <= TOL["depth"]
+    assert float((res["weights_coarse"].detach() - want["weights"]).abs().max()) <= TOL["weights"]
+    assert float((res["sem_logits_coarse"].detach() - want["sem_logits"]).abs().max()) <= TOL["sem_logits"]
     assert abs(float(loss) - float(want_loss)) <= 2e-3 * abs(float(want_loss))
     top = max(float(g.norm()) for g in want_grads.values())
     worst = {}
