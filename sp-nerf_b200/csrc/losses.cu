@@ -16,7 +16,7 @@ struct Workspace {
   unsigned int ticket;
   unsigned int n_labelled;
   unsigned int _pad[2];
-  float partial[kMaxBlocks][4];
+  float partial[kMaxBlocks][8];      // colour, depth, semantic, applied depth rays, labelled rays
 };
 
 __global__ void count_labels_kernel(const int64_t* __restrict__ labels, int64_t n, int n_sem, Workspace* ws) {
@@ -34,13 +34,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// COUNTED: the labelled rays were counted by count_labels_kernel (large batches).  Otherwise the kernel counts them
+// itself: the cross-entropy gradient is written without its 1 / n_labelled and the last block to finish divides it
+// (one launch less per training step; the same operations in the same order, so the same bits).
+constexpr int64_t kSelfCountMax = 1 << 18;      // gradient elements one block rescales in a few microseconds
+template <bool COUNTED>
 __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, Workspace* ws) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + wib, nw = (int64_t)gridDim.x * (kThreads / 32);
   const float inv_b = 1.f / (float)a.n_rays;
   const float lam_d = a.lambda_ds / 3.f;                                              // metrics.py:71
-  const float n_lab = a.sem_logits ? (float)ws->n_labelled : 1.f;
-  float s_col = 0.f, s_dep = 0.f, s_sem = 0.f, s_app = 0.f;   // lane 0 carries the warp's partial sums
+  float n_lab = (COUNTED && a.sem_logits) ? (float)ws->n_labelled : 1.f;
+  float s_col = 0.f, s_dep = 0.f, s_sem = 0.f, s_app = 0.f, s_lab = 0.f;   // lane 0 carries the warp's partial sums
   for (int64_t r = warp0; r < a.n_rays; r += nw) {
     if (a.rgb && lane < 3) {                                                           // metrics.py:31,38 MSELoss(mean)
       const float d = a.rgb[r * 3 + lane] - a.rgb_target[r * 3 + lane];
@@ -101,16 +106,17 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
       const float den = warp_sum(ex);
       if (lane < C) {
         const float sm = ex / den;
-        a.g_sem_logits[r * C + lane] = (lab == -100) ? 0.f : a.lambda_ss * (sm - (lane == lab ? 1.f : 0.f)) / n_lab;
+        const float t = a.lambda_ss * (sm - (lane == lab ? 1.f : 0.f));
+        a.g_sem_logits[r * C + lane] = (lab == -100) ? 0.f : (COUNTED ? t / n_lab : t);
       }
       const float picked = __shfl_sync(0xffffffffu, lg, lab == -100 ? 0 : (int)lab);
-      if (lane == 0 && lab != -100) s_sem += (logf(den) + m) - picked;
+      if (lane == 0 && lab != -100) { s_sem += (logf(den) + m) - picked; s_lab += 1.f; }
     }
   }
-  __shared__ float red[kThreads / 32][4];
-  if (lane == 0) { red[wib][0] = s_col; red[wib][1] = s_dep; red[wib][2] = s_sem; red[wib][3] = s_app; }
+  __shared__ float red[kThreads / 32][5];
+  if (lane == 0) { red[wib][0] = s_col; red[wib][1] = s_dep; red[wib][2] = s_sem; red[wib][3] = s_app; red[wib][4] = s_lab; }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 5) {
     float t = 0.f;
     for (int w = 0; w < kThreads / 32; ++w) t += red[w][threadIdx.x];
     ws->partial[blockIdx.x][threadIdx.x] = t;
@@ -120,19 +126,57 @@ __global__ void __launch_bounds__(kThreads) losses_kernel(const SpnerfLosses a, 
   __shared__ bool is_last;
   if (threadIdx.x == 0) is_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (is_last && threadIdx.x < 4) {
+  if (is_last) {      // every block's partial sums and gradient rows are visible (fence before its ticket)
+    // column k of the partials by warp k: lanes stride over the blocks, then a fixed shuffle tree (deterministic)
+    __shared__ float tot[5];
     __threadfence();
-    float t = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += ws->partial[b][threadIdx.x];
-    float v = t;
-    if (threadIdx.x == 0) v = t * inv_b / 3.f;
-    if (threadIdx.x == 1) v = lam_d * t * inv_b;
-    if (threadIdx.x == 2) v = a.lambda_ss * t / n_lab;
-    a.losses[threadIdx.x] = v;
-    a.losses[4 + threadIdx.x] = (threadIdx.x == 0 && a.sem_logits) ? n_lab : 0.f;
-    // the workspace cleans itself for the next call (no memsets on the stream): every block has read the label
-    // count and taken its ticket by now
-    if (threadIdx.x == 0) { ws->ticket = 0; ws->n_labelled = 0; }
+    if (wib < 5) {
+      float t = 0.f;
+      for (unsigned b = lane; b < gridDim.x; b += 32) t += ws->partial[b][wib];
+      t = warp_sum(t);
+      if (lane == 0) tot[wib] = t;
+    }
+    __syncthreads();
+    if (!COUNTED && a.sem_logits) {
+      n_lab = tot[4];      // exact: integers below 2^24
+      if (n_lab > 0.f) {
+        // one block touches the whole gradient array: 16-byte accesses, four independent ones in flight per thread
+        const int64_t n = a.n_rays * a.n_sem;
+        float* g = a.g_sem_logits;
+        const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+        if (vec) {
+          float4* g4 = reinterpret_cast<float4*>(g);
+          const int64_t n4 = n >> 2;
+          for (int64_t i0 = 0; i0 < n4; i0 += 4 * kThreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int64_t i = i0 + u * kThreads + threadIdx.x;
+              if (i < n4) v[u] = g4[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int64_t i = i0 + u * kThreads + threadIdx.x;
+              if (i < n4) g4[i] = make_float4(v[u].x / n_lab, v[u].y / n_lab, v[u].z / n_lab, v[u].w / n_lab);
+            }
+          }
+        } else {
+          for (int64_t i = threadIdx.x; i < n; i += kThreads) g[i] = g[i] / n_lab;
+        }
+      }
+    }
+    if (threadIdx.x < 4) {
+      const float t = tot[threadIdx.x];
+      float v = t;
+      if (threadIdx.x == 0) v = t * inv_b / 3.f;
+      if (threadIdx.x == 1) v = lam_d * t * inv_b;
+      if (threadIdx.x == 2) v = a.lambda_ss * t / n_lab;
+      a.losses[threadIdx.x] = v;
+      a.losses[4 + threadIdx.x] = (threadIdx.x == 0 && a.sem_logits) ? n_lab : 0.f;
+      // the workspace cleans itself for the next call (no memsets on the stream): every block has read the label
+      // count and taken its ticket by now
+      if (threadIdx.x == 0) { ws->ticket = 0; ws->n_labelled = 0; }
+    }
   }
 }
 
@@ -298,13 +342,15 @@ extern "C" int spnerf_losses(const SpnerfLosses* a, void* stream_) {
   if (a->sem_logits && (!a->labels || !a->g_sem_logits || a->n_sem < 1 || a->n_sem > 32)) return SPNERF_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Workspace* ws = static_cast<Workspace*>(a->workspace);
-  if (a->sem_logits) {
+  const bool counted = a->sem_logits && a->n_rays * (int64_t)a->n_sem > kSelfCountMax;
+  if (counted) {
     const int64_t nb = (a->n_rays + kThreads - 1) / kThreads;
     count_labels_kernel<<<(unsigned)(nb < 592 ? nb : 592), kThreads, 0, stream>>>(a->labels, a->n_rays, a->n_sem, ws);
   }
   const int64_t need = (a->n_rays + kThreads / 32 - 1) / (kThreads / 32);
-  const unsigned blocks = (unsigned)(need < kMaxBlocks ? need : kMaxBlocks);
-  losses_kernel<<<blocks, kThreads, 0, stream>>>(*a, ws);
+  const unsigned blocks = (unsigned)(need < 592 ? need : 592);      // 148 SMs x 4: a short serial tail in the last block
+  if (counted) losses_kernel<true><<<blocks, kThreads, 0, stream>>>(*a, ws);
+  else losses_kernel<false><<<blocks, kThreads, 0, stream>>>(*a, ws);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -397,7 +397,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
 }
 
 // dst[r * ld_row + c * ld_col] = inv_scale * sum over the job's slices of the workspace partials
-// One block row per scatter segment, 32 x 32 element tiles strided over blockIdx.y.  Reads are coalesced along
+// One block row per scatter segment, 32 x 128 (16-byte reads) or 32 x 32 element tiles strided over blockIdx.y.  Reads are coalesced along
 // the packed columns of the partial tiles; the parameter tensors are mostly the transpose (dW[m][i] from
 // D^T[i][m]: ld_row == 1), so the tile goes through shared memory and the writes are coalesced too.  The slice
 // offsets are staged once per block and the slice loop is unrolled for memory-level parallelism (the first
@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const Segment* __rest
                                                            const float* __restrict__ scale, int n_segs,
                                                            const FlushTable* __restrict__ flush) {
   __shared__ float tile[32][33];
+  __shared__ float tile4[32][129];      // the 16-byte path's tile (32 rows x 128 columns, padded)
   __shared__ long long offs[kMaxSlices];
   if ((int)blockIdx.x >= n_segs) {
     // the atomically accumulated slots: scratch -> gradient tensors, scratch cleared for the next step
@@ -427,12 +428,61 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const Segment* __rest
   const Segment sg = segs[blockIdx.x];
   const Job& job = jobs[sg.job];
   const int ns = job.nitems < kMaxSlices ? job.nitems : kMaxSlices;      // host guarantees nitems <= kMaxSlices
-  for (int s = threadIdx.x; s < ns; s += blockDim.x) offs[s] = items[job.item0 + s].ws_off;
-  __syncthreads();
+  int misaligned = 0;
+  for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+    offs[s] = items[job.item0 + s].ws_off;
+    misaligned |= (int)(offs[s] & 3);
+  }
+  const bool vec_ok = __syncthreads_or(misaligned) == 0;
   const float inv = 1.f / *scale;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                // 32 x 8 threads
-  const int tiles_c = (sg.ncols + 31) >> 5, tiles_r = (sg.nrows + 31) >> 5;
   const bool transposed = sg.ld_row == 1 && sg.ld_col != 1;              // dst contiguous along r
+  if (vec_ok && ((sg.ncols | sg.col0 | job.ncols) & 3) == 0) {
+    // 16-byte reads: a tile is 32 rows x 128 packed columns, a warp reads 512 contiguous bytes of one partial row
+    const int tiles_c = (sg.ncols + 127) >> 7, tiles_r = (sg.nrows + 31) >> 5;
+    for (int t = blockIdx.y; t < tiles_c * tiles_r; t += gridDim.y) {
+      const int r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 7;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + 4 * tx;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool in = r < sg.nrows && c < sg.ncols;
+        if (in) {
+          const float* base = ws + ((size_t)sg.rank * kWsRows + sg.row0 + r) * job.ncols + sg.col0 + c;
+          float4 a0 = acc, a1 = acc;
+          int s_ = 0;
+          for (; s_ + 2 <= ns; s_ += 2) {
+            const float4 u = *reinterpret_cast<const float4*>(base + offs[s_]);
+            const float4 v = *reinterpret_cast<const float4*>(base + offs[s_ + 1]);
+            a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+            a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+          }
+          if (s_ < ns) {
+            const float4 u = *reinterpret_cast<const float4*>(base + offs[s_]);
+            a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+          }
+          acc = make_float4((a0.x + a1.x) * inv, (a0.y + a1.y) * inv, (a0.z + a1.z) * inv, (a0.w + a1.w) * inv);
+        }
+        if (transposed) {
+          float* trow = &tile4[ty + 8 * k][4 * tx];
+          trow[0] = acc.x; trow[1] = acc.y; trow[2] = acc.z; trow[3] = acc.w;
+        } else if (in) {
+          float* d = sg.dst + (size_t)r * sg.ld_row + (size_t)c * sg.ld_col;
+          d[0] = acc.x; d[sg.ld_col] = acc.y; d[2 * (size_t)sg.ld_col] = acc.z; d[3 * (size_t)sg.ld_col] = acc.w;
+        }
+      }
+      if (transposed) {
+        __syncthreads();
+        for (int cc = ty; cc < 128; cc += 8) {
+          const int r = r0 + tx, c = c0 + cc;
+          if (r < sg.nrows && c < sg.ncols) sg.dst[(size_t)r + (size_t)c * sg.ld_col] = tile4[tx][cc];
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  const int tiles_c = (sg.ncols + 31) >> 5, tiles_r = (sg.nrows + 31) >> 5;
   for (int t = blockIdx.y; t < tiles_c * tiles_r; t += gridDim.y) {
     const int r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 5;
 #pragma unroll
