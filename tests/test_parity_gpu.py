@@ -220,7 +220,7 @@ def test_losses_against_oracle_and_edge_cases():
                                                                target_valid_depth=dev["valid_depth"],
                                                                target_std=dev["depth_std"])[0] \
             + metrics.SemanticLoss(0.5)(dres, dev["sems"])[0]
-        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+        assert abs(float(got.detach()) - float(want.detach())) <= 1e-5 * abs(float(want.detach()))
         keys = ("rgb_coarse", "depth_coarse", "sem_logits_coarse")
         gw = torch.autograd.grad(want, [res[k] for k in keys])
         gg = torch.autograd.grad(got, [dres[k] for k in keys])
@@ -234,6 +234,30 @@ def test_losses_against_oracle_and_edge_cases():
     # every label ignored -> NaN like torch.nn.CrossEntropyLoss
     l, _ = metrics.SemanticLoss(1.0)(dres, torch.full((b,), -100, device=DEV))
     assert bool(torch.isnan(l))
+
+
+@pytest.mark.parametrize("b,c", [(4099, 5), (65536, 4), (100003, 3)])
+def test_semantic_loss_both_counting_paths_against_torch(b, c):
+    """metrics.py:162-183 at sizes on either side of the kernel's self-counting limit (the last block normalises the
+    gradient for up to 2^18 elements, larger batches count the labelled rays in a launch of their own); -100 and
+    out-of-range labels are ignored, odd sizes exercise the scalar tail of the normalisation."""
+    gen = torch.Generator().manual_seed(b)
+    logits = (torch.randn(b, c, generator=gen) * 2).to(DEV)
+    labels = torch.randint(0, c, (b,), generator=gen)
+    labels[torch.rand(b, generator=gen) < 0.3] = -100
+    labels_dev = labels.to(DEV).clone()
+    labels_dev[::97] = c + 3                      # out of range: treated as ignored
+    ref_labels = labels_dev.clone()
+    ref_labels[::97] = -100
+    x = logits.clone().requires_grad_(True)
+    want = 0.7 * torch.nn.functional.cross_entropy(x.double(), ref_labels, ignore_index=-100)
+    gw, = torch.autograd.grad(want, x)
+    for _ in range(2):                            # twice: the workspace has to come back clean
+        out, _, _, g, _ = E.losses(b, sem_logits=logits, labels=labels_dev, lambda_ss=0.7)
+        torch.cuda.synchronize()
+        assert abs(float(out[2]) - float(want)) <= 2e-6 * abs(float(want))
+        assert float(out[4]) == float((ref_labels != -100).sum())
+        assert float((g - gw).abs().max()) <= 1e-6 * float(gw.abs().max())
 
 
 # ------------------------------------------------------------------------------------------------
