@@ -64,7 +64,7 @@ def fused_step(model, args, batch, lambda_ds=1.0, lambda_ss=1.0, use_all_depth=F
         target_depth=batch["depths"][:, 0], target_weight=batch["depths"][:, 1],
         target_std=batch["depth_std"], valid_depth=batch["valid_depth"], lambda_ds=lambda_ds,
         use_all_depth=use_all_depth, sem_logits=sem, labels=labels, lambda_ss=lambda_ss)
-    launches += 2 if sem is not None else 1
+    launches += 2 if (sem is not None and sem.numel() > (1 << 18)) else 1      # large batches count the labelled rays in a launch of their own
     t.mark("losses")
     g_out, g_sky_ray, absmax = E.composite_bwd(out, z, weights, trans, rgb_raw, eng.n_out, eng.col_sem, eng.n_sem,
                                                g_rgb=g_rgb, g_depth=g_depth, g_sem=g_sem, absmax=eng.absmax)
