@@ -51,19 +51,21 @@ __global__ void coarse_kernel(const float* __restrict__ rays, const float* __res
       if (atomicAdd(arrivals, 1u) == gridDim.x - 1) { *arrivals = 0u; rng_state[1] = step + 1; }
     }
   }
-  if (idx >= n_rays * n) return;
-  const int64_t r = idx / n;
-  const int i = (int)(idx - r * n);
-  const float near = rays[r * 11 + 6], far = rays[r * 11 + 7];
-  auto zlin = [&](int k) {                                        // rendering.py:133
-    const float t = t_tab[k];
-    return __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, t)), __fmul_rn(far, t));
-  };
-  const float zi = zlin(i);
-  const float lower = i == 0 ? zi : __fmul_rn(0.5f, __fadd_rn(zlin(i - 1), zi));        // :138-141
-  const float upper = i == n - 1 ? zi : __fmul_rn(0.5f, __fadd_rn(zi, zlin(i + 1)));
-  const float ui = rng_state ? philox_uniform(seed, step, (uint64_t)idx) : u[idx];
-  z[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), ui));                   // :143-144 (perturb = 1)
+  // grid-stride: a bounded grid keeps the arrival counter above to a few hundred atomics
+  for (int64_t k = idx; k < n_rays * n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = k / n;
+    const int i = (int)(k - r * n);
+    const float near = rays[r * 11 + 6], far = rays[r * 11 + 7];
+    auto zlin = [&](int q) {                                        // rendering.py:133
+      const float t = t_tab[q];
+      return __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, t)), __fmul_rn(far, t));
+    };
+    const float zi = zlin(i);
+    const float lower = i == 0 ? zi : __fmul_rn(0.5f, __fadd_rn(zlin(i - 1), zi));        // :138-141
+    const float upper = i == n - 1 ? zi : __fmul_rn(0.5f, __fadd_rn(zi, zlin(i + 1)));
+    const float ui = rng_state ? philox_uniform(seed, step, (uint64_t)k) : u[k];
+    z[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), ui));                     // :143-144 (perturb = 1)
+  }
 }
 
 // ---- torch.sum(row) for a contiguous fp32 row (ATen vectorized inner reduction, 8-float vectors) ----
@@ -201,7 +203,8 @@ extern "C" int spnerf_sample_coarse_rng(const float* rays, const float* t_table,
   if (!rays || !t_table || !rng_state || !z || n_samples < 2) return SPNERF_ERR_BAD_ARG;
   if (n_rays <= 0) return n_rays == 0 ? 0 : SPNERF_ERR_BAD_ARG;
   const int64_t total = n_rays * n_samples;
-  coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int64_t blocks = (total + 255) / 256;
+  coarse_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       rays, t_table, nullptr, reinterpret_cast<unsigned long long*>(rng_state), n_rays, n_samples, z);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
