@@ -8,6 +8,11 @@
 //   * streamed to the gradient save area, where the weight-gradient GEMMs (mlp_wgrad.cu) read it.
 // Same roles / handshake as mlp_fwd.cu; step order from build_backward() in mlp_pack.cu.
 #include <cstdlib>
+// store policy of the gradient tiles (mlp_roles.cuh stg16): default write-back (streaming stores measured +1.7 % here)
+#ifndef SPNERF_STG_MODE_BWD
+#define SPNERF_STG_MODE_BWD 0
+#endif
+#define SPNERF_STG_MODE SPNERF_STG_MODE_BWD
 #include "mlp_roles.cuh"
 
 using namespace roles;

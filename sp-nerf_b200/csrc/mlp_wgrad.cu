@@ -30,6 +30,12 @@
 using namespace sm100;
 using namespace net;
 
+// L2 eviction hints of the operand stream (0 = none, 1 = everything evict_first, 2 = A' evict_first / B' evict_last).
+// Alternating A/B on one box: 3.40 / 3.51 / 3.34 ms.
+#ifndef SPNERF_WGRAD_POLICY
+#define SPNERF_WGRAD_POLICY 2
+#endif
+
 namespace {
 
 constexpr int kChunkBytes = 2048;              // 8 features x 128 points, fp16
@@ -121,6 +127,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
 
   if (warp == 0) {
     // ---- producer: this CTA's rows of A' and its half of B', one stage per 128-point tile ----
+#if SPNERF_WGRAD_POLICY
+    // L2 hints of the operand stream: the input side (A', read by one pair) leaves first, the gradient side (B', read
+    // again by the pair that owns the layer's other rows) stays
+    const uint64_t pol_a = l2_policy_evict_first();
+    const uint64_t pol_b = SPNERF_WGRAD_POLICY == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
+#endif
     uint32_t stage = 0, phase = 0;
     for (int it = pair; it < p.n_items; it += npairs) {
       const Item item = p.items[it];
@@ -201,14 +213,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
             const Run run = job.a[rank][r];
             const uint8_t* src = (run.from_grads ? p.gsaves + k * p.grad_stride : p.saves + k * p.save_stride) +
                                  (size_t)run.unit * kSlabBytes + (size_t)run.chunk0 * kChunkBytes;
+#if SPNERF_WGRAD_POLICY
+            bulk_g2s_hint(dst + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes, &bar_full[stage], pol_a);
+#else
             bulk_g2s(dst + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes, &bar_full[stage]);
+#endif
           }
           for (int j = 0; j < job.nb; ++j) {
             const Run run = job.b[rank][j];
             const uint8_t* src = (run.from_grads ? p.gsaves + k * p.grad_stride : p.saves + k * p.save_stride) +
                                  (size_t)run.unit * kSlabBytes + (size_t)run.chunk0 * kChunkBytes;
+#if SPNERF_WGRAD_POLICY
+            bulk_g2s_hint(dst + kABytes + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes,
+                          &bar_full[stage], pol_b);
+#else
             bulk_g2s(dst + kABytes + run.dst_chunk * kChunkBytes, src, (uint32_t)run.nchunks * kChunkBytes,
                      &bar_full[stage]);
+#endif
           }
         }
         __syncwarp();
