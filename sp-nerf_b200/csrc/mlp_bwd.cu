@@ -8,9 +8,11 @@
 //   * streamed to the gradient save area, where the weight-gradient GEMMs (mlp_wgrad.cu) read it.
 // Same roles / handshake as mlp_fwd.cu; step order from build_backward() in mlp_pack.cu.
 #include <cstdlib>
-// store policy of the gradient tiles (mlp_roles.cuh stg16): default write-back (streaming stores measured +1.7 % here)
+// store policy of the gradient tiles (mlp_roles.cuh stg16): streaming, like the forward's saves.  Together with
+// L1::no_allocate loads of the saved outputs (below): 4.11 -> 4.00 ms in an alternating A/B (each alone -1.2 %), once
+// the weight ring was pinned in L2 (SPNERF_W_POLICY); before that neither moved the kernel.
 #ifndef SPNERF_STG_MODE_BWD
-#define SPNERF_STG_MODE_BWD 0
+#define SPNERF_STG_MODE_BWD 1
 #endif
 #define SPNERF_STG_MODE SPNERF_STG_MODE_BWD
 #include "mlp_roles.cuh"
@@ -32,11 +34,11 @@ struct BwdParams {
   int stagger, stagger_groups;      // start delay of cluster c: stagger * (c % groups) / groups cycles
 };
 
-// Streaming 16-byte load of a saved activation chunk.  SPNERF_LDG_MODE (experiment): 0 = ld.global.nc (allocates an L1
+// Streaming 16-byte load of a saved activation chunk.  SPNERF_LDG_MODE: 0 = ld.global.nc (allocates an L1
 // line per request; with 227 KB of shared memory carved out only ~28 KB of L1 are left to hold the requests in flight),
-// 1 = L1::no_allocate, 2 = .cs (evict-first), 3 = L1::no_allocate + L2::evict_first hint
+// 1 = L1::no_allocate (default), 2 = .cs (evict-first: +3 %), 3 = L1::no_allocate + L2::evict_first policy (-0.9 %)
 #ifndef SPNERF_LDG_MODE
-#define SPNERF_LDG_MODE 0
+#define SPNERF_LDG_MODE 1
 #endif
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
 #if SPNERF_LDG_MODE == 0
@@ -48,7 +50,10 @@ __device__ __forceinline__ uint4 ldg16(const uint8_t* p) {
 #elif SPNERF_LDG_MODE == 2
   asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
 #else
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
 #endif
   return v;
 #endif
