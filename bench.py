@@ -325,10 +325,13 @@ def run_ours(a):
     # ---- per-kernel durations (CUDA events on the launching stream), same steps ----
     kern = {}
     prof_steps = max(3, min(a.steps, 10))
-    for _ in range(prof_steps):
-        t = train_step.StepTimer(True)
+    timers = []
+    for _ in range(prof_steps):      # back to back like the timed region: the host stays ahead of the device, so an
+        t = train_step.StepTimer(True)      # interval between two events holds the kernels between them and no launch gap
         step(t)
-        torch.cuda.synchronize()
+        timers.append(t)
+    torch.cuda.synchronize()
+    for t in timers:
         for k, v in t.durations_ms().items():
             kern[k] = kern.get(k, 0.0) + v / prof_steps
     points = RAYS_PER_GPU * N_SAMPLES
