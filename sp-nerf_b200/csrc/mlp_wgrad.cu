@@ -45,7 +45,10 @@ constexpr int kStageBytes = kABytes + kBBytes; // 96 KB
 constexpr int kStages = 2;
 constexpr int kSmemW = kStages * kStageBytes + 256;
 constexpr int kWThreads = 256;                 // warp 0 producer, warp 1 issuer / relay, warps 4-7 epilogue
-constexpr int kTargetItemsPerPair = 8;
+#ifndef SPNERF_WGRAD_ITEMS
+#define SPNERF_WGRAD_ITEMS 8
+#endif
+constexpr int kTargetItemsPerPair = SPNERF_WGRAD_ITEMS;
 
 // `nchunks` consecutive chunks of one save region -> chunk slot `dst_chunk` of the A' or B' part
 struct Run { int16_t from_grads, unit, chunk0, nchunks, dst_chunk, _pad; };
