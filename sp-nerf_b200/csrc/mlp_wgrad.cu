@@ -30,8 +30,8 @@
 using namespace sm100;
 using namespace net;
 
-// L2 eviction hints of the operand stream (0 = none, 1 = everything evict_first, 2 = A' evict_first / B' evict_last).
-// Alternating A/B on one box: 3.40 / 3.51 / 3.34 ms.
+// L2 eviction hints of the operand stream (0 = none, 1 = everything evict_first, 2 = A' evict_first / B' evict_last,
+// 3 = A' normal / B' evict_last).  Alternating A/B on one box: 3.40 / 3.51 / 3.34 ms; 3 measures 1 % behind 2.
 #ifndef SPNERF_WGRAD_POLICY
 #define SPNERF_WGRAD_POLICY 2
 #endif
@@ -133,8 +133,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1) wgrad_
 #if SPNERF_WGRAD_POLICY
     // L2 hints of the operand stream: the input side (A', read by one pair) leaves first, the gradient side (B', read
     // again by the pair that owns the layer's other rows) stays
-    const uint64_t pol_a = l2_policy_evict_first();
-    const uint64_t pol_b = SPNERF_WGRAD_POLICY == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
+    const uint64_t pol_a = SPNERF_WGRAD_POLICY == 3 ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const uint64_t pol_b = SPNERF_WGRAD_POLICY >= 2 ? l2_policy_evict_last() : l2_policy_evict_first();
 #endif
     uint32_t stage = 0, phase = 0;
     for (int it = pair; it < p.n_items; it += npairs) {
