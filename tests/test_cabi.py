@@ -97,7 +97,7 @@ def _step_table(cfg, backward):
     tab = (ctypes.c_int32 * (8 * 384))()
     n = lib.spnerf_debug_step_table(ctypes.byref(cfg), backward, tab, 384)
     assert 0 < n <= 384
-    keys = ("n", "col", "a_slab", "ksteps", "first", "last", "lane", "early")
+    keys = ("n", "col", "a_slab", "ksteps", "first", "last", "lane", "half")
     return [dict(zip(keys, tab[8 * i:8 * i + 8])) for i in range(n)]
 
 
@@ -133,3 +133,33 @@ def test_step_table_keeps_accumulation_order_deterministic(kw, backward):
             assert {t["lane"] for t in phase} <= {0, 1}
             phase = []
     assert not phase
+
+
+@pytest.mark.parametrize("kw", [dict(mapping=0, sem=1), dict(mapping=1, sem=1, beta=1), dict(feat=256, mapping=1, sem=1)])
+def test_split_phases_of_the_backward_step_table(kw):
+    """Split phases (csrc/net_plan.h, SPNERF_SPLIT_BWD): a full-width phase is issued as quarter-width chunks, the
+    first accumulator half first.  Exactly one step of such a phase carries the `half` mark (both issuers commit to the
+    half-done barrier when they pass it, so a second mark would over-arrive); everything up to the mark accumulates
+    into columns below the half, everything after it at or above, and each issuer owns one chunk on either side."""
+    base = dict(feat=512, layers=8, skip_layer=4, mapping=0, sem=1, num_sem_classes=3, emb_dim=3, beta=0, t_dim=4)
+    base.update(kw)
+    steps = _step_table(_cabi.NetConfig(**base), 1)
+    half_cols = base["feat"] // 2
+    phase, n_split = [], 0
+    for s in steps:
+        phase.append(s)
+        if not s["last"]:
+            continue
+        marks = [i for i, t in enumerate(phase) if t["half"]]
+        assert len(marks) <= 1, phase
+        if marks:
+            n_split += 1
+            before, after = phase[:marks[0] + 1], phase[marks[0] + 1:]
+            assert after, "the mark cannot be the last step of a phase"
+            assert all(t["col"] + t["n"] <= half_cols for t in before), before
+            assert all(t["col"] >= half_cols for t in after), after
+            for part in (before, after):
+                assert {t["lane"] for t in part} == {0, 1}
+                assert len({(t["col"], t["n"]) for t in part}) == 2          # one chunk per issuer
+        phase = []
+    assert n_split >= 8      # the eight trunk layers at least
