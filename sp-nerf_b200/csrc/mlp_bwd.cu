@@ -98,6 +98,9 @@ constexpr int kYWin = SPNERF_YWIN;
 #ifndef SPNERF_BWD_HMUL
 #define SPNERF_BWD_HMUL 1
 #endif
+#ifndef SPNERF_BWD_EARLY_STS
+#define SPNERF_BWD_EARLY_STS 1
+#endif
 #ifndef SPNERF_BWD_NDIRECT
 #define SPNERF_BWD_NDIRECT 3
 #endif
@@ -488,10 +491,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_bwd
           if (L > 0) bwd_columns<RELU ? 4 : 0, NBC, PC>(taddr, cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win, NBC, keep);
           else       bwd_columns<RELU ? 4 : 1, NBC, PC>(taddr, cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win, NBC, keep);
           ywin_load<NBC>(win, xs(p.sm.y[L]), xs(p.sm.x[L]), H + cg * CW, row);
-          if (!RELU) { if (L > 0) ywin_to_dact<0, NBC>(win); else ywin_to_dact<1, NBC>(win); }
-          sync.begin();
+#if SPNERF_BWD_EARLY_STS
+          // the first half's gradients go to shared memory as soon as the rest of the phase no longer reads those slabs
+          // (half of the shared-memory stores leave the exposed epilogue, which is bound by the SM's store path)
+          sync.wait_first_half_free();
 #pragma unroll
           for (int q = 0; q < 2 * NBC; ++q) *reinterpret_cast<uint4*>(act + slab_off(cg * CW + 8 * q, row)) = keep[q];
+#endif
+          if (!RELU) { if (L > 0) ywin_to_dact<0, NBC>(win); else ywin_to_dact<1, NBC>(win); }
+          sync.begin();
+#if !SPNERF_BWD_EARLY_STS
+#pragma unroll
+          for (int q = 0; q < 2 * NBC; ++q) *reinterpret_cast<uint4*>(act + slab_off(cg * CW + 8 * q, row)) = keep[q];
+#endif
           if (L > 0) bwd_columns<RELU ? 4 : 0, NBC, PC>(taddr, H + cg * CW, xs(p.sm.y[L]), xs(p.sm.x[L]), act, 0, row, gdirect, win);
           else       bwd_columns<RELU ? 4 : 1, NBC, PC>(taddr, H + cg * CW, xs(p.sm.y[0]), xs(p.sm.x[0]), act, 0, row, gdirect, win);
           sync.end(more);

@@ -269,7 +269,9 @@ struct Builder {
   // split = true (four chunks of a quarter of the accumulator each): the first two chunks -- one per issuer, interleaved
   // -- make up the first accumulator half, the last two the second; the last item of the first half carries the `half`
   // mark.  Otherwise every chunk belongs to one issuer and the two lanes are interleaved over the whole phase.
-  void end_phase(bool split = false) {
+  // early_free_slabs > 0 (split phases of the backward trunk): mark the item after which nothing reads A slabs
+  // 0 .. early_free_slabs-1 any more (MmaStep::half bit 1)
+  void end_phase(bool split = false, int early_free_slabs = 0) {
     const size_t e = steps.size();
     chunk_begin.push_back(e);
     split = split && chunk_begin.size() == 5;      // the caller built four chunks because its direction splits
@@ -289,6 +291,14 @@ struct Builder {
           if (b < ls[1].size()) out.push_back(ls[1][b++]);
         }
         if (part == 0) out.back().half = 1;
+      }
+      if (early_free_slabs > 0) {
+        size_t p1 = 0;
+        while (!(out[p1].half & 1)) ++p1;
+        size_t q = p1 + 1;                                   // first item of the second half
+        for (size_t k = out.size(); k-- > p1 + 1;)
+          if (out[k].a_slab != kAuxSlab && (int)out[k].a_slab < early_free_slabs) { q = k; break; }
+        out[q].half |= 2;
       }
       for (size_t k = 0; k < out.size(); ++k) steps[phase_begin + k] = out[k];
       steps[e - 1].last = 1;
@@ -741,7 +751,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
     b.chunk(nullptr, 0, 0, g * PW, PW, g * PW, v, true, true);
     if (c.sem && 256 / PW > 1 && SH % (256 / PW) == 0) b.merge_last_chunk(256 / PW);   // the sigma step stays on its own
   }
-  b.end_phase(true);
+  b.end_phase(true, kSplitBwd ? SH : 0);      // the eight phases whose epilogue is the trunk loop of mlp_bwd.cu
   // trunk, layers 7..1; the label-embedding columns of the skip layer and of layer 0 get their own
   // 16-wide mini phases (only when the embedding exists)
   for (int L = 7; L >= 1; --L) {
@@ -756,7 +766,7 @@ void build_backward(const SpnerfNetConfig& c, const float* const* P, std::vector
       b.chunk(P[SPNERF_P_FC_W0 + 2 * L], F, cols, g * PW, PW, g * PW, ks(0, SF), true);
       if (256 / PW > 1) b.merge_last_chunk(256 / PW);
     }
-    b.end_phase(true);
+    b.end_phase(true, kSplitBwd ? SH : 0);
   }
   if (c.sem) {
     b.chunk(P[SPNERF_P_FC_W0], F, d.in_dim, base, 16, 0, ks(0, SF), true);

@@ -50,6 +50,7 @@ struct Smem {
   uint64_t* bar_mma;     // MMA phase retired -> epilogue (both CTAs)
   uint64_t* bar_epi;     // rank 0 only: both epilogues done -> MMA
   uint64_t* bar_par;     // parameter region landed (once)
+  uint64_t* bar_free;    // split phases: the A slabs of the first half's columns are no longer read (both issuers) -> epilogue
   uint64_t* bar_half;    // split phases: the first half of the accumulator retired (both issuers) -> epilogue (both CTAs)
   uint32_t* tmem_slot;
   uint32_t rank;
@@ -62,7 +63,7 @@ __device__ __forceinline__ Smem carve(uint8_t* smem) {
   s.wst = smem + kOffWst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   s.bar_full = bars; s.bar_empty = bars + 4;
-  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14; s.bar_half = bars + 15;
+  s.bar_mma = bars + 12; s.bar_epi = bars + 13; s.bar_par = bars + 14; s.bar_half = bars + 15; s.bar_free = bars + 17;      // (bars + 16 holds the TMEM base address)
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   s.rank = cluster_ctarank();
   return s;
@@ -79,7 +80,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, uint8_t* smem, const fl
       mbar_init(&s.bar_full[i], (s.rank == 0 && !(debug & 8)) ? 2 : 1); mbar_init(&s.bar_empty[i], 1);
       mbar_init(&s.bar_full[8 + i], (s.rank == 0 && !(debug & 8)) ? 2 : 1);
     }
-    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1); mbar_init(s.bar_half, 2);
+    mbar_init(s.bar_mma, 2); mbar_init(s.bar_epi, 2); mbar_init(s.bar_par, 1); mbar_init(s.bar_half, 2); mbar_init(s.bar_free, 2);
     fence_mbar_init();
     mbar_expect_tx(s.bar_par, kSmallWFloats * 4);
     bulk_g2s(smem + kOffRgb2, smallw, 3072 * 4, s.bar_par);              // rgb2 | sem2
@@ -219,7 +220,10 @@ __device__ __forceinline__ void mma_loop(const Smem& s, uint32_t tmem_base, cons
           if (plog && it == 2 && i <= 256) prof[1280 + i - 1] = clock64();       // commit issued
         }
         // split phases: the first half of the accumulator is complete once both issuers' MMAs up to here have retired
-        if (half && elect_one()) umma2_commit(s.bar_half);
+        if ((half & 1u) && elect_one()) umma2_commit(s.bar_half);
+        __syncwarp();
+        // ... and from here on nothing reads the A slabs under the first half's columns
+        if ((half & 2u) && elect_one()) umma2_commit(s.bar_free);
         __syncwarp();
         if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
       } while (!last);
@@ -239,7 +243,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 struct EpiSync {
   const Smem& s;
   bool issuer;
-  uint32_t mma_par = 0, half_par = 0;
+  uint32_t mma_par = 0, half_par = 0, free_par = 0;
   long long* prof;        // optional phase clock log (block 0 only)
   int prof_i = 0;
   uint32_t epi_remote;    // rank 1: the issuer CTA's bar_epi
@@ -268,6 +272,14 @@ struct EpiSync {
     epi_bar_sync();
     tc_fence_after();
     stamp();
+  }
+  // split phases of the backward trunk: the remaining MMAs of the phase no longer read the A slabs under the first
+  // half's columns (MmaStep::half bit 1), so that half's results may go to shared memory now instead of in the exposed
+  // epilogue after the phase.  Waited on exactly once per marked phase (one-bit phase parity).
+  __device__ __forceinline__ void wait_first_half_free() {
+    if (issuer) mbar_wait(s.bar_free, free_par, 33);
+    free_par ^= 1;
+    epi_bar_sync();
   }
   // publish shared-memory writes to the async proxy, order TMEM reads, release the MMA warp
   __device__ __forceinline__ void end(bool signal) {

@@ -52,8 +52,10 @@ struct __align__(16) MmaStep {
   uint8_t last;       // 1: last item of a phase (in ring order) -> both issuers signal the epilogue
   uint16_t bytes16;   // item size in 16-byte units
   uint8_t lane;       // which of the two MMA issuer warps owns this item (its accumulation chunk)
-  uint8_t half;       // 1: last item of the first accumulator half in a split phase: both issuers signal bar_half when they
-                      //    pass it (the epilogue starts on that half while the tensor pipe works on the second one)
+  uint8_t half;       // bit 0: last item of the first accumulator half in a split phase: both issuers signal bar_half when
+                      //    they pass it (the epilogue starts on that half while the tensor pipe works on the second one)
+                      // bit 1: no later item of the phase reads the A slabs of the first half's columns: both issuers
+                      //    signal bar_free, and the epilogue may write that half's new activations in place
 };
 
 // Split phases (SPNERF_SPLIT, default on).  A phase that fills the whole accumulator (trunk layers, feats_from_xyz and

@@ -145,13 +145,19 @@ def test_split_phases_of_the_backward_step_table(kw):
     base.update(kw)
     steps = _step_table(_cabi.NetConfig(**base), 1)
     half_cols = base["feat"] // 2
-    phase, n_split = [], 0
+    phase, n_split, n_free = [], 0, 0
     for s in steps:
         phase.append(s)
         if not s["last"]:
             continue
-        marks = [i for i, t in enumerate(phase) if t["half"]]
-        assert len(marks) <= 1, phase
+        marks = [i for i, t in enumerate(phase) if t["half"] & 1]
+        frees = [i for i, t in enumerate(phase) if t["half"] & 2]
+        n_free += len(frees)
+        assert len(marks) <= 1 and len(frees) <= 1, phase
+        if frees:
+            # nothing after the mark reads the A slabs under the first half's columns, and the mark sits in the second half
+            assert marks and frees[0] > marks[0]
+            assert all(t["a_slab"] >= half_cols // 64 for t in phase[frees[0] + 1:]), phase
         if marks:
             n_split += 1
             before, after = phase[:marks[0] + 1], phase[marks[0] + 1:]
@@ -162,4 +168,4 @@ def test_split_phases_of_the_backward_step_table(kw):
                 assert {t["lane"] for t in part} == {0, 1}
                 assert len({(t["col"], t["n"]) for t in part}) == 2          # one chunk per issuer
         phase = []
-    assert n_split >= 8      # the eight trunk layers at least
+    assert n_split >= 8 and n_free == 8      # the eight trunk phases carry the early-free mark
